@@ -1,0 +1,259 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the REAL reference (nftqcd/fthmc at /root/reference).
+
+Runs only in the build container (the reference cannot travel to the GPU box).  The reference is
+imported unmodified:
+  * hmc_2dU1.py                       (plain HMC, LeakyReLU flow copy)
+  * ipynb/field_transformation.py     (flow library, copy A)
+  * ipynb/ft_hmc.py lines 1-514       (everything before its module-level experiment block)
+  * fthmc/utils/layers.py             (copy B: [-pi,pi) convention)
+Momenta and Metropolis uniforms are the reference's own torch-RNG draws: they are recovered by
+replaying the generator from the same seed in the same order (randn_like, then rand([],float64)).
+
+usage:  python tests/golden/make_golden.py [--ref /root/reference]
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference(ref):
+    sys.path.insert(0, ref)
+    sys.path.insert(0, os.path.join(ref, "ipynb"))
+    import hmc_2dU1 as plain                      # noqa
+    import field_transformation as ftlib          # noqa
+    src = open(os.path.join(ref, "ipynb", "ft_hmc.py")).read().split("\n")
+    cut = next(i for i, l in enumerate(src) if l.startswith("# set param"))
+    fthmc_mod = types.ModuleType("ref_ft_hmc")
+    fthmc_mod.__file__ = os.path.join(ref, "ipynb", "ft_hmc.py")
+    exec(compile("\n".join(src[:cut]), fthmc_mod.__file__, "exec"), fthmc_mod.__dict__)
+    torch.set_default_dtype(torch.float64)
+    return plain, ftlib, fthmc_mod
+
+
+def flat_weights(flow):
+    rows = []
+    for layer in flow:
+        convs = [m for m in layer.plaq_coupling.net if hasattr(m, "weight")]
+        rows.append(np.concatenate([np.concatenate([c.weight.detach().numpy().ravel(),
+                                                    c.bias.detach().numpy().ravel()]) for c in convs]))
+    return np.stack(rows)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def replay_p_u(seed, shape):
+    st = torch.get_rng_state()
+    torch.manual_seed(seed)
+    p = torch.randn(shape, dtype=torch.float64)
+    u = torch.rand([], dtype=torch.float64)
+    torch.set_rng_state(st)
+    return p, u
+
+
+def gen_plain(plain, out):
+    """BASELINE config 1: plain HMC L=8 beta=2 tau=1 nstep=10 (hmc_2dU1.py on CPU, fp64)."""
+    P = plain.Param(beta=2.0, lat=(8, 8), tau=1.0, nstep=10)
+    torch.manual_seed(1331)
+    x = torch.empty((2, 8, 8)).uniform_(-np.pi, np.pi)
+    rec = dict(beta=2.0, dt=P.dt, nstep=10, x0=x.numpy().copy())
+    rec["action"] = float(plain.action(P, x))
+    rec["force"] = plain.force(P, x.clone()).numpy().copy()
+    rec["topo"] = float(plain.topocharge(x))
+    big = x * 7.3 + 1.1
+    rec["reg_in"] = big.numpy().copy()
+    rec["reg_out"] = plain.regularize(big).numpy().copy()
+    p = torch.randn_like(x)
+    lx, lp = plain.leapfrog(P, x.clone(), p)
+    rec["lf_p"], rec["lf_x_out"], rec["lf_p_out"] = p.numpy().copy(), lx.numpy().copy(), lp.numpy().copy()
+    # free-running chain of 40 trajectories; every trajectory's input, p, u and outputs are stored
+    xs, ps, us, dHs, accs, outs, topos, plaqs = [], [], [], [], [], [], [], []
+    cur = x.clone()
+    for n in range(40):
+        seed = 5000 + n
+        p, u = replay_p_u(seed, cur.shape)
+        torch.manual_seed(seed)
+        dH, e, acc, new = plain.hmc(P, cur.clone())
+        xs.append(cur.numpy().copy()); ps.append(p.numpy().copy()); us.append(float(u))
+        dHs.append(float(dH)); accs.append(bool(acc)); outs.append(new.numpy().copy())
+        topos.append(float(plain.topocharge(new)))
+        plaqs.append(float(plain.action(P, new) / (-P.beta * P.volume)))
+        cur = new.detach().clone()
+    rec.update(traj_x=np.stack(xs), traj_p=np.stack(ps), traj_u=np.array(us), traj_dH=np.array(dHs),
+               traj_acc=np.array(accs), traj_out=np.stack(outs), traj_topo=np.array(topos),
+               traj_plaq=np.array(plaqs))
+    # cold start known answers (hmc_2dU1.py:692-693)
+    z = torch.zeros((2, 8, 8))
+    rec["cold_plaq"] = float(plain.action(P, z) / (-P.beta * P.volume))
+    rec["cold_topo"] = float(plain.topocharge(z))
+    np.savez_compressed(os.path.join(out, "plain_L8.npz"), **rec)
+    print("plain_L8: acc rate", np.mean(accs), "dH", dHs[:4])
+
+
+def gen_flow_case(ftlib, ref, name, out, *, L, beta, n_layers, B, nstep, ntraj, scale=1.0, seed_w=3647,
+                  tau=1.0, hot=True):
+    torch.manual_seed(seed_w)
+    flow = ftlib.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=n_layers, n_mixture_comps=2,
+                                      hidden_sizes=[8, 8], kernel_size=3)
+    flow.eval()
+    if scale != 1.0:
+        with torch.no_grad():
+            for prm in flow.parameters():
+                prm.mul_(scale)
+    for prm in flow.parameters():
+        prm.requires_grad_(False)
+    P = ref.Param(beta=beta, lat=(L, L), tau=tau, nstep=nstep)
+    torch.manual_seed(1331)
+    if hot:
+        x = torch.empty((B, 2, L, L)).uniform_(-np.pi, np.pi)
+    else:
+        x = 0.3 * torch.randn((B, 2, L, L))
+    rec = dict(L=L, beta=beta, dt=P.dt, nstep=nstep, n_layers=n_layers, weights=flat_weights(flow),
+               activation="silu", convention=0, x=x.numpy().copy())
+    # per-layer forward of layer 0..: outputs and logJ
+    cur = x.clone()
+    lay_out, lay_logJ = [], []
+    for layer in flow:
+        cur, lj = layer.forward(cur)
+        lay_out.append(cur.numpy().copy()); lay_logJ.append(lj.numpy().copy())
+    rec["layer_out"] = np.stack(lay_out[:4])          # first 4 layers in full
+    rec["layer_logJ"] = np.stack(lay_logJ)            # all layers
+    y = ref.ft_flow(flow, x.clone())
+    rec["flow_fwd"] = y.numpy().copy()
+    rec["ft_action"] = ref.ft_action(P, flow, x.clone()).detach().numpy().copy()
+    rec["ft_force"] = ref.ft_force(P, flow, x.clone()).numpy().copy()
+    # reverse of single chains (the bisection stop test is tensor-global, so the reference path is B=1)
+    inv, inv_logJ0 = [], []
+    for b in range(B):
+        xi = quiet(ref.ft_flow_inv, flow, y[b:b + 1].clone())
+        inv.append(xi.numpy()[0].copy())
+        _, lj = flow[-1].reverse(y[b:b + 1].clone())
+        inv_logJ0.append(float(lj))
+    rec["flow_inv_of_fwd"] = np.stack(inv)
+    rec["last_layer_reverse_logJ"] = np.array(inv_logJ0)
+    # teacher-forced + free-running ft_hmc on chain 0
+    cur = wrap(y[0:1].clone())
+    xs, ps, us, dHs, accs, outs, topos, plaqs = [], [], [], [], [], [], [], []
+    for n in range(ntraj):
+        seed = 7000 + n
+        p, u = replay_p_u(seed, cur.shape)
+        torch.manual_seed(seed)
+        dH, e, acc, new = quiet(ref.ft_hmc, P, flow, cur.clone())
+        xs.append(cur.numpy()[0].copy()); ps.append(p.numpy()[0].copy()); us.append(float(u))
+        dHs.append(dH); accs.append(bool(acc)); outs.append(new.numpy()[0].copy())
+        topos.append(float(ref.topocharge(new[0])))
+        plaqs.append(float(ref.action(P, new[0]) / (-P.beta * P.volume)))
+        cur = new.detach().clone()
+    rec.update(traj_x=np.stack(xs), traj_p=np.stack(ps), traj_u=np.array(us), traj_dH=np.array(dHs),
+               traj_acc=np.array(accs), traj_out=np.stack(outs), traj_topo=np.array(topos),
+               traj_plaq=np.array(plaqs))
+    np.savez_compressed(os.path.join(out, name + ".npz"), **rec)
+    print(name, "acc", accs, "dH", [f"{d:.4g}" for d in dHs])
+
+
+def wrap(x):
+    return torch.remainder(x + np.pi, 2 * np.pi) - np.pi
+
+
+def gen_leaky(plain, out):
+    """hmc_2dU1.py's embedded flow copy (LeakyReLU, :260) and its round-trip self check (:719-745)."""
+    L = 8
+    torch.manual_seed(99)
+    flow = plain.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=16, n_mixture_comps=2,
+                                      hidden_sizes=[8, 8], kernel_size=3)
+    flow.eval()
+    with torch.no_grad():
+        for prm in flow.parameters():
+            prm.mul_(2.0)
+    torch.manual_seed(1331)
+    x = torch.empty((2, 2, L, L)).uniform_(-np.pi, np.pi)
+    cur, lj_tot = x.clone(), 0.0
+    for layer in flow:
+        cur, lj = layer.forward(cur)
+        lj_tot = lj_tot + lj
+    rec = dict(L=L, n_layers=16, weights=flat_weights(flow), activation="leaky_relu", convention=0,
+               x=x.numpy().copy(), flow_fwd=cur.detach().numpy().copy(), logJ=lj_tot.detach().numpy().copy())
+    invs = []
+    for b in range(2):
+        c = cur[b:b + 1].detach().clone()
+        for layer in reversed(flow):
+            c, _ = layer.reverse(c)
+        invs.append(c.detach().numpy()[0].copy())
+    rec["flow_inv_of_fwd"] = np.stack(invs)
+    np.savez_compressed(os.path.join(out, "leaky_L8.npz"), **rec)
+    print("leaky_L8 done; roundtrip err", np.abs(wrap(torch.from_numpy(np.stack(invs)) - x)).max().item())
+
+
+def gen_copyB(refroot, out):
+    """Copy B (fthmc/utils/layers.py): torch_mod in [-pi,pi), bisection on [-pi,pi]."""
+    st = io.StringIO()
+    with contextlib.redirect_stdout(st), contextlib.redirect_stderr(st):
+        import fthmc.utils.layers as LB
+    torch.set_default_dtype(torch.float64)
+    torch.set_default_tensor_type(torch.DoubleTensor)
+    L = 8
+    torch.manual_seed(4242)
+    try:
+        flow = LB.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=8, n_mixture_comps=2,
+                                       hidden_sizes=[8, 8], kernel_size=3)
+    except TypeError:
+        flow = LB.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=8, n_mixture_comps=2,
+                                       hidden_sizes=[8, 8], kernel_size=3, activation_fn="silu")
+    flow.eval()
+    flow = flow.double()
+    for layer in flow:
+        layer.active_mask = layer.active_mask.double()
+    with torch.no_grad():
+        for prm in flow.parameters():
+            prm.mul_(2.0)
+    torch.manual_seed(1331)
+    x = torch.empty((2, 2, L, L)).uniform_(-np.pi, np.pi)
+    cur, lj_tot = x.clone(), 0.0
+    for layer in flow:
+        cur, lj = layer.forward(cur)
+        lj_tot = lj_tot + lj
+    rec = dict(L=L, n_layers=8, weights=flat_weights(flow), activation="silu", convention=1,
+               x=x.numpy().copy(), flow_fwd=cur.detach().numpy().copy(), logJ=lj_tot.detach().numpy().copy())
+    invs = []
+    for b in range(2):
+        c = cur[b:b + 1].detach().clone()
+        for layer in reversed(flow):
+            c, _ = layer.reverse(c)
+        invs.append(c.detach().numpy()[0].copy())
+    rec["flow_inv_of_fwd"] = np.stack(invs)
+    np.savez_compressed(os.path.join(out, "copyB_L8.npz"), **rec)
+    print("copyB_L8 done; roundtrip err", np.abs(wrap(torch.from_numpy(np.stack(invs)) - x)).max().item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=HERE)
+    a = ap.parse_args()
+    plain, ftlib, ref = load_reference(a.ref)
+    gen_plain(plain, a.out)
+    gen_flow_case(ftlib, ref, "ft_L8_n8", a.out, L=8, beta=2.0, n_layers=8, B=3, nstep=6, ntraj=6, scale=2.0)
+    gen_flow_case(ftlib, ref, "ft_L16_b6", a.out, L=16, beta=6.0, n_layers=24, B=2, nstep=10, ntraj=3)
+    gen_flow_case(ftlib, ref, "ft_L32_b4", a.out, L=32, beta=4.0, n_layers=24, B=1, nstep=10, ntraj=2)
+    gen_flow_case(ftlib, ref, "ft_L32_b4_n40", a.out, L=32, beta=4.0, n_layers=24, B=1, nstep=40, ntraj=1,
+                  tau=1.0)
+    gen_leaky(plain, a.out)
+    try:
+        gen_copyB(a.ref, a.out)
+    except Exception as e:  # copy B is optional (it drags in the package's logger/config)
+        print("copyB generation failed:", repr(e))
+
+
+if __name__ == "__main__":
+    main()
