@@ -1,0 +1,932 @@
+// chain_engine.cuh -- one Markov chain's FT-HMC state machine, resident in shared memory.
+//
+// One CTA owns one chain.  The chain's link field, the gradient (force) field and every CNN
+// activation plane live in shared memory for the whole call; HBM/L2 is touched only to load/store
+// the field at the boundaries and for a small per-CTA workspace (momenta, saved active links).
+//
+// The code is written as block-cooperative *phases*: each phase is a strided loop over "tasks"
+// (task = one row of one 4-column stripe group) followed by a barrier.  Every phase is correct
+// for ANY thread count, including 1: that is what lets tests/emul compile this same header with
+// g++ and run it serially on the CPU (test infrastructure only; the product is the CUDA build).
+//
+// Reference semantics (paths relative to nftqcd/fthmc):
+//   coupling layer forward/reverse  ipynb/field_transformation.py:152-174, 288-338
+//   masks                           ipynb/field_transformation.py:175-248
+//   tan mixture + logJ + bisection  ipynb/field_transformation.py:249-285
+//   ft_flow/ft_flow_inv/ft_action/ft_force   ipynb/ft_hmc.py:220-249
+//   ft_leapfrog/ft_hmc              ipynb/ft_hmc.py:394-435
+//   action/force/regularize/topocharge/leapfrog/hmc   hmc_2dU1.py:100-155
+// The force of the flowed action, which the reference takes from torch.autograd, is the
+// hand-derived adjoint of SURVEY.md section 8a row 11 (validated against autograd by
+// oracle.ft_force_adjoint in tests/test_oracle_golden.py).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FT_HD __host__ __device__ __forceinline__
+#define FT_PHASE __host__ __device__ __noinline__
+#else
+#define FT_HD inline
+#define FT_PHASE
+#endif
+
+namespace fthmc {
+
+// ---- network shape (every reference config: hidden_sizes=[8,8], n_mixture_comps=2, kernel 3) ----
+constexpr int NH = 8;          // hidden channels of both hidden layers
+constexpr int NK = 2;          // mixture components (s_1..s_K), +1 channel for t
+constexpr int NOUT = NK + 1;
+
+// ---- packed per-layer weight block (doubles), canonical orientation: a = offset along the
+//      stripe direction ("row"), b = offset across stripes ("column") ----
+constexpr int OFF_W1F = 0;      // [b][a][ci=2][o=8]   conv1 forward
+constexpr int OFF_B1  = 144;    // [q=4][o=8]          conv1 bias incl. the constant (cos,sin)=(1,0) taps, per column class
+constexpr int OFF_W2F = 176;    // [ci=8][a][b][o=8]   conv2 forward
+constexpr int OFF_B2  = 752;    // [o=8]
+constexpr int OFF_W3F = 760;    // [ci=8][a][b][o=4]   conv3 forward (o padded 3->4)
+constexpr int OFF_B3  = 1048;   // [o=4]
+constexpr int OFF_W3T = 1052;   // [o=3][a][k=3][ci=8] conv3 transposed (input gradient)
+constexpr int OFF_W2T = 1268;   // [o=8][a][b][ci=8]   conv2 transposed
+constexpr int OFF_W1T = 1844;   // [o=8][a][b][ci=2]   conv1 transposed
+constexpr int PACK_DOUBLES = 1988;
+
+constexpr double PI_D = 3.141592653589793;       // == math.pi == np.pi
+constexpr double TWO_PI_D = 6.283185307179586;   // == 2*math.pi (exact doubling)
+
+enum Activation { ACT_SILU = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+
+// torch.remainder(x, 2pi) (fmod, then +2pi if negative); convention 1: remainder(x+pi,2pi)-pi.
+FT_HD double mod_2pi(double x, int conv) {
+    if (conv == 0) {
+        double r = fmod(x, TWO_PI_D);
+        if (r != 0.0 && r < 0.0) r += TWO_PI_D;
+        return r;
+    }
+    double r = fmod(x + PI_D, TWO_PI_D);
+    if (r != 0.0 && r < 0.0) r += TWO_PI_D;
+    return r - PI_D;
+}
+
+// hmc_2dU1.py:127-129
+FT_HD double regularize1(double f) {
+    double g = (f - PI_D) / TWO_PI_D;
+    return TWO_PI_D * (g - floor(g) - 0.5);
+}
+
+FT_HD void act_fwd(int act, double z, double& h) {
+    if (act == ACT_SILU) {
+        h = z / (1.0 + exp(-z));
+    } else if (act == ACT_LEAKY) {
+        h = z > 0.0 ? z : 0.01 * z;
+    } else {
+        h = z > 0.0 ? z : 0.0;
+    }
+}
+
+// activation and its derivative
+FT_HD void act_fwd_der(int act, double z, double& h, double& d) {
+    if (act == ACT_SILU) {
+        double sg = 1.0 / (1.0 + exp(-z));
+        h = z * sg;
+        d = sg * (1.0 + z * (1.0 - sg));
+    } else if (act == ACT_LEAKY) {
+        h = z > 0.0 ? z : 0.01 * z;
+        d = z > 0.0 ? 1.0 : 0.01;
+    } else {
+        h = z > 0.0 ? z : 0.0;
+        d = z > 0.0 ? 1.0 : 0.0;
+    }
+}
+
+FT_HD double act_der(int act, double z) {
+    double h, d;
+    act_fwd_der(act, z, h, d);
+    return d;
+}
+
+// mean_k mod(2 atan(e^{s_k} tan(x/2)))   (ipynb/field_transformation.py:249-257), es_k = e^{s_k}
+FT_HD double mixture_fwd(double x, double es0, double es1, int conv) {
+    double th = tan(x / 2);
+    double g0 = mod_2pi(2 * atan(es0 * th), conv);
+    double g1 = mod_2pi(2 * atan(es1 * th), conv);
+    return (g0 + g1) / 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (throughput mode: momenta and Metropolis uniforms made on the device)
+// ------------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    FT_HD static uint32_t mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+    FT_HD void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+        uint32_t a = k0, b = k1;
+        for (int i = 0; i < 10; ++i) {
+            uint32_t h0 = mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+            uint32_t h1 = mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = h1 ^ c1 ^ a, n1 = l1, n2 = h0 ^ c3 ^ b, n3 = l0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+// uniform in (0,1) with 53 random bits
+FT_HD double u53(uint32_t hi, uint32_t lo) {
+    uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
+//   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
+// ------------------------------------------------------------------------------------------------
+struct LayerGeom {
+    int mu, off;
+    int R;     // sites along the stripes
+    int Cn;    // sites across the stripes (multiple of 4)
+    int G;     // Cn / 4 stripe groups
+};
+
+struct EngineParams {
+    int L0, L1;
+    int nlayers;
+    int act, conv;
+    double inv_tol;
+    int inv_max_iter;
+    const double* wpack;   // global: nlayers * PACK_DOUBLES
+    const int* lmu;        // global: per layer mu
+    const int* loff;       // global: per layer off
+};
+
+FT_HD size_t engine_smem_doubles(int L0, int L1) {
+    size_t V = (size_t)L0 * L1, LP = L1 + 1;
+    return 2 * L0 * LP * 2      // X, GR
+         + V                    // CS
+         + V / 4                // UA
+         + 3 * (V / 4)          // OUT
+         + 8 * V + 6 * V + 6 * V// A, B, C
+         + PACK_DOUBLES + 4     // W (+pad)
+         + 64;                  // reduction scratch
+}
+
+// per-CTA global workspace (doubles): momenta, x0, y0, saved active links
+FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers) {
+    size_t V = (size_t)L0 * L1;
+    return 3 * 2 * V + (size_t)nlayers * (V / 4);
+}
+
+template <class E>
+struct Engine {
+    E& ex;
+    EngineParams pr;
+    int L0, L1, LP, V, VQ;
+    double *X, *GR, *CS, *UA, *OUT, *A, *B, *C, *W;
+    double *wsP, *wsX0, *wsY0, *wsSave;   // global per-CTA workspace
+    int* iters_out;                        // optional global: bisection iterations per layer (diagnostics)
+
+    FT_HD Engine(E& e, const EngineParams& p, double* smem, double* ws) : ex(e), pr(p) {
+        L0 = p.L0; L1 = p.L1; LP = L1 + 1; V = L0 * L1; VQ = V / 4;
+        double* s = smem;
+        X = s;   s += 2 * L0 * LP;
+        GR = s;  s += 2 * L0 * LP;
+        CS = s;  s += V;
+        UA = s;  s += VQ;
+        OUT = s; s += 3 * VQ;
+        s += ((uintptr_t)s & 8) ? 1 : 0;      // 16-byte align the planes/weights
+        A = s;   s += 8 * V;
+        B = s;   s += 6 * V;
+        C = s;   s += 6 * V;
+        W = s;   s += PACK_DOUBLES;
+        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsSave = ws + 6 * V;
+        iters_out = nullptr;
+    }
+
+    // ---- geometry ----
+    FT_HD LayerGeom geom(int l) const {
+        LayerGeom g;
+        g.mu = pr.lmu[l]; g.off = pr.loff[l];
+        g.R = g.mu == 0 ? L0 : L1;
+        g.Cn = g.mu == 0 ? L1 : L0;
+        g.G = g.Cn / 4;
+        return g;
+    }
+    FT_HD int xi(int mu, int n0, int n1) const { return (mu * L0 + n0) * LP + n1; }
+    // canonical (row r, shifted column c) -> lattice site
+    FT_HD void site(const LayerGeom& g, int r, int c, int& n0, int& n1) const {
+        int co = c + g.off; if (co >= g.Cn) co -= g.Cn;
+        if (g.mu == 0) { n0 = r; n1 = co; } else { n0 = co; n1 = r; }
+    }
+    // plaquette angle; order 0: ipynb/field_transformation.py:118-119, order 1: qed_helpers.py:83-86 / hmc_2dU1.py:114-120
+    FT_HD double plaq(int n0, int n1, int order) const {
+        int n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1p = n1 + 1 == L1 ? 0 : n1 + 1;
+        double a = X[xi(0, n0, n1)], b = X[xi(1, n0p, n1)], c = X[xi(0, n0, n1p)], d = X[xi(1, n0, n1)];
+        return order == 0 ? ((a + b) - c) - d : ((a - d) - c) + b;
+    }
+
+    // ---- global <-> shared field copies (global layout (2,L0,L1) contiguous) ----
+    FT_HD void load_field(double* dst, const double* g) {
+        for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
+            int n1 = i % L1, rest = i / L1;
+            dst[rest * LP + n1] = g[i];
+        }
+    }
+    FT_HD void store_field(double* g, const double* src) {
+        for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
+            int n1 = i % L1, rest = i / L1;
+            g[i] = src[rest * LP + n1];
+        }
+    }
+    FT_HD void load_weights(int l) {
+        const double* src = pr.wpack + (size_t)l * PACK_DOUBLES;
+        for (int i = ex.tid(); i < PACK_DOUBLES; i += ex.nt()) W[i] = src[i];
+    }
+
+    // =============================================================================================
+    // plain Wilson action pieces on the resident field
+    // =============================================================================================
+    // -beta * sum cos P   (order 0: U1GaugeAction, order 1: hmc_2dU1.action)
+    FT_PHASE double wilson_action(double beta, int order) {
+        double acc = 0.0;
+        for (int i = ex.tid(); i < V; i += ex.nt()) acc += cos(plaq(i / L1, i % L1, order));
+        return -beta * ex.sum(acc);
+    }
+    // floor(0.1 + sum regularize(P) / 2pi)   hmc_2dU1.py:123-124
+    FT_PHASE double topo_floor() {
+        double acc = 0.0;
+        for (int i = ex.tid(); i < V; i += ex.nt()) acc += regularize1(plaq(i / L1, i % L1, 1));
+        return floor(0.1 + ex.sum(acc) / TWO_PI_D);
+    }
+    // GR = dS/dx of the Wilson action: F0 = beta[sinP(n) - sinP(n-e1)], F1 = beta[sinP(n-e0) - sinP(n)]
+    FT_PHASE void wilson_force(double beta, int order) {
+        double* S = A;                                   // scratch plane, pitch L1
+        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(i / L1, i % L1, order));
+        ex.sync();
+        for (int i = ex.tid(); i < V; i += ex.nt()) {
+            int n0 = i / L1, n1 = i % L1;
+            int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+            double s = S[i];
+            GR[xi(0, n0, n1)] = beta * (s - S[n0 * L1 + n1m]);
+            GR[xi(1, n0, n1)] = beta * (S[n0m * L1 + n1] - s);
+        }
+        ex.sync();
+    }
+
+    // =============================================================================================
+    // coupling-layer phases (canonical stripe geometry)
+    // =============================================================================================
+    // cos/sin of the frozen plaquettes and the raw active plaquette
+    FT_PHASE void ph_planes(const LayerGeom g) {
+        const int T = g.G * g.R, order = pr.conv;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / g.R, r = t - gi * g.R, n0, n1;
+            site(g, r, 4 * gi, n0, n1);
+            UA[t] = plaq(n0, n1, order);
+            for (int k = 0; k < 2; ++k) {
+                site(g, r, 4 * gi + 1 + k, n0, n1);
+                double p = plaq(n0, n1, order);
+                CS[(2 * gi + k) * g.R + r] = cos(p);
+                CS[V / 2 + (2 * gi + k) * g.R + r] = sin(p);
+            }
+        }
+    }
+
+    // conv1 pre-activations for the 4 columns of group gi at row r.  z[q][o]
+    FT_HD void conv1_z(const LayerGeom& g, int gi, int r, double z[4][NH]) const {
+        const int R = g.R;
+        int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
+        double in[2][3][2];                                  // [k][a][ci]
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                in[k][a][0] = CS[(2 * gi + k) * R + rr[a]];
+                in[k][a][1] = CS[V / 2 + (2 * gi + k) * R + rr[a]];
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int o = 0; o < NH; ++o) z[q][o] = W[OFF_B1 + q * NH + o];
+        // (q, b, k): output column class q sees frozen column k through kernel column b
+        const int QB[6][3] = { {0, 2, 0}, {1, 1, 0}, {1, 2, 1}, {2, 0, 0}, {2, 1, 1}, {3, 0, 1} };
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+            const int q = QB[e][0], b = QB[e][1], k = QB[e][2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    const double* w = W + OFF_W1F + ((b * 3 + a) * 2 + ci) * NH;
+                    double v = in[k][a][ci];
+#pragma unroll
+                    for (int o = 0; o < NH; ++o) z[q][o] = fma(w[o], v, z[q][o]);
+                }
+        }
+    }
+
+    // h1 = act(conv1) on all columns -> A[o][c][r]
+    FT_PHASE void ph_conv1(const LayerGeom g) {
+        const int T = g.G * g.R, R = g.R, act = pr.act;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            double z[4][NH];
+            conv1_z(g, gi, r, z);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int o = 0; o < NH; ++o) {
+                    double h; act_fwd(act, z[q][o], h);
+                    A[(o * g.Cn + 4 * gi + q) * R + r] = h;
+                }
+        }
+    }
+
+    // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r]; optionally act' -> C
+    FT_PHASE void ph_conv2(const LayerGeom g, bool want_der) {
+        const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
+            int cc[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { int c = 4 * gi - 2 + j; cc[j] = c < 0 ? c + Cn : (c >= Cn ? c - Cn : c); }
+            double acc[3][NH];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int o = 0; o < NH; ++o) acc[k][o] = W[OFF_B2 + o];
+#pragma unroll 1
+            for (int ci = 0; ci < NH; ++ci) {
+                double in[3][5];
+                const double* Ap = A + ci * Cn * R;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) in[a][j] = Ap[cc[j] * R + rr[a]];
+                const double* wc = W + OFF_W2F + ci * 9 * NH;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double* w = wc + (a * 3 + b) * NH;
+#pragma unroll
+                        for (int o = 0; o < NH; ++o) {
+                            double wv = w[o];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) acc[k][o] = fma(wv, in[a][k + b], acc[k][o]);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int o = 0; o < NH; ++o) {
+                    int idx = (o * 3 * g.G + 3 * gi + k) * R + r;
+                    if (want_der) {
+                        double h, d; act_fwd_der(act, acc[k][o], h, d);
+                        B[idx] = h; C[idx] = d;
+                    } else {
+                        double h; act_fwd(act, acc[k][o], h);
+                        B[idx] = h;
+                    }
+                }
+        }
+    }
+
+    // conv3 at the active site of task (gi,r): out[0..2] = (s_1, s_2, t)
+    FT_HD void conv3_out(const LayerGeom& g, int gi, int r, double out[NOUT]) const {
+        const int R = g.R;
+        int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
+        double o0 = W[OFF_B3 + 0], o1 = W[OFF_B3 + 1], o2 = W[OFF_B3 + 2];
+#pragma unroll 2
+        for (int ci = 0; ci < NH; ++ci) {
+            const double* Bp = B + (ci * 3 * g.G + 3 * gi) * R;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    double v = Bp[b * R + rr[a]];
+                    const double* w = W + OFF_W3F + ((ci * 3 + a) * 3 + b) * 4;
+                    o0 = fma(w[0], v, o0); o1 = fma(w[1], v, o1); o2 = fma(w[2], v, o2);
+                }
+        }
+        out[0] = o0; out[1] = o1; out[2] = o2;
+    }
+
+    // forward transform of the active plaquettes + link update; returns this thread's logJ partial.
+    // save != nullptr: the pre-update active link values are stored there (for the reverse sweep).
+    FT_PHASE double ph_conv3_forward(const LayerGeom g, bool want_logJ, double* save) {
+        const int T = g.G * g.R, R = g.R, conv = pr.conv;
+        double lj = 0.0;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            double out[NOUT];
+            conv3_out(g, gi, r, out);
+            double u = UA[t];
+            double es0 = exp(out[0]), es1 = exp(out[1]);
+            double fx1 = mixture_fwd(u, es0, es1, conv);
+            double newp = mod_2pi(fx1 + out[2], conv);
+            double delta = newp - u;
+            int n0, n1; site(g, r, 4 * gi, n0, n1);
+            int li = xi(g.mu, n0, n1);
+            double xo = X[li];
+            if (save) save[t] = xo;
+            X[li] = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
+            if (want_logJ) {
+                double c = cos(u / 2), s = sin(u / 2);
+                double l0 = -log(exp(-out[0]) * (c * c) + es0 * (s * s));
+                double l1 = -log(exp(-out[1]) * (c * c) + es1 * (s * s));
+                double m = l0 > l1 ? l0 : l1;
+                lj += (m + log(exp(l0 - m) + exp(l1 - m))) - 0.6931471805599453;
+            }
+        }
+        return lj;
+    }
+
+    // one coupling layer forward on the resident field; returns logJ (valid on all threads) if asked
+    FT_HD double layer_forward(int l, bool want_logJ, double* save) {
+        LayerGeom g = geom(l);
+        load_weights(l);
+        ph_planes(g);
+        ex.sync();
+        ph_conv1(g);
+        ex.sync();
+        ph_conv2(g, false);
+        ex.sync();
+        double lj = ph_conv3_forward(g, want_logJ, save);
+        double tot = want_logJ ? ex.sum(lj) : 0.0;
+        ex.sync();
+        return tot;
+    }
+
+    // ---- reverse (ipynb/field_transformation.py:168-174, 319-338, 263-285) ----
+    // per-chain bisection: the reference path is single-chain, so its tensor-global stop test is a
+    // per-chain stop test here.  The "reached floating point precision" exit (:276-279) can never
+    // fire within max_iter=1000 because non-active sites (y=0,f=0) keep halving towards 0 without
+    // reaching it, so only the tolerance and max_iter exits exist.
+    FT_PHASE double ph_conv3_reverse(const LayerGeom g, bool want_logJ, int* iters) {
+        const int T = g.G * g.R, R = g.R, conv = pr.conv;
+        double* Y = A; double* ES0 = A + T; double* ES1 = A + 2 * T; double* LO = A + 3 * T; double* HI = A + 4 * T;
+        double* MID = A + 5 * T;
+        const double lo0 = conv == 0 ? 0.0 : -PI_D, hi0 = conv == 0 ? TWO_PI_D : PI_D;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            double out[NOUT];
+            conv3_out(g, gi, r, out);
+            OUT[t] = out[0]; OUT[T + t] = out[1];
+            ES0[t] = exp(out[0]); ES1[t] = exp(out[1]);
+            Y[t] = mod_2pi(UA[t] - out[2], conv);
+            LO[t] = lo0; HI[t] = hi0;
+        }
+        ex.sync();     // (A was the conv2 input; all conv3 reads of B are unaffected)
+        int it = 0;
+        for (; it < pr.inv_max_iter; ++it) {
+            double err = 0.0;
+            for (int t = ex.tid(); t < T; t += ex.nt()) {
+                double mid = (LO[t] + HI[t]) / 2;
+                double f = mixture_fwd(mid, ES0[t], ES1[t], conv);
+                double y = Y[t];
+                double e = fabs(y - f);
+                err = e > err ? e : err;
+                MID[t] = mid;
+                if (y > f) LO[t] = mid; else HI[t] = mid;
+            }
+            err = ex.maxv(err);
+            if (err < pr.inv_tol) { ++it; break; }
+        }
+        if (iters) *iters = it;
+        double lj = 0.0;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            double x1 = MID[t];
+            double delta = x1 - UA[t];
+            int n0, n1; site(g, r, 4 * gi, n0, n1);
+            int li = xi(g.mu, n0, n1);
+            X[li] = mod_2pi((g.mu == 0 ? delta : -delta) + X[li], conv);
+            if (want_logJ) {
+                double c = cos(x1 / 2), s = sin(x1 / 2);
+                double l0 = -log(exp(-OUT[t]) * (c * c) + ES0[t] * (s * s));
+                double l1 = -log(exp(-OUT[T + t]) * (c * c) + ES1[t] * (s * s));
+                double m = l0 > l1 ? l0 : l1;
+                lj -= (m + log(exp(l0 - m) + exp(l1 - m))) - 0.6931471805599453;
+            }
+        }
+        return lj;
+    }
+
+    FT_HD double layer_reverse(int l, bool want_logJ) {
+        LayerGeom g = geom(l);
+        load_weights(l);
+        ph_planes(g);
+        ex.sync();
+        ph_conv1(g);
+        ex.sync();
+        ph_conv2(g, false);
+        ex.sync();
+        int iters = 0;
+        double lj = ph_conv3_reverse(g, want_logJ, &iters);
+        if (iters_out && ex.tid() == 0) iters_out[l] = iters;
+        double tot = want_logJ ? ex.sum(lj) : 0.0;
+        ex.sync();
+        return tot;
+    }
+
+    // =============================================================================================
+    // adjoint of one layer: GR holds d/dy on entry, d/dx on exit; X holds y on entry, x on exit.
+    // =============================================================================================
+    FT_PHASE void ph_restore(const LayerGeom g, const double* save) {
+        const int T = g.G * g.R, R = g.R;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R, n0, n1;
+            site(g, r, 4 * gi, n0, n1);
+            X[xi(g.mu, n0, n1)] = save[t];
+        }
+    }
+
+    // conv3 + adjoint of the mixture transform and of -logJ at the active sites:
+    // OUT <- (s1bar, s2bar, tbar), UA <- Pbar(active)
+    FT_PHASE void ph_conv3_adjoint(const LayerGeom g) {
+        const int T = g.G * g.R, R = g.R;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            double out[NOUT];
+            conv3_out(g, gi, r, out);
+            int n0, n1; site(g, r, 4 * gi, n0, n1);
+            double gl = GR[xi(g.mu, n0, n1)];
+            double db = g.mu == 0 ? gl : -gl;                 // delta-bar
+            double u = UA[t];
+            double c = cos(u / 2), s = sin(u / 2), su = sin(u);
+            double c2 = c * c, s2 = s * s;
+            double ep0 = exp(out[0]), em0 = exp(-out[0]), ep1 = exp(out[1]), em1 = exp(-out[1]);
+            double e0 = 1.0 / (em0 * c2 + ep0 * s2), e1 = 1.0 / (em1 * c2 + ep1 * s2);   // e^{l_k}
+            double sg0 = e0 / (e0 + e1), sg1 = e1 / (e0 + e1);                             // softmax_k l_k
+            // w = -1 multiplies the logJ terms (ft_action = S - sum logJ)
+            double ub = -db + db * (0.5 * (e0 + e1))
+                      + (sg0 * (0.5 * (ep0 - em0)) * su * e0 + sg1 * (0.5 * (ep1 - em1)) * su * e1);
+            double sb0 = db * su * e0 * 0.5 - sg0 * (em0 * c2 - ep0 * s2) * e0;
+            double sb1 = db * su * e1 * 0.5 - sg1 * (em1 * c2 - ep1 * s2) * e1;
+            OUT[t] = sb0; OUT[T + t] = sb1; OUT[2 * T + t] = db;
+            UA[t] = ub;
+        }
+    }
+
+    // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C)
+    FT_PHASE void ph_conv3T(const LayerGeom g) {
+        const int T = g.G * g.R, R = g.R;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            // out-gradient rows r-a+1 for a=0,1,2 -> r+1, r, r-1
+            int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };
+            double ob[NOUT][3];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) ob[o][a] = OUT[o * T + gi * R + rs[a]];
+            double acc[3][NH];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci) acc[k][ci] = 0.0;
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double* w = W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH;
+#pragma unroll
+                        for (int ci = 0; ci < NH; ++ci) acc[k][ci] = fma(w[ci], ob[o][a], acc[k][ci]);
+                    }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci) {
+                    int idx = (ci * 3 * g.G + 3 * gi + k) * R + r;
+                    C[idx] = acc[k][ci] * C[idx];
+                }
+        }
+    }
+
+    // zbar1 = conv2^T(zbar2) * act'(z1) -> A[ci][c][r]   (z1 recomputed from the frozen planes)
+    FT_PHASE void ph_conv2T(const LayerGeom g) {
+        const int T = g.G * g.R, R = g.R, G = g.G, act = pr.act;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            int gn = gi + 1 == G ? 0 : gi + 1;
+            int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
+            // source column slots j=0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1,4g,4g+1,4g+3,4g+4
+            int sc[5] = { 3 * gi, 3 * gi + 1, 3 * gi + 2, 3 * gn, 3 * gn + 1 };
+            const int CO[5] = { -1, 0, 1, 3, 4 };                                // column offsets from 4g
+            double acc[4][NH];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci) acc[q][ci] = 0.0;
+#pragma unroll 1
+            for (int o = 0; o < NH; ++o) {
+                const double* Cp = C + o * 3 * G * R;
+                double zb[3][5];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) zb[a][j] = Cp[sc[j] * R + rs[a]];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int b = q - CO[j] + 1;           // src column = col - b + 1
+                            if (b >= 0 && b <= 2) {
+                                const double* w = W + OFF_W2T + ((o * 3 + a) * 3 + b) * NH;
+#pragma unroll
+                                for (int ci = 0; ci < NH; ++ci) acc[q][ci] = fma(w[ci], zb[a][j], acc[q][ci]);
+                            }
+                        }
+            }
+            double z[4][NH];
+            conv1_z(g, gi, r, z);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci)
+                    A[(ci * g.Cn + 4 * gi + q) * R + r] = acc[q][ci] * act_der(act, z[q][ci]);
+        }
+    }
+
+    // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar on the lattice (PB, pitch LP)
+    FT_PHASE void ph_conv1T(const LayerGeom g, double* PB) {
+        const int T = g.G * g.R, R = g.R, Cn = g.Cn;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            int gi = t / R, r = t - gi * R;
+            int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
+            int n0, n1;
+            site(g, r, 4 * gi, n0, n1);     PB[n0 * LP + n1] = UA[t];
+            site(g, r, 4 * gi + 3, n0, n1); PB[n0 * LP + n1] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = 4 * gi + 1 + k;
+                double gc = 0.0, gs = 0.0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    int cs = c - b + 1; cs = cs >= Cn ? cs - Cn : cs;     // 4g .. 4g+3 (+1) ; never negative
+#pragma unroll 2
+                    for (int o = 0; o < NH; ++o)
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            double v = A[(o * Cn + cs) * R + rs[a]];
+                            const double* w = W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2;
+                            gc = fma(w[0], v, gc); gs = fma(w[1], v, gs);
+                        }
+                }
+                double cp = CS[(2 * gi + k) * R + r], sp = CS[V / 2 + (2 * gi + k) * R + r];
+                site(g, r, c, n0, n1);
+                PB[n0 * LP + n1] = -sp * gc + cp * gs;
+            }
+        }
+    }
+
+    // GR += plaquette^T(Pbar)
+    FT_PHASE void ph_scatter(const double* PB) {
+        for (int i = ex.tid(); i < V; i += ex.nt()) {
+            int n0 = i / L1, n1 = i - n0 * L1;
+            int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+            double pb = PB[n0 * LP + n1];
+            GR[xi(0, n0, n1)] += pb - PB[n0 * LP + n1m];
+            GR[xi(1, n0, n1)] += PB[n0m * LP + n1] - pb;
+        }
+    }
+
+    FT_HD void layer_adjoint(int l, const double* save) {
+        LayerGeom g = geom(l);
+        load_weights(l);
+        ph_restore(g, save);
+        ex.sync();
+        ph_planes(g);
+        ex.sync();
+        ph_conv1(g);
+        ex.sync();
+        ph_conv2(g, true);
+        ex.sync();
+        ph_conv3_adjoint(g);
+        ex.sync();
+        ph_conv3T(g);
+        ex.sync();
+        ph_conv2T(g);
+        ex.sync();
+        double* PB = B;                  // h2 is dead
+        ph_conv1T(g, PB);
+        ex.sync();
+        ph_scatter(PB);
+        ex.sync();
+    }
+
+    // =============================================================================================
+    // chain programs on the resident field X
+    // =============================================================================================
+    // X <- F(X); returns sum of logJ (if asked).  save_base: per-layer saved active links (or null)
+    FT_HD double flow_forward(bool want_logJ, double* save_base, double* layer_logJ = nullptr) {
+        double tot = 0.0;
+        for (int l = 0; l < pr.nlayers; ++l) {
+            double lj = layer_forward(l, want_logJ, save_base ? save_base + (size_t)l * VQ : nullptr);
+            tot += lj;
+            if (layer_logJ && ex.tid() == 0) layer_logJ[l] = lj;
+        }
+        return tot;
+    }
+    FT_HD double flow_reverse(bool want_logJ, double* layer_logJ = nullptr) {
+        double tot = 0.0;
+        for (int l = pr.nlayers - 1; l >= 0; --l) {
+            double lj = layer_reverse(l, want_logJ);
+            tot += lj;
+            if (layer_logJ && ex.tid() == 0) layer_logJ[l] = lj;
+        }
+        return tot;
+    }
+    // ft_action (ipynb/ft_hmc.py:230-238): X <- F(X), returns S(F(x)) - sum logJ; *s_plain = S(F(x))
+    FT_HD double ft_action(double beta, double* s_plain = nullptr) {
+        double lj = flow_forward(true, nullptr);
+        double s = wilson_action(beta, 0);
+        if (s_plain) *s_plain = s;
+        return s - lj;
+    }
+    // ft_force (ipynb/ft_hmc.py:240-249): GR <- d/dx [S(F(x)) - sum logJ]; X is preserved.
+    FT_HD void ft_force(double beta) {
+        flow_forward(false, wsSave);
+        ex.sync();                        // saved links are read back through global memory
+        wilson_force(beta, 0);
+        for (int l = pr.nlayers - 1; l >= 0; --l) layer_adjoint(l, wsSave + (size_t)l * VQ);
+    }
+
+    // elementwise helpers on the link field (skip the pitch padding)
+    template <class F> FT_HD void for_links(F f) {
+        for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
+            int n1 = i % L1, rest = i / L1;
+            f(rest * LP + n1, i);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// trajectory programs (one chain).  Momenta live in the per-CTA global workspace (L2 resident).
+// ------------------------------------------------------------------------------------------------
+struct TrajIO {
+    const double* field_in;    // (2,L0,L1)
+    double* field_out;         // (2,L0,L1)
+    const double* p_in;        // (2,L0,L1) or null -> Philox
+    const double* u_in;        // scalar or null -> Philox
+    double* p_out;             // optional final momenta
+    uint64_t seed, chain, traj;
+    double beta, dt; int nstep;
+    double* out_dH; double* out_expmdH; int* out_acc; double* out_plaq; double* out_Q;
+    double* out_h0; double* out_h1;
+};
+
+// Box-Muller normals from Philox: element pair index j -> two normals
+template <class E>
+FT_HD void philox_momenta(Engine<E>& en, const TrajIO& io, double* P) {
+    Philox ph{ (uint32_t)io.seed, (uint32_t)(io.seed >> 32) };
+    const int n = 2 * en.V;
+    for (int j = en.ex.tid(); j < n / 2; j += en.ex.nt()) {
+        uint32_t r[4];
+        ph.gen((uint32_t)j, (uint32_t)io.traj, (uint32_t)io.chain, (uint32_t)(io.chain >> 32) ^ 0x5EEDu, r);
+        double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+        double rad = sqrt(-2.0 * log(u1)), sn, cs;
+        sn = sin(TWO_PI_D * u2); cs = cos(TWO_PI_D * u2);
+        P[2 * j] = rad * cs; P[2 * j + 1] = rad * sn;
+    }
+}
+FT_HD double philox_uniform(const TrajIO& io) {
+    Philox ph{ (uint32_t)io.seed, (uint32_t)(io.seed >> 32) };
+    uint32_t r[4];
+    ph.gen(0xFFFFFFFFu, (uint32_t)io.traj, (uint32_t)io.chain, (uint32_t)(io.chain >> 32) ^ 0xACCE97u, r);
+    return u53(r[0], r[1]);
+}
+
+// leapfrog skeleton shared by the plain and the field-transformed trajectory
+// (hmc_2dU1.py:132-141, ipynb/ft_hmc.py:394-418): position-first, nstep force evaluations.
+template <class E, class ForceFn>
+FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, ForceFn force) {
+    auto& ex = en.ex;
+    const double hdt = 0.5 * dt;
+    en.for_links([&](int si, int gi) { en.X[si] = en.X[si] + hdt * P[gi]; });
+    ex.sync();
+    for (int s = 0; s < nstep; ++s) {
+        force();
+        const bool last = s == nstep - 1;
+        const double step = last ? hdt : dt;
+        en.for_links([&](int si, int gi) {
+            double pn = P[gi] + (-dt) * en.GR[si];
+            P[gi] = pn;
+            en.X[si] = en.X[si] + step * pn;
+        });
+        ex.sync();
+    }
+}
+
+// FT-HMC trajectory (ipynb/ft_hmc.py:420-435)
+template <class E>
+FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
+    auto& ex = en.ex;
+    const int V = en.V;
+    double* P = en.wsP;
+    en.load_field(en.X, io.field_in);
+    ex.sync();
+    en.flow_reverse(false);                                     // x = ft_flow_inv(field)
+    en.for_links([&](int si, int gi) { en.wsX0[gi] = en.X[si]; });
+    if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
+    else philox_momenta(en, io, P);
+    ex.sync();
+    double k0 = 0.0;
+    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k0 += P[i] * P[i];
+    k0 = ex.sum(k0);
+    double s0_plain;
+    double h0 = en.ft_action(io.beta, &s0_plain) + 0.5 * k0;    // X <- y0 = F(x)
+    en.for_links([&](int si, int gi) { en.wsY0[gi] = en.X[si]; });
+    ex.sync();
+    en.for_links([&](int si, int gi) { en.X[si] = en.wsX0[gi]; });
+    ex.sync();
+    leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.ft_force(io.beta); });
+    en.for_links([&](int si, int gi) { en.X[si] = regularize1(en.X[si]); });
+    ex.sync();
+    double k1 = 0.0;
+    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
+    k1 = ex.sum(k1);
+    double s1_plain;
+    double h1 = en.ft_action(io.beta, &s1_plain) + 0.5 * k1;    // X <- F(xr)
+    double u = io.u_in ? *io.u_in : philox_uniform(io);
+    double dH = h1 - h0;
+    double e = exp(-dH);
+    bool acc = u < e;
+    if (!acc) {                                                  // newfield = ft_flow(x) = y0
+        ex.sync();
+        en.for_links([&](int si, int gi) { en.X[si] = en.wsY0[gi]; });
+    }
+    ex.sync();
+    double q = en.topo_floor();
+    en.store_field(io.field_out, en.X);
+    if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
+    if (ex.tid() == 0) {
+        if (io.out_dH) *io.out_dH = dH;
+        if (io.out_expmdH) *io.out_expmdH = e;
+        if (io.out_acc) *io.out_acc = acc ? 1 : 0;
+        if (io.out_plaq) *io.out_plaq = (acc ? s1_plain : s0_plain) / (-io.beta * V);
+        if (io.out_Q) *io.out_Q = q;
+        if (io.out_h0) *io.out_h0 = h0;
+        if (io.out_h1) *io.out_h1 = h1;
+    }
+    ex.sync();
+}
+
+// plain HMC trajectory (hmc_2dU1.py:144-155)
+template <class E>
+FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
+    auto& ex = en.ex;
+    const int V = en.V;
+    double* P = en.wsP;
+    en.load_field(en.X, io.field_in);
+    if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
+    else philox_momenta(en, io, P);
+    ex.sync();
+    double k0 = 0.0;
+    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k0 += P[i] * P[i];
+    k0 = ex.sum(k0);
+    double s0 = en.wilson_action(io.beta, 1);
+    double h0 = s0 + 0.5 * k0;
+    leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.wilson_force(io.beta, 1); });
+    en.for_links([&](int si, int gi) { en.X[si] = regularize1(en.X[si]); });
+    ex.sync();
+    double k1 = 0.0;
+    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
+    k1 = ex.sum(k1);
+    double s1 = en.wilson_action(io.beta, 1);
+    double h1 = s1 + 0.5 * k1;
+    double u = io.u_in ? *io.u_in : philox_uniform(io);
+    double dH = h1 - h0;
+    double e = exp(-dH);
+    bool acc = u < e;
+    if (!acc) {
+        ex.sync();
+        en.load_field(en.X, io.field_in);                        // newx = x (bit-identical input)
+    }
+    ex.sync();
+    double q = en.topo_floor();
+    en.store_field(io.field_out, en.X);
+    if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
+    if (ex.tid() == 0) {
+        if (io.out_dH) *io.out_dH = dH;
+        if (io.out_expmdH) *io.out_expmdH = e;
+        if (io.out_acc) *io.out_acc = acc ? 1 : 0;
+        if (io.out_plaq) *io.out_plaq = (acc ? s1 : s0) / (-io.beta * V);
+        if (io.out_Q) *io.out_Q = q;
+        if (io.out_h0) *io.out_h0 = h0;
+        if (io.out_h1) *io.out_h1 = h1;
+    }
+    ex.sync();
+}
+
+}  // namespace fthmc

@@ -1,0 +1,110 @@
+// chain_programs.cuh -- what one CTA does with one chain for each C-ABI entry point.
+// Shared by the CUDA kernel (fthmc_capi.cu) and the serial CPU emulation used only by tests.
+#pragma once
+#include "chain_engine.cuh"
+
+namespace fthmc {
+
+enum ChainMode {
+    MODE_FLOW_FWD = 0,     // ft_flow         ipynb/ft_hmc.py:220   (+ summed / per-layer logJ)
+    MODE_FLOW_INV = 1,     // ft_flow_inv     ipynb/ft_hmc.py:225
+    MODE_FT_ACTION = 2,    // ft_action       ipynb/ft_hmc.py:230
+    MODE_FT_FORCE = 3,     // ft_force        ipynb/ft_hmc.py:240
+    MODE_FT_LEAPFROG = 4,  // ft_leapfrog     ipynb/ft_hmc.py:394
+    MODE_FT_HMC = 5,       // ft_hmc          ipynb/ft_hmc.py:420
+    MODE_HMC = 6,          // hmc             hmc_2dU1.py:144
+    MODE_LEAPFROG = 7,     // leapfrog        hmc_2dU1.py:132
+};
+
+struct ChainArgs {
+    int mode;
+    int B;
+    EngineParams pr;
+    double beta, dt;
+    int nstep;
+    const double* field_in;   // (B,2,L0,L1)
+    const double* p_in;       // (B,2,L0,L1) or null
+    const double* u_in;       // (B) or null
+    double* field_out;        // (B,2,L0,L1): flowed field / force / new field
+    double* p_out;            // (B,2,L0,L1) or null
+    double* s_out;            // (B): logJ / action / dH
+    double* layer_logJ;       // (B,nlayers) or null
+    int* iters;               // (B,nlayers) or null (bisection iteration counts)
+    double* expmdH; int* acc; double* plaq; double* topo; double* h0; double* h1;   // (B) each, trajectory modes
+    uint64_t seed, traj, chain0;
+    double* ws;               // per-CTA workspace base
+    size_t ws_stride;         // doubles per CTA
+};
+
+template <class E>
+FT_HD void run_chain(E& ex, const ChainArgs& a, double* smem, double* ws, int b) {
+    Engine<E> en(ex, a.pr, smem, ws);
+    const size_t fs = (size_t)2 * en.V;
+    const double* fin = a.field_in + (size_t)b * fs;
+    double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
+    en.iters_out = a.iters ? a.iters + (size_t)b * a.pr.nlayers : nullptr;
+    double* llj = a.layer_logJ ? a.layer_logJ + (size_t)b * a.pr.nlayers : nullptr;
+    switch (a.mode) {
+    case MODE_FLOW_FWD: {
+        en.load_field(en.X, fin); ex.sync();
+        double lj = en.flow_forward(a.s_out != nullptr || llj != nullptr, nullptr, llj);
+        en.store_field(fout, en.X);
+        if (a.s_out && ex.tid() == 0) a.s_out[b] = lj;
+        ex.sync();
+    } break;
+    case MODE_FLOW_INV: {
+        en.load_field(en.X, fin); ex.sync();
+        double lj = en.flow_reverse(a.s_out != nullptr || llj != nullptr, llj);
+        en.store_field(fout, en.X);
+        if (a.s_out && ex.tid() == 0) a.s_out[b] = lj;
+        ex.sync();
+    } break;
+    case MODE_FT_ACTION: {
+        en.load_field(en.X, fin); ex.sync();
+        double s = en.ft_action(a.beta);
+        if (ex.tid() == 0) a.s_out[b] = s;
+        if (fout) en.store_field(fout, en.X);
+        ex.sync();
+    } break;
+    case MODE_FT_FORCE: {
+        en.load_field(en.X, fin); ex.sync();
+        en.ft_force(a.beta);
+        en.store_field(fout, en.GR);
+        ex.sync();
+    } break;
+    case MODE_FT_LEAPFROG:
+    case MODE_LEAPFROG: {
+        en.load_field(en.X, fin);
+        for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) en.wsP[i] = a.p_in[(size_t)b * fs + i];
+        ex.sync();
+        if (a.mode == MODE_FT_LEAPFROG)
+            leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.ft_force(a.beta); });
+        else
+            leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
+        en.store_field(fout, en.X);
+        for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) a.p_out[(size_t)b * fs + i] = en.wsP[i];
+        ex.sync();
+    } break;
+    case MODE_FT_HMC:
+    case MODE_HMC: {
+        TrajIO io;
+        io.field_in = fin; io.field_out = fout;
+        io.p_in = a.p_in ? a.p_in + (size_t)b * fs : nullptr;
+        io.u_in = a.u_in ? a.u_in + b : nullptr;
+        io.p_out = a.p_out ? a.p_out + (size_t)b * fs : nullptr;
+        io.seed = a.seed; io.chain = a.chain0 + (uint64_t)b; io.traj = a.traj;
+        io.beta = a.beta; io.dt = a.dt; io.nstep = a.nstep;
+        io.out_dH = a.s_out ? a.s_out + b : nullptr;
+        io.out_expmdH = a.expmdH ? a.expmdH + b : nullptr;
+        io.out_acc = a.acc ? a.acc + b : nullptr;
+        io.out_plaq = a.plaq ? a.plaq + b : nullptr;
+        io.out_Q = a.topo ? a.topo + b : nullptr;
+        io.out_h0 = a.h0 ? a.h0 + b : nullptr;
+        io.out_h1 = a.h1 ? a.h1 + b : nullptr;
+        if (a.mode == MODE_FT_HMC) ft_hmc_trajectory(en, io); else hmc_trajectory(en, io);
+    } break;
+    default: break;
+    }
+}
+
+}  // namespace fthmc

@@ -1,0 +1,42 @@
+// Serial CPU build of the chain engine (fthmc_b200/csrc/chain_engine.cuh) -- TEST INFRASTRUCTURE ONLY.
+// The engine's phases are correct for any thread count; here they run with one "thread" so the
+// indexing, the weight packing and the hand-derived adjoint can be checked against the oracle
+// without a GPU.  Nothing in the product package loads this library.
+#include <cstdlib>
+#include <vector>
+#include "../../fthmc_b200/csrc/chain_programs.cuh"
+#include "../../fthmc_b200/csrc/weight_pack.h"
+
+namespace {
+struct SerialExec {
+    int tid() const { return 0; }
+    int nt() const { return 1; }
+    void sync() const {}
+    double sum(double v) const { return v; }
+    double maxv(double v) const { return v; }
+};
+}
+
+extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const double* raw, const int* mu, const int* off,
+                        int act, int conv, double tol, int max_iter, double beta, double dt, int nstep,
+                        const double* field_in, const double* p_in, const double* u_in, double* field_out, double* p_out,
+                        double* s_out, double* layer_logJ, int* iters, double* expmdH, int* acc, double* plaq, double* topo,
+                        double* h0, double* h1, unsigned long long seed, unsigned long long traj) {
+    using namespace fthmc;
+    if (L0 % 4 || L1 % 4) return -1;
+    std::vector<double> pack((size_t)nlayers * PACK_DOUBLES);
+    for (int l = 0; l < nlayers; ++l) pack_layer(raw + (size_t)l * RAW_DOUBLES, mu[l], pack.data() + (size_t)l * PACK_DOUBLES);
+    std::vector<double> smem(engine_smem_doubles(L0, L1) + 8), ws(engine_ws_doubles(L0, L1, nlayers) + 8);
+    ChainArgs a{};
+    a.mode = mode; a.B = B;
+    a.pr.L0 = L0; a.pr.L1 = L1; a.pr.nlayers = nlayers; a.pr.act = act; a.pr.conv = conv;
+    a.pr.inv_tol = tol; a.pr.inv_max_iter = max_iter; a.pr.wpack = pack.data(); a.pr.lmu = mu; a.pr.loff = off;
+    a.beta = beta; a.dt = dt; a.nstep = nstep;
+    a.field_in = field_in; a.p_in = p_in; a.u_in = u_in; a.field_out = field_out; a.p_out = p_out;
+    a.s_out = s_out; a.layer_logJ = layer_logJ; a.iters = iters;
+    a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
+    a.seed = seed; a.traj = traj; a.chain0 = 0;
+    SerialExec ex;
+    for (int b = 0; b < B; ++b) run_chain(ex, a, smem.data(), ws.data(), b);
+    return 0;
+}

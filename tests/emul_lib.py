@@ -1,0 +1,63 @@
+"""ctypes access to the serial CPU build of the chain engine (tests/emul/emul.cpp).  Test
+infrastructure only: lets the non-GPU test-suite exercise the exact device code (indexing, packing,
+adjoint) that the CUDA library compiles."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "emul.cpp")
+LIB = os.path.join(HERE, "emul", "libfthmc_emul.so")
+CSRC = os.path.join(os.path.dirname(HERE), "fthmc_b200", "csrc")
+
+MODES = dict(flow_fwd=0, flow_inv=1, ft_action=2, ft_force=3, ft_leapfrog=4, ft_hmc=5, hmc=6, leapfrog=7)
+ACTS = dict(silu=0, swish=0, leaky_relu=1, relu=2)
+
+
+def build(force=False):
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("chain_engine.cuh", "chain_programs.cuh", "weight_pack.h")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC",
+                               "-o", LIB, SRC])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.emul_run.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a, ct=ctypes.c_double):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, act="silu", conv=0,
+        tol=1e-6, max_iter=1000, mu=None, off=None, seed=0, traj=0):
+    """field: (B,2,L0,L1) float64.  Returns a dict of outputs."""
+    field = np.ascontiguousarray(field, dtype=np.float64)
+    B, _, L0, L1 = field.shape
+    raw = np.ascontiguousarray(raw_weights, dtype=np.float64) if raw_weights is not None else np.zeros((0, 955))
+    n = raw.shape[0]
+    mu = np.array([i % 2 for i in range(n)] if mu is None else mu, dtype=np.int32)
+    off = np.array([(i // 2) % 4 for i in range(n)] if off is None else off, dtype=np.int32)
+    out = dict(field=np.zeros_like(field), p=np.zeros_like(field), s=np.zeros(B), layer_logJ=np.zeros((B, max(n, 1))),
+               iters=np.zeros((B, max(n, 1)), dtype=np.int32), expmdH=np.zeros(B), acc=np.zeros(B, dtype=np.int32),
+               plaq=np.zeros(B), topo=np.zeros(B), h0=np.zeros(B), h1=np.zeros(B))
+    p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+    u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+    rc = lib().emul_run(MODES[mode], B, L0, L1, n, _p(raw), _p(mu, ctypes.c_int), _p(off, ctypes.c_int),
+                        ACTS[act], conv, ctypes.c_double(tol), max_iter, ctypes.c_double(beta), ctypes.c_double(dt),
+                        nstep, _p(field), _p(p), _p(u), _p(out["field"]), _p(out["p"]), _p(out["s"]),
+                        _p(out["layer_logJ"]), _p(out["iters"], ctypes.c_int), _p(out["expmdH"]),
+                        _p(out["acc"], ctypes.c_int), _p(out["plaq"]), _p(out["topo"]), _p(out["h0"]), _p(out["h1"]),
+                        ctypes.c_ulonglong(seed), ctypes.c_ulonglong(traj))
+    assert rc == 0, rc
+    return out

@@ -1,0 +1,97 @@
+"""The chain engine's device code (fthmc_b200/csrc/chain_engine.cuh), compiled serially for the CPU,
+against the golden vectors from the reference.  This checks the algorithm the CUDA kernels run
+(canonical stripe geometry, packed weights, pruned convolutions, bisection inverse, hand-written
+adjoint, trajectory logic) without a GPU; the `-m gpu` tests check the same through the C ABI."""
+import numpy as np
+import pytest
+
+import emul_lib as E
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)))
+
+
+def wrap(x):
+    return np.remainder(x + np.pi, 2 * np.pi) - np.pi
+
+
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4"])
+def test_flow_forward_action_force(golden, name):
+    g = golden(name)
+    x, w, beta = g["x"], g["weights"], float(g["beta"])
+    o = E.run("flow_fwd", w, x)
+    assert np.max(np.abs(o["field"] - g["flow_fwd"])) < 1e-12
+    assert np.max(np.abs(o["layer_logJ"] - g["layer_logJ"].T)) < 1e-11
+    assert relerr(o["s"], g["layer_logJ"].sum(axis=0)) < 1e-12
+    o = E.run("ft_action", w, x, beta=beta)
+    assert relerr(o["s"], g["ft_action"]) < 1e-12
+    o = E.run("ft_force", w, x, beta=beta)
+    assert relerr(o["field"], g["ft_force"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4"])
+def test_flow_inverse_bit_exact_midpoints(golden, name):
+    g = golden(name)
+    o = E.run("flow_inv", g["weights"], g["flow_fwd"])
+    # the bisection returns dyadic midpoints: same decisions => agreement to rounding, not to 1e-6
+    assert np.max(np.abs(o["field"] - g["flow_inv_of_fwd"])) < 1e-11
+    assert np.max(np.abs(wrap(o["field"] - g["x"]))) < 2e-5
+    assert np.all(o["iters"] > 10) and np.all(o["iters"] < 40)
+
+
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4", "ft_L32_b4_n40"])
+def test_ft_hmc_teacher_forced(golden, name):
+    g = golden(name)
+    n = len(g["traj_u"])
+    o = E.run("ft_hmc", g["weights"], g["traj_x"], beta=float(g["beta"]), dt=float(g["dt"]), nstep=int(g["nstep"]),
+              p=g["traj_p"], u=g["traj_u"])
+    assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["traj_acc"])
+    assert np.array_equal(o["topo"], g["traj_topo"])
+    assert np.max(np.abs(o["plaq"] - g["traj_plaq"])) < 1e-12
+    assert np.max(np.abs(o["field"] - g["traj_out"])) < 1e-8
+    assert n >= 1
+
+
+def test_plain_hmc_teacher_forced(golden):
+    g = golden("plain_L8")
+    o = E.run("hmc", None, g["traj_x"], beta=float(g["beta"]), dt=float(g["dt"]), nstep=int(g["nstep"]),
+              p=g["traj_p"], u=g["traj_u"])
+    assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-11
+    assert np.array_equal(o["acc"].astype(bool), g["traj_acc"])
+    assert np.array_equal(o["topo"], g["traj_topo"])
+    assert np.max(np.abs(o["field"] - g["traj_out"])) < 1e-12
+    o = E.run("leapfrog", None, g["x0"][None], beta=float(g["beta"]), dt=float(g["dt"]), nstep=int(g["nstep"]),
+              p=g["lf_p"][None])
+    assert np.max(np.abs(o["field"][0] - g["lf_x_out"])) < 1e-13
+    assert np.max(np.abs(o["p"][0] - g["lf_p_out"])) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["leaky_L8", "copyB_L8"])
+def test_variants(golden, name):
+    g = golden(name)
+    kw = dict(act=str(g["activation"]), conv=int(g["convention"]))
+    o = E.run("flow_fwd", g["weights"], g["x"], **kw)
+    assert np.max(np.abs(o["field"] - g["flow_fwd"])) < 1e-12
+    assert relerr(o["s"], g["logJ"]) < 1e-12
+    o = E.run("flow_inv", g["weights"], g["flow_fwd"], **kw)
+    assert np.max(np.abs(o["field"] - g["flow_inv_of_fwd"])) < 1e-11
+
+
+def test_rectangular_lattice_against_oracle():
+    """L0 != L1 exercises the row/column bookkeeping of the two mask orientations."""
+    import torch
+    from oracle import fthmc_oracle as O
+    flow = O.random_flow(n_layers=8, seed=11, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()])
+                                    for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    torch.manual_seed(5)
+    x = torch.empty(2, 2, 8, 12).uniform_(-np.pi, np.pi)
+    y, lj = O.ft_flow_logJ(flow, x)
+    o = E.run("flow_fwd", raw, x.numpy())
+    assert np.max(np.abs(o["field"] - y.numpy())) < 1e-12
+    assert relerr(o["s"], lj.numpy()) < 1e-12
+    f = O.ft_force(2.5, flow, x)
+    o = E.run("ft_force", raw, x.numpy(), beta=2.5)
+    assert relerr(o["field"], f.numpy()) < 1e-11
