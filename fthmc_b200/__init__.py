@@ -1,0 +1,13 @@
+"""fthmc_b200 -- B200 (sm_100a) implementation of nftqcd/fthmc's FT-HMC trajectory path.
+
+Python here is only the host-side mirror of the reference's function interface; every body is a CUDA
+kernel in libfthmc_b200.so (C ABI: include/fthmc_b200.h).  Importing the package does not need a GPU;
+calling any entry point does, and raises if the library or the device is missing."""
+from ._lib import FthmcError, LIB_PATH, lib  # noqa: F401
+from .flow import PackedFlow, pack, raw_weights_of  # noqa: F401
+from .api import (Param, action, u1_action, force, regularize, topocharge, topo_charge, leapfrog, hmc, hmc_batch,  # noqa: F401
+                  ft_flow, ft_flow_inv, ft_action, ft_force, ft_leapfrog, ft_hmc, ft_hmc_batch)
+
+__all__ = ["Param", "action", "u1_action", "force", "regularize", "topocharge", "topo_charge", "leapfrog", "hmc",
+           "hmc_batch", "ft_flow", "ft_flow_inv", "ft_action", "ft_force", "ft_leapfrog", "ft_hmc", "ft_hmc_batch",
+           "PackedFlow", "pack", "raw_weights_of", "FthmcError", "lib", "LIB_PATH"]

@@ -1,0 +1,326 @@
+"""Drop-in entry points of the FT-HMC trajectory path, same names / argument order / return structure
+as the reference scripts (copy A):
+
+    action force plaqphase-free topocharge regularize leapfrog hmc        hmc_2dU1.py:100-155
+    topo_charge                                                           ipynb/field_transformation.py:138
+    ft_flow ft_flow_inv ft_action ft_force                                ipynb/ft_hmc.py:220-249
+    ft_leapfrog ft_hmc                                                    ipynb/ft_hmc.py:394-435
+
+Tensors keep the reference layouts: links (2,L0,L1) for the single-chain plain functions, (B,2,L0,L1)
+for the flow functions.  CPU tensors are accepted like in the reference (copied to the GPU, result
+copied back); CUDA tensors stay on the device.  Bodies are CUDA kernels reached through the C ABI of
+libfthmc_b200.so -- there is no PyTorch/CPU fallback.
+
+Batched extensions (`*_batch`) take explicit momenta `p` and uniforms `u` (parity mode) or a Philox
+seed (throughput mode) and return per-chain dH / acc / plaq / Q."""
+import math
+import os
+from functools import reduce
+
+import torch
+
+from . import _lib
+from .flow import PackedFlow, pack
+
+F64, F32 = 0, 1
+
+
+class Param:
+    """Same fields as the reference's Param (ipynb/ft_hmc.py:57-72, hmc_2dU1.py:41-70)."""
+
+    def __init__(self, beta=6.0, lat=(64, 64), tau=2.0, nstep=50, ntraj=256, nrun=4, nprint=256, seed=11 * 13,
+                 randinit=False, nth=int(os.environ.get("OMP_NUM_THREADS", "2")), nth_interop=2):
+        self.beta = beta
+        self.lat = tuple(lat)
+        self.nd = len(lat)
+        self.volume = reduce(lambda x, y: x * y, lat)
+        self.tau = tau
+        self.nstep = nstep
+        self.dt = self.tau / self.nstep
+        self.ntraj, self.nrun, self.nprint, self.seed = ntraj, nrun, nprint, seed
+        self.randinit, self.nth, self.nth_interop = randinit, nth, nth_interop
+
+    def initializer(self):
+        if self.randinit:
+            return torch.empty((self.nd,) + self.lat).uniform_(-math.pi, math.pi)
+        return torch.zeros((self.nd,) + self.lat)
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+_ws = {}
+
+
+def _device(t=None):
+    if t is not None and t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("fthmc_b200 needs a CUDA device: there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _workspace(flow_handle, B, L0, L1, dev):
+    need = _lib.lib().fthmc_workspace_bytes(flow_handle, B, L0, L1)
+    buf = _ws.get(dev)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=dev)
+        _ws[dev] = buf
+    return buf
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_in(t, dev, dtype=None):
+    """contiguous device copy (no copy if already there)."""
+    t = t.detach()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(dev, non_blocking=True).contiguous()
+
+
+def _back(out, like):
+    return out if like.is_cuda else out.cpu()
+
+
+def _dt(t):
+    if t.dtype == torch.float64:
+        return F64
+    if t.dtype == torch.float32:
+        return F32
+    raise _lib.FthmcError(-3, f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _as_batch(f):
+    """(2,L0,L1) -> (1,2,L0,L1); (B,2,L0,L1) unchanged."""
+    if f.dim() == 3:
+        return f.unsqueeze(0), True
+    if f.dim() == 4:
+        return f, False
+    raise _lib.FthmcError(-1, f"links must be (2,L0,L1) or (B,2,L0,L1), got {tuple(f.shape)}")
+
+
+# ------------------------------------------------------------------------------------------------
+# plain Wilson stencils
+# ------------------------------------------------------------------------------------------------
+def _reduce_call(fn_name, f, order_or_rounded, beta=None):
+    fb, single = _as_batch(f)
+    dev = _device(fb)
+    with torch.cuda.device(dev):
+        x = _dev_in(fb, dev)
+        B, _, L0, L1 = x.shape
+        out = torch.empty(B, dtype=x.dtype, device=dev)
+        L = _lib.lib()
+        if fn_name == "action":
+            _lib.check(L.fthmc_action(x.data_ptr(), B, L0, L1, float(beta), order_or_rounded, out.data_ptr(), _dt(x), _stream()))
+        else:
+            _lib.check(L.fthmc_topo_charge(x.data_ptr(), B, L0, L1, order_or_rounded, out.data_ptr(), _dt(x), _stream()))
+    out = _back(out, f)
+    return out[0] if single else out
+
+
+def action(param, f):
+    """hmc_2dU1.py:100 -- -beta * sum cos(plaqphase(f)); (2,L0,L1) -> 0-d (a (B,2,L0,L1) batch gives (B,))."""
+    return _reduce_call("action", f, 1, param.beta)
+
+
+def u1_action(beta, cfgs):
+    """U1GaugeAction(beta)(cfgs), ipynb/field_transformation.py:120 -- (B,2,L0,L1) -> (B,)."""
+    return _reduce_call("action", cfgs, 0, beta)
+
+
+def topocharge(f):
+    """hmc_2dU1.py:123 -- floor(0.1 + sum regularize(P)/2pi)."""
+    return _reduce_call("topo", f, 1)
+
+
+def topo_charge(x):
+    """ipynb/field_transformation.py:138 -- batched, un-rounded."""
+    return _reduce_call("topo", x, 0)
+
+
+def force(param, f, order=1):
+    """hmc_2dU1.py:104 -- dS/df (the reference gets it from autograd; closed form here)."""
+    fb, single = _as_batch(f)
+    dev = _device(fb)
+    with torch.cuda.device(dev):
+        x = _dev_in(fb, dev)
+        B, _, L0, L1 = x.shape
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().fthmc_force(x.data_ptr(), B, L0, L1, float(param.beta), order, out.data_ptr(), _dt(x), _stream()))
+    out = _back(out, f)
+    return out[0] if single else out
+
+
+def regularize(f):
+    """hmc_2dU1.py:127"""
+    dev = _device(f)
+    with torch.cuda.device(dev):
+        x = _dev_in(f, dev)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().fthmc_regularize(x.data_ptr(), out.data_ptr(), x.numel(), _dt(x), _stream()))
+    return _back(out, f)
+
+
+# ------------------------------------------------------------------------------------------------
+# plain HMC
+# ------------------------------------------------------------------------------------------------
+def leapfrog(param, x, p):
+    """hmc_2dU1.py:132 -- returns (x_, p_)."""
+    xb, single = _as_batch(x)
+    pb, _ = _as_batch(p)
+    dev = _device(xb)
+    with torch.cuda.device(dev):
+        xd, pd = _dev_in(xb, dev, torch.float64), _dev_in(pb, dev, torch.float64)
+        B, _, L0, L1 = xd.shape
+        xo, po = torch.empty_like(xd), torch.empty_like(pd)
+        ws = _workspace(None, B, L0, L1, dev)
+        _lib.check(_lib.lib().fthmc_leapfrog(xd.data_ptr(), pd.data_ptr(), xo.data_ptr(), po.data_ptr(), B, L0, L1,
+                                             float(param.beta), float(param.dt), int(param.nstep),
+                                             ws.data_ptr(), ws.numel(), _stream()))
+    xo, po = _back(xo, x), _back(po, x)
+    return (xo[0], po[0]) if single else (xo, po)
+
+
+def _traj_call(flow_pf, beta, dt, nstep, x, p, u, seed, traj, chain0, want_h=False):
+    """shared body of hmc_batch / ft_hmc_batch.  x (B,2,L0,L1) on any device."""
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        xd = _dev_in(x, dev, torch.float64)
+        B, _, L0, L1 = xd.shape
+        pd = None if p is None else _dev_in(p, dev, torch.float64)
+        ud = None if u is None else _dev_in(u.reshape(-1), dev, torch.float64)
+        if pd is not None and pd.shape != xd.shape:
+            raise _lib.FthmcError(-1, "p must have the shape of x")
+        if ud is not None and ud.numel() != B:
+            raise _lib.FthmcError(-1, "u must have one entry per chain")
+        xo = torch.empty_like(xd)
+        sc = torch.empty((6, B), dtype=torch.float64, device=dev)      # dH, exp(-dH), plaq, Q, h0, h1
+        acc = torch.empty(B, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        if flow_pf is None:
+            ws = _workspace(None, B, L0, L1, dev)
+            _lib.check(L.fthmc_hmc_traj(xd.data_ptr(), xo.data_ptr(), _ptr(pd), _ptr(ud), seed, traj, chain0, B, L0, L1,
+                                        float(beta), float(dt), int(nstep), sc[0].data_ptr(), sc[1].data_ptr(),
+                                        acc.data_ptr(), sc[2].data_ptr(), sc[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        else:
+            ws = _workspace(flow_pf.handle, B, L0, L1, dev)
+            _lib.check(L.fthmc_ft_hmc_traj(flow_pf.handle, xd.data_ptr(), xo.data_ptr(), _ptr(pd), _ptr(ud), seed, traj, chain0,
+                                           B, L0, L1, float(beta), float(dt), int(nstep), sc[0].data_ptr(), sc[1].data_ptr(),
+                                           acc.data_ptr(), sc[2].data_ptr(), sc[3].data_ptr(),
+                                           sc[4].data_ptr() if want_h else None, sc[5].data_ptr() if want_h else None,
+                                           ws.data_ptr(), ws.numel(), _stream()))
+    res = dict(field=_back(xo, x), dH=_back(sc[0], x), exp_mdH=_back(sc[1], x), acc=_back(acc, x).bool(),
+               plaq=_back(sc[2], x), topo=_back(sc[3], x))
+    if want_h:
+        res.update(h0=_back(sc[4], x), h1=_back(sc[5], x))
+    return res
+
+
+def hmc_batch(param, x, p=None, u=None, seed=0, traj=0, chain0=0):
+    """B independent plain-HMC trajectories in one persistent launch.  p/u None => device Philox."""
+    return _traj_call(None, param.beta, param.dt, param.nstep, x, p, u, seed, traj, chain0)
+
+
+def hmc(param, x):
+    """hmc_2dU1.py:144 -- (dH, exp_mdH, acc, newx).  Momenta and the Metropolis uniform come from the
+    torch generator in the reference's order (randn_like(x), then rand([], float64)), so a seeded run
+    reproduces the reference chain."""
+    p = torch.randn_like(x)
+    u = torch.rand([], dtype=torch.float64)
+    r = hmc_batch(param, x.unsqueeze(0), p.unsqueeze(0), u.reshape(1))
+    return r["dH"][0], r["exp_mdH"][0], r["acc"][0], r["field"][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# field transformation
+# ------------------------------------------------------------------------------------------------
+def _flow_call(kind, flow, f, beta=0.0, want_logJ=False, convention=0):
+    dev = _device(f)
+    with torch.cuda.device(dev):
+        pf = pack(flow, convention=convention, device=dev)
+        xd = _dev_in(f, dev, torch.float64)
+        if xd.dim() != 4:
+            raise _lib.FthmcError(-1, f"field must be (B,2,L0,L1), got {tuple(xd.shape)}")
+        B, _, L0, L1 = xd.shape
+        ws = _workspace(pf.handle, B, L0, L1, dev)
+        L = _lib.lib()
+        logJ = torch.empty(B, dtype=torch.float64, device=dev) if (want_logJ or kind == "action") else None
+        out = torch.empty_like(xd) if kind != "action" else None
+        if kind == "fwd":
+            _lib.check(L.fthmc_flow_fwd(pf.handle, xd.data_ptr(), out.data_ptr(), _ptr(logJ), None, B, L0, L1,
+                                        ws.data_ptr(), ws.numel(), _stream()))
+        elif kind == "inv":
+            _lib.check(L.fthmc_flow_inv(pf.handle, xd.data_ptr(), out.data_ptr(), _ptr(logJ), None, None, B, L0, L1,
+                                        ws.data_ptr(), ws.numel(), _stream()))
+        elif kind == "action":
+            _lib.check(L.fthmc_ft_action(pf.handle, xd.data_ptr(), float(beta), logJ.data_ptr(), None, B, L0, L1,
+                                         ws.data_ptr(), ws.numel(), _stream()))
+        elif kind == "force":
+            _lib.check(L.fthmc_ft_force(pf.handle, xd.data_ptr(), float(beta), out.data_ptr(), B, L0, L1,
+                                        ws.data_ptr(), ws.numel(), _stream()))
+    if kind == "action":
+        return _back(logJ, f)
+    if want_logJ:
+        return _back(out, f), _back(logJ, f)
+    return _back(out, f)
+
+
+def ft_flow(flow, f, with_logJ=False):
+    """ipynb/ft_hmc.py:220 -- F(f) (detached).  with_logJ=True also returns sum_layers logJ (B,)."""
+    return _flow_call("fwd", flow, f, want_logJ=with_logJ)
+
+
+def ft_flow_inv(flow, f, with_logJ=False):
+    """ipynb/ft_hmc.py:225 -- F^{-1}(f) by per-chain bisection to 1e-6, decision for decision."""
+    return _flow_call("inv", flow, f, want_logJ=with_logJ)
+
+
+def ft_action(param, flow, f):
+    """ipynb/ft_hmc.py:230 -- S(F(f)) - sum logJ, (B,)."""
+    return _flow_call("action", flow, f, beta=param.beta)
+
+
+def ft_force(param, flow, field, create_graph=False):
+    """ipynb/ft_hmc.py:240 -- d/dfield sum(ft_action): hand-written adjoint kernel, no autograd."""
+    if create_graph:
+        raise NotImplementedError("create_graph=True (second-order training path) is outside the trajectory path")
+    return _flow_call("force", flow, field, beta=param.beta)
+
+
+def ft_leapfrog(param, flow, x, p):
+    """ipynb/ft_hmc.py:394 -- returns (x_, p_) (the reference's per-step prints are not reproduced)."""
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+        xd, pd = _dev_in(x, dev, torch.float64), _dev_in(p, dev, torch.float64)
+        B, _, L0, L1 = xd.shape
+        xo, po = torch.empty_like(xd), torch.empty_like(pd)
+        ws = _workspace(pf.handle, B, L0, L1, dev)
+        _lib.check(_lib.lib().fthmc_ft_leapfrog(pf.handle, xd.data_ptr(), pd.data_ptr(), xo.data_ptr(), po.data_ptr(),
+                                                B, L0, L1, float(param.beta), float(param.dt), int(param.nstep),
+                                                ws.data_ptr(), ws.numel(), _stream()))
+    return _back(xo, x), _back(po, x)
+
+
+def ft_hmc_batch(param, flow, field, p=None, u=None, seed=0, traj=0, chain0=0, want_h=False):
+    """B independent FT-HMC trajectories, one persistent CTA per chain.  p/u None => device Philox
+    keyed by (seed, chain0+b, traj)."""
+    dev = _device(field)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+    return _traj_call(pf, param.beta, param.dt, param.nstep, field, p, u, seed, traj, chain0, want_h=want_h)
+
+
+def ft_hmc(param, flow, field):
+    """ipynb/ft_hmc.py:420 -- (float dH, float exp_mdH, 0-d bool acc, newfield), field (1,2,L0,L1)."""
+    p = torch.randn_like(field)
+    u = torch.rand([], dtype=torch.float64)
+    r = ft_hmc_batch(param, flow, field, p, u.reshape(1))
+    return float(r["dH"][0]), float(r["exp_mdH"][0]), r["acc"][0], r["field"]

@@ -163,8 +163,9 @@ struct EngineParams {
     const int* loff;       // global: per layer off
 };
 
-FT_HD size_t engine_smem_doubles(int L0, int L1) {
+FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true) {
     size_t V = (size_t)L0 * L1, LP = L1 + 1;
+    if (!flow) return 2 * L0 * LP * 2 + V + 64 + 4;      // X, GR, one scratch plane
     return 2 * L0 * LP * 2      // X, GR
          + V                    // CS
          + V / 4                // UA
@@ -194,6 +195,12 @@ struct Engine {
         double* s = smem;
         X = s;   s += 2 * L0 * LP;
         GR = s;  s += 2 * L0 * LP;
+        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsSave = ws + 6 * V;
+        iters_out = nullptr;
+        if (p.nlayers == 0) {               // plain HMC: only a scratch plane is needed
+            A = s; CS = UA = OUT = B = C = W = nullptr;
+            return;
+        }
         CS = s;  s += V;
         UA = s;  s += VQ;
         OUT = s; s += 3 * VQ;
@@ -202,8 +209,6 @@ struct Engine {
         B = s;   s += 6 * V;
         C = s;   s += 6 * V;
         W = s;   s += PACK_DOUBLES;
-        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsSave = ws + 6 * V;
-        iters_out = nullptr;
     }
 
     // ---- geometry ----
@@ -673,7 +678,7 @@ struct Engine {
                 double gc = 0.0, gs = 0.0;
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    int cs = c - b + 1; cs = cs >= Cn ? cs - Cn : cs;     // 4g .. 4g+3 (+1) ; never negative
+                    const int cs = c - b + 1;                                  // 4g .. 4g+3: always in range
 #pragma unroll 2
                     for (int o = 0; o < NH; ++o)
 #pragma unroll
@@ -750,7 +755,7 @@ struct Engine {
     // ft_action (ipynb/ft_hmc.py:230-238): X <- F(X), returns S(F(x)) - sum logJ; *s_plain = S(F(x))
     FT_HD double ft_action(double beta, double* s_plain = nullptr) {
         double lj = flow_forward(true, nullptr);
-        double s = wilson_action(beta, 0);
+        double s = wilson_action(beta, pr.conv);
         if (s_plain) *s_plain = s;
         return s - lj;
     }
@@ -758,7 +763,7 @@ struct Engine {
     FT_HD void ft_force(double beta) {
         flow_forward(false, wsSave);
         ex.sync();                        // saved links are read back through global memory
-        wilson_force(beta, 0);
+        wilson_force(beta, pr.conv);
         for (int l = pr.nlayers - 1; l >= 0; --l) layer_adjoint(l, wsSave + (size_t)l * VQ);
     }
 

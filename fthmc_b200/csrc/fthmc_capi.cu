@@ -1,0 +1,496 @@
+// fthmc_capi.cu -- sm_100a kernels and the C ABI of libfthmc_b200.so (declared in include/fthmc_b200.h).
+//
+//   k_chain          persistent one-CTA-per-chain kernel: every flow / trajectory entry point
+//   k_action_topo    streaming Wilson action / topological charge  (HBM bound)
+//   k_force          streaming Wilson force with a shared-memory sin(P) tile (HBM bound)
+//   k_regularize     elementwise wrap
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false (FMAs are written
+// explicitly in the convolutions; elementwise updates keep the reference's separate mul/add rounding).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/fthmc_b200.h"
+#include "chain_programs.cuh"
+#include "weight_pack.h"
+
+using namespace fthmc;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char* msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+extern "C" const char* fthmc_last_error_string(void) { return g_err.c_str(); }
+extern "C" int fthmc_version(void) { return 100; }
+extern "C" unsigned long long fthmc_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// CTA execution policy for the chain engine
+// ------------------------------------------------------------------------------------------------
+struct CtaExec {
+    double* red;   // 64 doubles of shared scratch
+    __host__ __device__ int tid() const {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ int nt() const {
+#ifdef __CUDA_ARCH__
+        return blockDim.x;
+#else
+        return 1;
+#endif
+    }
+    __host__ __device__ void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+    __host__ __device__ double sum(double v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) red[w] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int i = 0; i < nw; ++i) t += red[i];
+        __syncthreads();
+        return t;
+#else
+        return v;
+#endif
+    }
+    __host__ __device__ double maxv(double v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) red[w] = v;
+        __syncthreads();
+        double t = red[0];
+        for (int i = 1; i < nw; ++i) t = fmax(t, red[i]);
+        __syncthreads();
+        return t;
+#else
+        return v;
+#endif
+    }
+};
+
+__global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    CtaExec ex{ smem };
+    double* ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(ex, a, smem + 64, ws, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming stencils
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct M;
+template <> struct M<double> {
+    static __device__ double cosv(double x) { return cos(x); }
+    static __device__ double sinv(double x) { return sin(x); }
+    static __device__ double floorv(double x) { return floor(x); }
+    static __device__ double modv(double x, double y) { return fmod(x, y); }
+};
+template <> struct M<float> {
+    static __device__ float cosv(float x) { return cosf(x); }
+    static __device__ float sinv(float x) { return sinf(x); }
+    static __device__ float floorv(float x) { return floorf(x); }
+    static __device__ float modv(float x, float y) { return fmodf(x, y); }
+};
+
+template <typename T>
+__device__ __forceinline__ T plaq_g(const T* __restrict__ f, int L0, int L1, int n0, int n1, int order) {
+    const int n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1p = n1 + 1 == L1 ? 0 : n1 + 1;
+    const T a = f[n0 * L1 + n1], b = f[(L0 + n0p) * L1 + n1], c = f[n0 * L1 + n1p], d = f[(L0 + n0) * L1 + n1];
+    return order == 0 ? ((a + b) - c) - d : ((a - d) - c) + b;
+}
+
+template <typename T>
+__device__ __forceinline__ T regularize_t(T f) {
+    const T PI = (T)3.141592653589793, TP = (T)6.283185307179586;
+    T g = (f - PI) / TP;
+    return TP * (g - M<T>::floorv(g) - (T)0.5);
+}
+
+// torch_wrap(x) = remainder(x+pi, 2pi) - pi
+template <typename T>
+__device__ __forceinline__ T wrap_t(T x) {
+    const T PI = (T)3.141592653589793, TP = (T)6.283185307179586;
+    T r = M<T>::modv(x + PI, TP);
+    if (r != (T)0 && r < (T)0) r += TP;
+    return r - PI;
+}
+
+// what: 0 = sum cos P (action), 1 = sum regularize(P) (floored charge), 2 = sum wrap(P) (batched charge)
+// grid (nchunk, B); each block reduces rows [c*rows, (c+1)*rows) of one chain in fp64.
+template <typename T>
+__global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links, int L0, int L1, int rows, int what, int order,
+                                                   double* __restrict__ partial) {
+    __shared__ double red[8];
+    const int b = blockIdx.y, c = blockIdx.x;
+    const T* f = links + (size_t)b * 2 * L0 * L1;
+    const int r0 = c * rows, r1 = min(L0, r0 + rows);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (r1 - r0) * L1; i += blockDim.x) {
+        const int n0 = r0 + i / L1, n1 = i % L1;
+        const T p = plaq_g(f, L0, L1, n0, n1, order);
+        acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+        partial[(size_t)b * gridDim.x + c] = t;
+    }
+}
+
+template <typename T>
+__global__ void k_finalize(const double* __restrict__ partial, int nchunk, int B, int what, double beta, int rounded, T* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double t = 0.0;
+    for (int c = 0; c < nchunk; ++c) t += partial[(size_t)b * nchunk + c];
+    double r;
+    if (what == 0) r = -beta * t;
+    else if (rounded) r = floor(0.1 + t / TWO_PI_D);
+    else r = t / TWO_PI_D;
+    out[b] = (T)r;
+}
+
+// grid (nchunk, B): rows [r0,r1) of one chain; sin P of rows r0-1..r1-1 staged in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int L0, int L1, int rows, T beta, int order, T* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* S = reinterpret_cast<T*>(smem_raw);                  // (rows+1) x L1, row 0 is r0-1
+    const int b = blockIdx.y, c = blockIdx.x;
+    const T* f = links + (size_t)b * 2 * L0 * L1;
+    T* o = out + (size_t)b * 2 * L0 * L1;
+    const int r0 = c * rows, r1 = min(L0, r0 + rows), nr = r1 - r0;
+    for (int i = threadIdx.x; i < (nr + 1) * L1; i += blockDim.x) {
+        int n0 = r0 - 1 + i / L1; if (n0 < 0) n0 += L0;
+        S[i] = M<T>::sinv(plaq_g(f, L0, L1, n0, i % L1, order));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * L1; i += blockDim.x) {
+        const int rr = i / L1, n1 = i % L1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+        const T s = S[(rr + 1) * L1 + n1];
+        o[(r0 + rr) * L1 + n1] = beta * (s - S[(rr + 1) * L1 + n1m]);
+        o[(L0 + r0 + rr) * L1 + n1] = beta * (S[rr * L1 + n1] - s);
+    }
+}
+
+template <typename T>
+__global__ void k_regularize(const T* __restrict__ in, T* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = regularize_t(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+struct fthmc_flow {
+    int n_layers, act, conv, max_iter;
+    double tol;
+    double* wpack;   // device
+    int* lmu;        // device
+    int* loff;       // device
+};
+
+struct DevInfo { int sm = 0; int smem_optin = 0; bool ok = false; };
+static DevInfo& devinfo() {
+    static thread_local DevInfo d;
+    static thread_local int dev_cached = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return d;
+    if (!d.ok || dev != dev_cached) {
+        cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        d.ok = true; dev_cached = dev;
+    }
+    return d;
+}
+
+static int chain_threads(int L0, int L1, bool flow) {
+    int tasks = flow ? (L0 * L1) / 4 : L0 * L1;
+    int nt = ((tasks + 31) / 32) * 32;
+    return nt < 32 ? 32 : (nt > 256 ? 256 : nt);
+}
+static size_t chain_smem_bytes(int L0, int L1, bool flow) { return (engine_smem_doubles(L0, L1, flow) + 64) * sizeof(double); }
+
+// grid of the persistent kernel: one CTA per chain up to what is co-resident on the device
+static int chain_grid(int B, int L0, int L1, bool flow, int* occ_out = nullptr) {
+    DevInfo& d = devinfo();
+    int occ = 1;
+    size_t smem = chain_smem_bytes(L0, L1, flow);
+    cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain, chain_threads(L0, L1, flow), smem) != cudaSuccess || occ < 1) occ = 1;
+    if (occ_out) *occ_out = occ;
+    long long g = (long long)d.sm * occ;
+    return (int)(B < g ? B : g);
+}
+
+static int check_lattice(int B, int L0, int L1, bool flow) {
+    if (B <= 0 || L0 <= 0 || L1 <= 0) return fail(FTHMC_E_ARG, "B, L0, L1 must be positive");
+    if (L0 % 4 || L1 % 4) return fail(FTHMC_E_LATTICE, "L0 and L1 must be multiples of 4 (4-periodic stripe masks)");
+    DevInfo& d = devinfo();
+    if (!d.ok) return fail(FTHMC_E_ARG, "no CUDA device");
+    if (chain_smem_bytes(L0, L1, flow) > (size_t)d.smem_optin)
+        return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
+    return 0;
+}
+
+extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
+    if (B <= 0 || L0 <= 0 || L1 <= 0) return 0;
+    DevInfo& d = devinfo();
+    // upper bound on the persistent grid: co-resident CTAs cannot exceed 32 per SM
+    long long g = (long long)(d.sm > 0 ? d.sm : 148) * 32;
+    if (B < g) g = B;
+    return (size_t)g * engine_ws_doubles(L0, L1, flow ? flow->n_layers : 0) * sizeof(double) + 256;
+}
+
+static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    const bool has_flow = flow != nullptr;
+    int rc = check_lattice(a.B, L0, L1, has_flow);
+    if (rc) return rc;
+    a.pr.L0 = L0; a.pr.L1 = L1;
+    if (has_flow) {
+        a.pr.nlayers = flow->n_layers; a.pr.act = flow->act; a.pr.conv = flow->conv;
+        a.pr.inv_tol = flow->tol; a.pr.inv_max_iter = flow->max_iter;
+        a.pr.wpack = flow->wpack; a.pr.lmu = flow->lmu; a.pr.loff = flow->loff;
+    } else {
+        a.pr.nlayers = 0; a.pr.act = 0; a.pr.conv = 0; a.pr.inv_tol = 0; a.pr.inv_max_iter = 0;
+        a.pr.wpack = nullptr; a.pr.lmu = nullptr; a.pr.loff = nullptr;
+    }
+    const int grid = chain_grid(a.B, L0, L1, has_flow);
+    a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers);
+    const size_t need = (size_t)grid * a.ws_stride * sizeof(double);
+    if (!ws || ws_bytes < need) return fail(FTHMC_E_WORKSPACE, "workspace null or smaller than fthmc_workspace_bytes()");
+    if (((uintptr_t)ws) & 7) return fail(FTHMC_E_WORKSPACE, "workspace must be 8-byte aligned");
+    a.ws = (double*)ws;
+    k_chain<<<grid, chain_threads(L0, L1, has_flow), chain_smem_bytes(L0, L1, has_flow), (cudaStream_t)stream>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: stencils
+// ------------------------------------------------------------------------------------------------
+static int stencil_rows(int L0, int L1) {
+    int rows = 8192 / L1; if (rows < 1) rows = 1; if (rows > L0) rows = L0;
+    return rows;
+}
+
+template <typename T>
+static int reduce_launch(const void* links, int B, int L0, int L1, int what, int order, double beta, int rounded, void* out, cudaStream_t st) {
+    const int rows = stencil_rows(L0, L1), nchunk = (L0 + rows - 1) / rows;
+    double* partial = nullptr;
+    CK(cudaMallocAsync(&partial, sizeof(double) * (size_t)B * nchunk, st));
+    k_action_topo<T><<<dim3(nchunk, B), 256, 0, st>>>((const T*)links, L0, L1, rows, what, order, partial);
+    k_finalize<T><<<(B + 127) / 128, 128, 0, st>>>(partial, nchunk, B, what, beta, rounded, (T*)out);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(partial, st));
+    return 0;
+}
+
+static int check_stencil(const void* in, const void* out, int B, int L0, int L1, int dtype) {
+    if (!in || !out) return fail(FTHMC_E_ARG, "null pointer");
+    if (B <= 0 || L0 <= 0 || L1 <= 0) return fail(FTHMC_E_ARG, "B, L0, L1 must be positive");
+    if (B > 65535) return fail(FTHMC_E_ARG, "B > 65535: split the batch");
+    if (dtype != FTHMC_F64 && dtype != FTHMC_F32) return fail(FTHMC_E_DTYPE, "dtype must be FTHMC_F64 or FTHMC_F32");
+    return 0;
+}
+
+extern "C" int fthmc_action(const void* links, int B, int L0, int L1, double beta, int order, void* out, int dtype, void* stream) {
+    int rc = check_stencil(links, out, B, L0, L1, dtype); if (rc) return rc;
+    if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
+    return dtype == FTHMC_F64 ? reduce_launch<double>(links, B, L0, L1, 0, order, beta, 0, out, (cudaStream_t)stream)
+                              : reduce_launch<float>(links, B, L0, L1, 0, order, beta, 0, out, (cudaStream_t)stream);
+}
+
+extern "C" int fthmc_topo_charge(const void* links, int B, int L0, int L1, int rounded, void* out, int dtype, void* stream) {
+    int rc = check_stencil(links, out, B, L0, L1, dtype); if (rc) return rc;
+    // rounded: hmc_2dU1.topocharge (plaqphase order, regularize); else field_transformation.topo_charge (u1_plaq order, torch_wrap)
+    const int what = rounded ? 1 : 2, order = rounded ? 1 : 0;
+    return dtype == FTHMC_F64 ? reduce_launch<double>(links, B, L0, L1, what, order, 0.0, rounded, out, (cudaStream_t)stream)
+                              : reduce_launch<float>(links, B, L0, L1, what, order, 0.0, rounded, out, (cudaStream_t)stream);
+}
+
+extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta, int order, void* force_out, int dtype, void* stream) {
+    int rc = check_stencil(links, force_out, B, L0, L1, dtype); if (rc) return rc;
+    if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
+    const size_t es = dtype == FTHMC_F64 ? 8 : 4;
+    int rows = (int)((40 * 1024) / (es * L1)) - 1;
+    if (rows < 1) return fail(FTHMC_E_LATTICE, "L1 too large for the force tile");
+    if (rows > L0) rows = L0;
+    const int nchunk = (L0 + rows - 1) / rows;
+    const size_t smem = (size_t)(rows + 1) * L1 * es;
+    if (dtype == FTHMC_F64)
+        k_force<double><<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const double*)links, L0, L1, rows, beta, order, (double*)force_out);
+    else
+        k_force<float><<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const float*)links, L0, L1, rows, (float)beta, order, (float*)force_out);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fthmc_regularize(const void* in, void* out, long long n, int dtype, void* stream) {
+    if (!in || !out || n <= 0) return fail(FTHMC_E_ARG, "null pointer or n <= 0");
+    long long blocks = (n + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dtype == FTHMC_F64) k_regularize<double><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, n);
+    else if (dtype == FTHMC_F32) k_regularize<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)in, (float*)out, n);
+    else return fail(FTHMC_E_DTYPE, "dtype must be FTHMC_F64 or FTHMC_F32");
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: flow handle
+// ------------------------------------------------------------------------------------------------
+extern "C" int fthmc_flow_pack(const double* raw_host, int n_layers, const int* mu_host, const int* off_host,
+                               int hidden0, int hidden1, int n_mix, int ksize, int activation, int convention,
+                               double inv_tol, int inv_max_iter, fthmc_flow_t* out) {
+    if (!raw_host || !mu_host || !off_host || !out || n_layers <= 0) return fail(FTHMC_E_ARG, "null pointer or n_layers <= 0");
+    if (hidden0 != NH || hidden1 != NH || n_mix != NK || ksize != 3)
+        return fail(FTHMC_E_NETSHAPE, "only the reference CNN shape is built: hidden_sizes=[8,8], n_mixture_comps=2, kernel_size=3");
+    if (activation < 0 || activation > 2) return fail(FTHMC_E_ARG, "activation must be silu(0), leaky_relu(1) or relu(2)");
+    if (convention != 0 && convention != 1) return fail(FTHMC_E_ARG, "convention must be 0 ([0,2pi)) or 1 ([-pi,pi))");
+    if (!(inv_tol > 0) || inv_max_iter <= 0) return fail(FTHMC_E_ARG, "inv_tol and inv_max_iter must be positive");
+    for (int l = 0; l < n_layers; ++l)
+        if ((mu_host[l] != 0 && mu_host[l] != 1) || off_host[l] < 0 || off_host[l] > 3)
+            return fail(FTHMC_E_ARG, "mask mu must be 0/1 and mask off in 0..3");
+    std::vector<double> pack((size_t)n_layers * PACK_DOUBLES);
+    for (int l = 0; l < n_layers; ++l) pack_layer(raw_host + (size_t)l * RAW_DOUBLES, mu_host[l], pack.data() + (size_t)l * PACK_DOUBLES);
+    fthmc_flow* f = new fthmc_flow();
+    f->n_layers = n_layers; f->act = activation; f->conv = convention; f->tol = inv_tol; f->max_iter = inv_max_iter;
+    f->wpack = nullptr; f->lmu = nullptr; f->loff = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&f->wpack, pack.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&f->lmu, n_layers * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&f->loff, n_layers * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemcpy(f->wpack, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(f->lmu, mu_host, n_layers * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(f->loff, off_host, n_layers * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(f->wpack); cudaFree(f->lmu); cudaFree(f->loff); delete f;
+        return cuda_fail(e, "fthmc_flow_pack");
+    }
+    *out = f;
+    return 0;
+}
+
+extern "C" int fthmc_flow_free(fthmc_flow_t f) {
+    if (!f) return 0;
+    cudaFree(f->wpack); cudaFree(f->lmu); cudaFree(f->loff);
+    delete f;
+    return 0;
+}
+
+extern "C" int fthmc_flow_n_layers(fthmc_flow_t f) { return f ? f->n_layers : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: resident-chain entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int fthmc_flow_fwd(fthmc_flow_t flow, const double* x_in, double* x_out, double* logJ, double* layer_logJ,
+                              int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x_in || !x_out) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FLOW_FWD; a.B = B; a.field_in = x_in; a.field_out = x_out; a.s_out = logJ; a.layer_logJ = layer_logJ;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_flow_inv(fthmc_flow_t flow, const double* x_in, double* x_out, double* logJ, double* layer_logJ, int* iters,
+                              int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x_in || !x_out) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FLOW_INV; a.B = B; a.field_in = x_in; a.field_out = x_out; a.s_out = logJ; a.layer_logJ = layer_logJ;
+    a.iters = iters;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_ft_action(fthmc_flow_t flow, const double* x, double beta, double* out, double* flowed,
+                               int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x || !out) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FT_ACTION; a.B = B; a.field_in = x; a.field_out = flowed; a.s_out = out; a.beta = beta;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_ft_force(fthmc_flow_t flow, const double* x, double beta, double* force_out,
+                              int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x || !force_out) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FT_FORCE; a.B = B; a.field_in = x; a.field_out = force_out; a.beta = beta;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+static int leapfrog_common(fthmc_flow_t flow, int mode, const double* x_in, const double* p_in, double* x_out, double* p_out,
+                           int B, int L0, int L1, double beta, double dt, int nstep, void* ws, size_t ws_bytes, void* stream) {
+    if (!x_in || !p_in || !x_out || !p_out) return fail(FTHMC_E_ARG, "null pointer");
+    if (nstep < 1) return fail(FTHMC_E_ARG, "nstep must be >= 1");
+    ChainArgs a{}; a.mode = mode; a.B = B; a.field_in = x_in; a.p_in = p_in; a.field_out = x_out; a.p_out = p_out;
+    a.beta = beta; a.dt = dt; a.nstep = nstep;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_leapfrog(const double* x_in, const double* p_in, double* x_out, double* p_out, int B, int L0, int L1,
+                              double beta, double dt, int nstep, void* ws, size_t ws_bytes, void* stream) {
+    return leapfrog_common(nullptr, MODE_LEAPFROG, x_in, p_in, x_out, p_out, B, L0, L1, beta, dt, nstep, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_ft_leapfrog(fthmc_flow_t flow, const double* x_in, const double* p_in, double* x_out, double* p_out,
+                                 int B, int L0, int L1, double beta, double dt, int nstep, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow) return fail(FTHMC_E_ARG, "null flow");
+    return leapfrog_common(flow, MODE_FT_LEAPFROG, x_in, p_in, x_out, p_out, B, L0, L1, beta, dt, nstep, ws, ws_bytes, stream);
+}
+
+static int traj_common(fthmc_flow_t flow, int mode, const double* field_in, double* field_out, const double* p_in, const double* u_in,
+                       unsigned long long seed, unsigned long long traj, unsigned long long chain0,
+                       int B, int L0, int L1, double beta, double dt, int nstep,
+                       double* dH, double* exp_mdH, int* acc, double* plaq, double* topo, double* h0, double* h1,
+                       void* ws, size_t ws_bytes, void* stream) {
+    if (!field_in || !field_out) return fail(FTHMC_E_ARG, "null pointer");
+    if (nstep < 1) return fail(FTHMC_E_ARG, "nstep must be >= 1");
+    ChainArgs a{}; a.mode = mode; a.B = B; a.field_in = field_in; a.field_out = field_out; a.p_in = p_in; a.u_in = u_in;
+    a.seed = seed; a.traj = traj; a.chain0 = chain0; a.beta = beta; a.dt = dt; a.nstep = nstep;
+    a.s_out = dH; a.expmdH = exp_mdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
+    return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_hmc_traj(const double* x_in, double* x_out, const double* p_in, const double* u_in,
+                              unsigned long long seed, unsigned long long traj, unsigned long long chain0,
+                              int B, int L0, int L1, double beta, double dt, int nstep,
+                              double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
+                              void* ws, size_t ws_bytes, void* stream) {
+    return traj_common(nullptr, MODE_HMC, x_in, x_out, p_in, u_in, seed, traj, chain0, B, L0, L1, beta, dt, nstep,
+                       dH, exp_mdH, acc, plaq, topo, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int fthmc_ft_hmc_traj(fthmc_flow_t flow, const double* field_in, double* field_out, const double* p_in, const double* u_in,
+                                 unsigned long long seed, unsigned long long traj, unsigned long long chain0,
+                                 int B, int L0, int L1, double beta, double dt, int nstep,
+                                 double* dH, double* exp_mdH, int* acc, double* plaq, double* topo, double* h0, double* h1,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (!flow) return fail(FTHMC_E_ARG, "null flow");
+    return traj_common(flow, MODE_FT_HMC, field_in, field_out, p_in, u_in, seed, traj, chain0, B, L0, L1, beta, dt, nstep,
+                       dH, exp_mdH, acc, plaq, topo, h0, h1, ws, ws_bytes, stream);
+}

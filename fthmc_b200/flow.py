@@ -1,0 +1,99 @@
+"""Packing of a reference flow (`nn.ModuleList` of `GaugeEquivCouplingLayer`,
+ipynb/field_transformation.py:339-356) into the device-resident handle the kernels read."""
+import ctypes
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ACTIVATIONS = {"silu": 0, "swish": 0, "leaky_relu": 1, "relu": 2}
+RAW_PER_LAYER = 955
+
+
+def _activation_of(net):
+    for m in net:
+        name = type(m).__name__.lower()
+        if name == "silu":
+            return "silu"
+        if name == "leakyrelu":
+            return "leaky_relu"
+        if name == "relu":
+            return "relu"
+    return "silu"
+
+
+class PackedFlow:
+    """Immutable device copy of a flow's CNN weights + mask parameters (fthmc_flow_pack)."""
+
+    def __init__(self, raw, mu=None, off=None, activation="silu", convention=0, inv_prec=1e-6, inv_max_iter=1000,
+                 hidden=(8, 8), n_mix=2, ksize=3, device=None):
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        if raw.ndim != 2 or raw.shape[1] != RAW_PER_LAYER:
+            raise _lib.FthmcError(-5, f"expected (n_layers,{RAW_PER_LAYER}) raw weights, got {raw.shape}")
+        n = raw.shape[0]
+        self.n_layers = n
+        self.mu = np.ascontiguousarray([i % 2 for i in range(n)] if mu is None else mu, dtype=np.int32)
+        self.off = np.ascontiguousarray([(i // 2) % 4 for i in range(n)] if off is None else off, dtype=np.int32)
+        self.activation, self.convention = activation, int(convention)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fthmc_flow_pack(
+                raw.ctypes.data, n, self.mu.ctypes.data, self.off.ctypes.data, int(hidden[0]), int(hidden[1]),
+                int(n_mix), int(ksize), ACTIVATIONS[activation], self.convention, float(inv_prec), int(inv_max_iter),
+                ctypes.byref(h)))
+        self.handle = h
+        self._fin = weakref.finalize(self, _lib.lib().fthmc_flow_free, h)
+
+    def __len__(self):
+        return self.n_layers
+
+
+def raw_weights_of(flow_module):
+    """(n_layers,955) float64 in the reference's parameter order of layer.plaq_coupling.net."""
+    rows = []
+    for layer in flow_module:
+        convs = [m for m in layer.plaq_coupling.net if hasattr(m, "weight")]
+        shapes = [tuple(c.weight.shape) for c in convs]
+        if shapes != [(8, 2, 3, 3), (8, 8, 3, 3), (3, 8, 3, 3)]:
+            raise _lib.FthmcError(-5, f"unsupported CNN shape {shapes}: built for hidden_sizes=[8,8], "
+                                      "n_mixture_comps=2, kernel_size=3")
+        rows.append(np.concatenate([np.concatenate([c.weight.detach().double().cpu().numpy().ravel(),
+                                                    c.bias.detach().double().cpu().numpy().ravel()]) for c in convs]))
+    return np.stack(rows)
+
+
+_cache = {}
+
+
+def pack(flow, convention=0, device=None):
+    """PackedFlow for `flow`: a PackedFlow (returned as is) or a reference-style ModuleList.  Cached by
+    object identity + parameter versions, so repeated ft_hmc calls do not re-upload."""
+    if isinstance(flow, PackedFlow):
+        return flow
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    params = [p for layer in flow for p in layer.plaq_coupling.net.parameters()]
+    key = (id(flow), dev.index, convention)
+    ver = tuple((p.data_ptr(), p._version) for p in params)
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    layers = list(flow)
+    mu, off = [], []
+    for i, l in enumerate(layers):
+        m, o = i % 2, (i // 2) % 4            # make_u1_equiv_layers, ipynb/field_transformation.py:343-344
+        am = getattr(l, "active_mask", None)  # if the layer carries its link mask, read (mu, off) from it
+        if am is not None:
+            am = am.detach().cpu()
+            m = 0 if bool(am[0].any()) else 1
+            line = am[0][0, :] if m == 0 else am[1][:, 0]
+            o = int(torch.nonzero(line)[0])
+        mu.append(m)
+        off.append(o)
+    pc = layers[0].plaq_coupling
+    pf = PackedFlow(raw_weights_of(flow), mu=mu, off=off, activation=_activation_of(pc.net), convention=convention,
+                    inv_prec=getattr(pc, "inv_prec", 1e-6), inv_max_iter=getattr(pc, "inv_max_iter", 1000), device=dev)
+    _cache[key] = (ver, pf)
+    return pf

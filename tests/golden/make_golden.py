@@ -236,6 +236,65 @@ def gen_copyB(refroot, out):
     print("copyB_L8 done; roundtrip err", np.abs(wrap(torch.from_numpy(np.stack(invs)) - x)).max().item())
 
 
+def thousand_inputs(L, n=1000, seed=20261018):
+    """Deterministic inputs for the 1000-trajectory parity runs; regenerated (not stored) by the tests.
+    torch's CPU generator is bit-reproducible across machines."""
+    g = torch.Generator().manual_seed(seed)
+    amp = 0.2 + 1.3 * torch.rand(n, 1, 1, 1, generator=g, dtype=torch.float64)
+    x = amp * torch.randn(n, 2, L, L, generator=g, dtype=torch.float64)
+    p = torch.randn(n, 2, L, L, generator=g, dtype=torch.float64)
+    u = torch.rand(n, generator=g, dtype=torch.float64)
+    return x, p, u
+
+
+def patched_rng(p_next, u_next):
+    """Feed the reference's own randn_like / rand calls with prescribed draws."""
+    class Ctx:
+        def __enter__(self):
+            self.rl, self.r = torch.randn_like, torch.rand
+            torch.randn_like = lambda t, *a, **k: p_next.reshape(t.shape).clone()
+            torch.rand = lambda *a, **k: u_next.clone()
+        def __exit__(self, *e):
+            torch.randn_like, torch.rand = self.rl, self.r
+    return Ctx()
+
+
+def gen_thousand(plain, ftlib, ref, out):
+    """north_star: accept/reject and integer topological charge bit-exact over 1000 trajectories,
+    momenta and uniforms supplied from the reference run."""
+    L, n = 8, 1000
+    x, p, u = thousand_inputs(L, n)
+    # plain HMC, BASELINE config 1 parameters
+    P = plain.Param(beta=2.0, lat=(L, L), tau=1.0, nstep=10)
+    dH, acc, topo, chk = [], [], [], []
+    for i in range(n):
+        with patched_rng(p[i], u[i]):
+            d, e, a, new = plain.hmc(P, x[i].clone())
+        dH.append(float(d)); acc.append(bool(a)); topo.append(float(plain.topocharge(new))); chk.append(float(new.sum()))
+    np.savez_compressed(os.path.join(out, "plain_L8_1000.npz"), beta=2.0, dt=P.dt, nstep=10, L=L, dH=np.array(dH),
+                        acc=np.array(acc), topo=np.array(topo), field_sum=np.array(chk))
+    print("plain 1000: acc rate", np.mean(acc))
+    # FT-HMC, 8-layer flow (all mask arrangements), weights x2
+    torch.manual_seed(3647)
+    flow = ftlib.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=8, n_mixture_comps=2, hidden_sizes=[8, 8], kernel_size=3)
+    flow.eval()
+    with torch.no_grad():
+        for prm in flow.parameters():
+            prm.mul_(2.0)
+    for prm in flow.parameters():
+        prm.requires_grad_(False)
+    P = ref.Param(beta=2.0, lat=(L, L), tau=0.6, nstep=6)
+    dH, acc, topo, chk = [], [], [], []
+    for i in range(n):
+        with patched_rng(p[i][None], u[i]):
+            d, e, a, new = quiet(ref.ft_hmc, P, flow, x[i][None].clone())
+        dH.append(d); acc.append(bool(a)); topo.append(float(ref.topocharge(new[0]))); chk.append(float(new.sum()))
+    np.savez_compressed(os.path.join(out, "ft_L8_1000.npz"), beta=2.0, dt=P.dt, nstep=6, L=L, n_layers=8,
+                        weights=flat_weights(flow), activation="silu", convention=0, dH=np.array(dH), acc=np.array(acc),
+                        topo=np.array(topo), field_sum=np.array(chk))
+    print("ft 1000: acc rate", np.mean(acc), "dH range", np.min(dH), np.max(dH))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -249,6 +308,7 @@ def main():
     gen_flow_case(ftlib, ref, "ft_L32_b4_n40", a.out, L=32, beta=4.0, n_layers=24, B=1, nstep=40, ntraj=1,
                   tau=1.0)
     gen_leaky(plain, a.out)
+    gen_thousand(plain, ftlib, ref, a.out)
     try:
         gen_copyB(a.ref, a.out)
     except Exception as e:  # copy B is optional (it drags in the package's logger/config)

@@ -95,3 +95,21 @@ def test_rectangular_lattice_against_oracle():
     f = O.ft_force(2.5, flow, x)
     o = E.run("ft_force", raw, x.numpy(), beta=2.5)
     assert relerr(o["field"], f.numpy()) < 1e-11
+
+
+def test_thousand_trajectories_bit_exact_decisions(golden):
+    """north_star: accept/reject decisions and integer topological charges bit-exact over 1000
+    trajectories with the reference's momenta and uniforms; dH within 1e-8."""
+    from conftest import thousand_inputs
+    x, p, u = thousand_inputs(8)
+    g = golden("plain_L8_1000")
+    o = E.run("hmc", None, x.numpy(), beta=float(g["beta"]), dt=float(g["dt"]), nstep=int(g["nstep"]), p=p.numpy(), u=u.numpy())
+    assert np.max(np.abs(o["s"] - g["dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["acc"]) and np.array_equal(o["topo"], g["topo"])
+    assert np.max(np.abs(o["field"].sum(axis=(1, 2, 3)) - g["field_sum"])) < 1e-9
+    g = golden("ft_L8_1000")
+    o = E.run("ft_hmc", g["weights"], x.numpy(), beta=float(g["beta"]), dt=float(g["dt"]), nstep=int(g["nstep"]),
+              p=p.numpy(), u=u.numpy())
+    assert np.max(np.abs(o["s"] - g["dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["acc"]) and np.array_equal(o["topo"], g["topo"])
+    assert np.max(np.abs(o["field"].sum(axis=(1, 2, 3)) - g["field_sum"])) < 1e-7

@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the Python mirror -> C ABI -> sm_100a kernels) with
+  (a) golden vectors dumped from the real reference (tests/golden/*.npz), and
+  (b) the CPU oracle on fresh seeded inputs.
+Tolerances (north_star): action / force / log-det 1e-10 relative, dH 1e-8 absolute, accept/reject
+and integer topological charge bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import fthmc_b200 as ft
+from conftest import oracle_flow_from_golden, thousand_inputs
+from oracle import fthmc_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+REL = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def wrap(x):
+    return np.remainder(x + np.pi, 2 * np.pi) - np.pi
+
+
+def packed(g):
+    return ft.PackedFlow(g["weights"], activation=str(g["activation"]), convention=int(g["convention"]))
+
+
+# ---------------------------------------------------------------- plain stencils
+def test_plain_pointwise_golden(golden):
+    g = golden("plain_L8")
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=1.0, nstep=10)
+    x = T(g["x0"])
+    assert abs(float(ft.action(P, x)) - float(g["action"])) <= REL * abs(float(g["action"]))
+    assert relerr(ft.force(P, x).numpy(), g["force"]) < REL
+    assert float(ft.topocharge(x)) == float(g["topo"])
+    assert np.max(np.abs(ft.regularize(T(g["reg_in"])).numpy() - g["reg_out"])) < 1e-15
+    lx, lp = ft.leapfrog(P, x, T(g["lf_p"]))
+    assert np.max(np.abs(lx.numpy() - g["lf_x_out"])) < 1e-12 and np.max(np.abs(lp.numpy() - g["lf_p_out"])) < 1e-12
+    z = torch.zeros(2, 8, 8)
+    assert float(ft.action(P, z)) / (-P.beta * P.volume) == 1.0 and float(ft.topocharge(z)) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 4), (7, 8, 12), (5, 32, 32), (3, 64, 64), (2, 256, 128)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_stencils_vs_oracle(shape, dtype):
+    B, L0, L1 = shape
+    gen = torch.Generator().manual_seed(B * 1000 + L0)
+    x = (torch.rand(B, 2, L0, L1, generator=gen, dtype=torch.float64) * 2 - 1) * 3.0
+    xd = x.to(dtype).cuda()
+    P = ft.Param(beta=2.5, lat=(L0, L1))
+    tol = REL if dtype == torch.float64 else 2e-5
+    x64 = xd.double().cpu()
+    act = torch.stack([O.action(2.5, x64[b]) for b in range(B)])
+    assert relerr(ft.action(P, xd).double().cpu().numpy(), act.numpy()) < tol
+    assert relerr(ft.u1_action(2.5, xd).double().cpu().numpy(), O.u1_action(2.5, x64).numpy()) < tol
+    frc = torch.stack([O.force_closed_form(2.5, x64[b]) for b in range(B)])
+    assert relerr(ft.force(P, xd).double().cpu().numpy(), frc.numpy()) < (tol if dtype == torch.float64 else 1e-4)
+    if dtype == torch.float64:
+        q = torch.stack([O.topocharge(x64[b]) for b in range(B)])
+        assert np.array_equal(ft.topocharge(xd).cpu().numpy(), q.numpy())
+        assert np.max(np.abs(ft.topo_charge(xd).cpu().numpy() - O.topo_charge(x64).numpy())) < 1e-9
+        assert np.array_equal(ft.regularize(xd).cpu().numpy(), O.regularize(x64).numpy())
+
+
+# ---------------------------------------------------------------- plain HMC
+def test_plain_hmc_teacher_forced_golden(golden):
+    g = golden("plain_L8")
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=1.0, nstep=int(g["nstep"]))
+    r = ft.hmc_batch(P, T(g["traj_x"]), T(g["traj_p"]), T(g["traj_u"]))
+    assert np.max(np.abs(r["dH"].numpy() - g["traj_dH"])) < 1e-8
+    assert np.array_equal(r["acc"].numpy(), g["traj_acc"])
+    assert np.array_equal(r["topo"].numpy(), g["traj_topo"])
+    assert np.max(np.abs(r["field"].numpy() - g["traj_out"])) < 1e-10
+    assert np.max(np.abs(r["plaq"].numpy() - g["traj_plaq"])) < 1e-12
+
+
+def test_plain_hmc_dropin_reproduces_reference_chain(golden):
+    """hmc(param,x) draws p,u from torch's generator in the reference's order: same seed, same chain."""
+    g = golden("plain_L8")
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=1.0, nstep=int(g["nstep"]))
+    cur = T(g["traj_x"][0]).clone()
+    for n in range(12):
+        torch.manual_seed(5000 + n)
+        dH, e, acc, cur = ft.hmc(P, cur)
+        assert abs(float(dH) - g["traj_dH"][n]) < 1e-8 and bool(acc) == bool(g["traj_acc"][n])
+        assert abs(float(e) - np.exp(-g["traj_dH"][n])) < 1e-8
+    assert np.max(np.abs(cur.numpy() - g["traj_out"][11])) < 1e-9
+
+
+def test_thousand_trajectories_plain(golden):
+    g = golden("plain_L8_1000")
+    x, p, u = thousand_inputs(8)
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=1.0, nstep=int(g["nstep"]))
+    r = ft.hmc_batch(P, x, p, u)
+    assert np.max(np.abs(r["dH"].numpy() - g["dH"])) < 1e-8
+    assert np.array_equal(r["acc"].numpy(), g["acc"])
+    assert np.array_equal(r["topo"].numpy(), g["topo"])
+    assert np.max(np.abs(r["field"].sum(dim=(1, 2, 3)).numpy() - g["field_sum"])) < 1e-9
+
+
+# ---------------------------------------------------------------- flow
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4"])
+def test_flow_forward_action_force_golden(golden, name):
+    g = golden(name)
+    pf = packed(g)
+    L = int(g["L"])
+    P = ft.Param(beta=float(g["beta"]), lat=(L, L))
+    x = T(g["x"])
+    y, lj = ft.ft_flow(pf, x, with_logJ=True)
+    assert np.max(np.abs(y.numpy() - g["flow_fwd"])) < 1e-11
+    assert relerr(lj.numpy(), g["layer_logJ"].sum(axis=0)) < REL
+    assert relerr(ft.ft_action(P, pf, x).numpy(), g["ft_action"]) < REL
+    assert relerr(ft.ft_force(P, pf, x).numpy(), g["ft_force"]) < REL
+
+
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4"])
+def test_flow_inverse_golden(golden, name):
+    g = golden(name)
+    pf = packed(g)
+    xi = ft.ft_flow_inv(pf, T(g["flow_fwd"]))
+    # same bisection decisions => the same dyadic midpoints (agreement far below the 1e-6 tolerance)
+    assert np.max(np.abs(xi.numpy() - g["flow_inv_of_fwd"])) < 1e-10
+    assert np.max(np.abs(wrap(xi.numpy() - g["x"]))) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["leaky_L8", "copyB_L8"])
+def test_variants_golden(golden, name):
+    g = golden(name)
+    pf = packed(g)
+    y, lj = ft.ft_flow(pf, T(g["x"]), with_logJ=True)
+    assert np.max(np.abs(y.numpy() - g["flow_fwd"])) < 1e-11 and relerr(lj.numpy(), g["logJ"]) < REL
+    xi = ft.ft_flow_inv(pf, T(g["flow_fwd"]))
+    assert np.max(np.abs(xi.numpy() - g["flow_inv_of_fwd"])) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["ft_L8_n8", "ft_L16_b6", "ft_L32_b4", "ft_L32_b4_n40"])
+def test_ft_hmc_teacher_forced_golden(golden, name):
+    g = golden(name)
+    pf = packed(g)
+    L = int(g["L"])
+    P = ft.Param(beta=float(g["beta"]), lat=(L, L), tau=float(g["dt"]) * int(g["nstep"]), nstep=int(g["nstep"]))
+    r = ft.ft_hmc_batch(P, pf, T(g["traj_x"]), T(g["traj_p"]), T(g["traj_u"]))
+    assert np.max(np.abs(r["dH"].numpy() - g["traj_dH"])) < 1e-8
+    assert np.array_equal(r["acc"].numpy(), g["traj_acc"])
+    assert np.array_equal(r["topo"].numpy(), g["traj_topo"])
+    assert np.max(np.abs(r["plaq"].numpy() - g["traj_plaq"])) < 1e-11
+    assert np.max(np.abs(r["field"].numpy() - g["traj_out"])) < 1e-8
+
+
+def test_thousand_trajectories_ft(golden):
+    g = golden("ft_L8_1000")
+    pf = packed(g)
+    x, p, u = thousand_inputs(8)
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=float(g["dt"]) * int(g["nstep"]), nstep=int(g["nstep"]))
+    r = ft.ft_hmc_batch(P, pf, x, p, u)
+    assert np.max(np.abs(r["dH"].numpy() - g["dH"])) < 1e-8
+    assert np.array_equal(r["acc"].numpy(), g["acc"])
+    assert np.array_equal(r["topo"].numpy(), g["topo"])
+    assert np.max(np.abs(r["field"].sum(dim=(1, 2, 3)).numpy() - g["field_sum"])) < 1e-7
+
+
+def test_ft_hmc_dropin_signature(golden):
+    """ft_hmc(param, flow, field) on the reference's own kind of flow object (an nn.ModuleList-like
+    container exposing layer.plaq_coupling.net), CPU tensors in, CPU tensors out."""
+    g = golden("ft_L8_n8")
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8), tau=float(g["dt"]) * int(g["nstep"]), nstep=int(g["nstep"]))
+    flow = module_like(g)
+    torch.manual_seed(7000)
+    dH, e, acc, new = ft.ft_hmc(P, flow, T(g["traj_x"][0][None]))
+    assert isinstance(dH, float) and isinstance(e, float) and acc.dtype == torch.bool and new.shape == (1, 2, 8, 8)
+    assert abs(dH - g["traj_dH"][0]) < 1e-8 and bool(acc) == bool(g["traj_acc"][0])
+    assert np.max(np.abs(new.numpy()[0] - g["traj_out"][0])) < 1e-8
+
+
+def module_like(g):
+    """Stand-in for the reference's ModuleList of GaugeEquivCouplingLayer (same attribute names)."""
+    import torch.nn as nn
+    shapes = [(8, 2, 3, 3), (8,), (8, 8, 3, 3), (8,), (3, 8, 3, 3), (3,)]
+
+    class PlaqCoupling(nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net, self.inv_prec, self.inv_max_iter = net, 1e-6, 1000
+
+    class Layer(nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.plaq_coupling = PlaqCoupling(net)
+
+    layers = []
+    for row in g["weights"]:
+        convs = [nn.Conv2d(2, 8, 3, padding=1, padding_mode="circular"), nn.Conv2d(8, 8, 3, padding=1, padding_mode="circular"),
+                 nn.Conv2d(8, 3, 3, padding=1, padding_mode="circular")]
+        pos = 0
+        with torch.no_grad():
+            for c, (ws, bs) in zip(convs, zip(shapes[0::2], shapes[1::2])):
+                n = int(np.prod(ws)); c.weight.copy_(T(row[pos:pos + n].reshape(ws))); pos += n
+                n = int(np.prod(bs)); c.bias.copy_(T(row[pos:pos + n].reshape(bs))); pos += n
+        layers.append(Layer(nn.Sequential(convs[0], nn.SiLU(), convs[1], nn.SiLU(), convs[2])))
+    return nn.ModuleList(layers).double()
+
+
+# ---------------------------------------------------------------- fresh inputs vs the oracle
+@pytest.mark.parametrize("shape", [(3, 8, 8), (2, 8, 12), (2, 16, 16), (1, 12, 20)])
+@pytest.mark.parametrize("act", ["silu", "leaky_relu", "relu"])
+def test_flow_vs_oracle_fresh(shape, act):
+    B, L0, L1 = shape
+    flow = O.random_flow(n_layers=8, seed=B + L0 + L1, activation=act, scale=2.5)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                    for lw in flow.layers])
+    pf = ft.PackedFlow(raw, activation=act)
+    gen = torch.Generator().manual_seed(17)
+    x = (torch.rand(B, 2, L0, L1, generator=gen, dtype=torch.float64) * 2 - 1) * 4.0     # un-wrapped angles
+    P = ft.Param(beta=3.0, lat=(L0, L1))
+    y, lj = O.ft_flow_logJ(flow, x)
+    yg, ljg = ft.ft_flow(pf, x.cuda(), with_logJ=True)
+    assert yg.is_cuda and np.max(np.abs(yg.cpu().numpy() - y.numpy())) < 1e-11
+    assert relerr(ljg.cpu().numpy(), lj.numpy()) < REL
+    assert relerr(ft.ft_action(P, pf, x).numpy(), O.ft_action(3.0, flow, x).numpy()) < REL
+    assert relerr(ft.ft_force(P, pf, x).numpy(), O.ft_force(3.0, flow, x).numpy()) < REL
+    for b in range(B):
+        xi = O.ft_flow_inv(flow, y[b:b + 1])
+        assert np.max(np.abs(ft.ft_flow_inv(pf, y[b:b + 1]).numpy() - xi.numpy())) < 1e-10
+
+
+def test_ft_leapfrog_vs_oracle():
+    flow = O.random_flow(n_layers=8, seed=5, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                    for lw in flow.layers])
+    pf = ft.PackedFlow(raw)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 2, 8, 8, generator=gen, dtype=torch.float64) * 6 - 3
+    p = torch.randn(2, 2, 8, 8, generator=gen, dtype=torch.float64)
+    P = ft.Param(beta=2.0, lat=(8, 8), tau=0.5, nstep=5)
+    xo, po = O.ft_leapfrog(2.0, P.dt, 5, flow, x, p)
+    xg, pg = ft.ft_leapfrog(P, pf, x, p)
+    assert np.max(np.abs(xg.numpy() - xo.numpy())) < 1e-10 and np.max(np.abs(pg.numpy() - po.numpy())) < 1e-10
+
+
+# ---------------------------------------------------------------- size-independent properties at full size
+def test_full_size_properties_L32():
+    """BASELINE config 3 shape (L=32, beta=4, 24 layers) at B=296 (two waves of the persistent grid):
+    round trip to the bisection tolerance, logJ antisymmetry, gauge invariance, chain independence of
+    batching, Philox determinism, reversibility of the integrator."""
+    flow = O.random_flow(n_layers=24, seed=3647)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                    for lw in flow.layers])
+    pf = ft.PackedFlow(raw)
+    B, L = 296, 32
+    gen = torch.Generator().manual_seed(1331)
+    x = ((torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+    P = ft.Param(beta=4.0, lat=(L, L), tau=1.0, nstep=10)
+    y, lj = ft.ft_flow(pf, x, with_logJ=True)
+    xi, lji = ft.ft_flow_inv(pf, y, with_logJ=True)
+    assert float(torch.max(torch.abs(torch.remainder(xi - x + np.pi, 2 * np.pi) - np.pi))) < 5e-5
+    assert float(torch.max(torch.abs(lj + lji))) < 1e-3
+    # gauge invariance of action / charge / logJ, equivariance of the flow
+    alpha = torch.rand(B, L, L, generator=gen, dtype=torch.float64).cuda() * 2 * np.pi
+    xg = x.clone()
+    xg[:, 0] = alpha + x[:, 0] - torch.roll(alpha, -1, 1)
+    xg[:, 1] = alpha + x[:, 1] - torch.roll(alpha, -1, 2)
+    assert float(torch.max(torch.abs(ft.u1_action(4.0, x) - ft.u1_action(4.0, xg)))) < 1e-8
+    assert torch.equal(ft.topocharge(x), ft.topocharge(xg))
+    yg, ljg = ft.ft_flow(pf, xg, with_logJ=True)
+    assert float(torch.max(torch.abs(lj - ljg))) < 1e-8
+    assert float(torch.max(torch.abs(ft.ft_action(P, pf, x) - ft.ft_action(P, pf, xg)))) < 1e-7
+    # a chain's result does not depend on which CTA / batch position ran it
+    f_all = ft.ft_force(P, pf, x)
+    f_one = ft.ft_force(P, pf, x[200:201])
+    assert torch.equal(f_all[200:201], f_one)
+    # oracle spot-check of one chain at full size
+    fo = O.ft_force(4.0, flow, x[5:6].cpu())
+    assert relerr(f_all[5:6].cpu().numpy(), fo.numpy()) < REL
+    # Philox throughput mode: deterministic in (seed, chain, traj), different across chains
+    r1 = ft.ft_hmc_batch(P, pf, x[:150], seed=11, traj=3)
+    r2 = ft.ft_hmc_batch(P, pf, x[:150], seed=11, traj=3)
+    assert torch.equal(r1["field"], r2["field"]) and torch.equal(r1["dH"], r2["dH"])
+    r3 = ft.ft_hmc_batch(P, pf, x[100:150], seed=11, traj=3, chain0=100)
+    assert torch.equal(r1["field"][100:150], r3["field"]) and torch.equal(r1["acc"][100:150], r3["acc"])
+    assert float(torch.std(r1["dH"])) > 0
+    q = r1["topo"]
+    assert torch.equal(q, torch.round(q)) and torch.equal(q, ft.topocharge(r1["field"]))
+    # leapfrog reversibility: integrate, flip momenta, integrate back
+    p = torch.randn(8, 2, L, L, generator=gen, dtype=torch.float64).cuda()
+    xa, pa = ft.ft_leapfrog(P, pf, x[:8], p)
+    xb, pb = ft.ft_leapfrog(P, pf, xa, -pa)
+    assert float(torch.max(torch.abs(xb - x[:8]))) < 1e-9 and float(torch.max(torch.abs(pb + p))) < 1e-9
+
+
+def test_errors_are_loud():
+    P = ft.Param(beta=1.0, lat=(6, 6))
+    with pytest.raises(ft.FthmcError) as e:
+        ft.hmc_batch(P, torch.zeros(1, 2, 6, 6))
+    assert e.value.code == -2
+    flow = O.random_flow(n_layers=2, seed=1)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                    for lw in flow.layers])
+    pf = ft.PackedFlow(raw)
+    with pytest.raises(ft.FthmcError) as e:
+        ft.ft_flow(pf, torch.zeros(1, 2, 64, 64))       # does not fit one SM's shared memory
+    assert e.value.code == -2
+    with pytest.raises(ft.FthmcError):
+        ft.PackedFlow(np.zeros((2, 900)))
