@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""bench.py -- FT-HMC trajectories/s at L=32, beta=4 (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one FT-HMC trajectory for every chain of the per-GPU batch (BASELINE config 3: 4096 chains,
+L=32, beta=4, the reference's 24-layer random-init flow, tau=1, nstep=10), i.e. ONE launch of the
+persistent one-CTA-per-chain kernel through the C ABI, followed by the observables reduction
+(plaquette, Q, Q^2, acceptance, dH, exp(-dH)), which is all-reduced over NCCL when N>1.  Chains are
+independent, so ranks shard them with no data-path collective ("weak" scaling: 4096 chains per GPU).
+
+Prints ONE JSON line (rank 0).  `value` = chain-trajectories/s with the fields resident in HBM;
+`e2e` = the same through the public API with HOST tensors (H2D + kernel + D2H inside the timed region).
+`--impl reference` times the CPU port of the reference path (oracle/, torch fp64 on the host cores) on a
+bounded sample of the same workload: one chain-trajectory per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "ft_hmc_trajectories_per_sec"
+UNIT = "trajectories/s"
+# algorithmic work per chain-trajectory, W = N*V*[nstep*3744 + 4*1872] flop
+FLOP_PER_SITE_FORCE, FLOP_PER_SITE_FWD = 3744, 1872
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--L", type=int, default=32)
+    ap.add_argument("--beta", type=float, default=4.0)
+    ap.add_argument("--tau", type=float, default=1.0)
+    ap.add_argument("--nstep", type=int, default=10)
+    ap.add_argument("--layers", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"FT-HMC 2D U(1) L={a.L} beta={a.beta} {a.chains} chains/GPU, {a.layers}-layer random-init flow "
+            f"(seed 3647), tau={a.tau} nstep={a.nstep}, fp64")
+
+
+def alg_flop_per_chain_traj(a):
+    return a.layers * a.L * a.L * (a.nstep * FLOP_PER_SITE_FORCE + 4 * FLOP_PER_SITE_FWD)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (bench.py may execute oracle/ only here)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_setup(a):
+    from oracle import fthmc_oracle as O
+    from fthmc_b200.flow import default_init_raw
+    torch.set_default_dtype(torch.float64)
+    raw = default_init_raw(a.layers, 3647)
+    shapes = [(8, 2, 3, 3), (8,), (8, 8, 3, 3), (8,), (3, 8, 3, 3), (3,)]
+    layers = []
+    for i, row in enumerate(raw):
+        parts, pos = [], 0
+        for shp in shapes:
+            n = int(np.prod(shp))
+            parts.append(torch.from_numpy(row[pos:pos + n].reshape(shp).copy()))
+            pos += n
+        layers.append(O.LayerWeights(w=parts[0::2], b=parts[1::2], mu=i % 2, off=(i // 2) % 4))
+    flow = O.Flow(layers=layers)
+    torch.manual_seed(1331)
+    field = torch.empty(1, 2, a.L, a.L).uniform_(-np.pi, np.pi)
+    return O, flow, field
+
+
+def cpu_port_traj(O, flow, field, a):
+    t = time.perf_counter()
+    dH, e, acc, field = O.ft_hmc(a.beta, a.tau / a.nstep, a.nstep, flow, field)
+    return time.perf_counter() - t, field
+
+
+def cpu_baseline(a, budget_s):
+    O, flow, field = cpu_port_setup(a)
+    dt, field = cpu_port_traj(O, flow, field, a)        # warm-up
+    times, t0 = [], time.perf_counter()
+    while len(times) < 2 or (time.perf_counter() - t0 < budget_s and len(times) < 12):
+        dt, field = cpu_port_traj(O, flow, field, a)
+        times.append(dt)
+    return {"value": len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} single-chain ft_hmc trajectories of the same workload (oracle/fthmc_oracle.py, "
+                      f"torch {torch.__version__} CPU fp64, autograd force), after 1 warm-up"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, flow, field = cpu_port_setup(a)
+    for _ in range(max(1, min(a.warmup, 1))):
+        _, field = cpu_port_traj(O, flow, field, a)
+    tot = 0.0
+    for _ in range(a.steps):
+        dt, field = cpu_port_traj(O, flow, field, a)
+        tot += dt
+    val = a.steps / tot
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "step": "one chain-trajectory on the host CPU (bounded sample)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{a.steps} single-chain ft_hmc trajectories (oracle port of ipynb/ft_hmc.py:420)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    import fthmc_b200 as ft
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_default_dtype(torch.float64)
+    L, B = a.L, a.chains
+    lib = ft.lib()
+    pf = ft.PackedFlow(ft.default_init_raw(a.layers, 3647))
+    P = ft.Param(beta=a.beta, lat=(L, L), tau=a.tau, nstep=a.nstep)
+    gen = torch.Generator().manual_seed(1331 + rank)
+    host = torch.empty(B, 2, L, L, dtype=torch.float64).uniform_(-np.pi, np.pi, generator=gen).pin_memory()
+    x = host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    obs = torch.zeros(7, dtype=torch.float64, device=dev)
+
+    def step(xin, it):
+        """one trajectory for every chain + the observables reduction (all-reduced when N>1)"""
+        r = ft.ft_hmc_batch(P, pf, xin, seed=20261018, traj=it, chain0=rank * B)
+        q = r["topo"]
+        o = torch.stack([r["plaq"].sum(), q.sum(), (q * q).sum(), r["acc"].double().sum(), r["dH"].sum(),
+                         r["exp_mdH"].sum(), torch.tensor(float(B), device=q.device)])
+        if world > 1:
+            dist.all_reduce(o)
+        return r, o
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    it = 0
+    for _ in range(a.warmup):
+        r, obs = step(x, it); x = r["field"]; it += 1
+    # ---- value: fields resident in HBM; per-step CUDA events, L2 flushed between steps (not timed) ----
+    clocks = Clocks(local)
+    sync_all()
+    clocks.start()
+    n0 = lib.fthmc_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(a.steps)]
+    for k in range(a.steps):
+        flush.zero_()
+        ev[k][0].record()
+        r = ft.ft_hmc_batch(P, pf, x, seed=20261018, traj=it, chain0=rank * B)
+        ev[k][1].record()                                   # the dominant kernel alone
+        q = r["topo"]
+        obs = torch.stack([r["plaq"].sum(), q.sum(), (q * q).sum(), r["acc"].double().sum(), r["dH"].sum(),
+                           r["exp_mdH"].sum(), torch.tensor(float(B), device=dev)])
+        if world > 1:
+            dist.all_reduce(obs)
+        ev[k][2].record()
+        x = r["field"]; it += 1
+    sync_all()
+    launches = lib.fthmc_launch_count() - n0
+    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
+    kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_ms = float(tot_ms)
+    clk = clocks.stop()
+    value = world * B * a.steps / (tot_ms * 1e-3)
+    obs_h = obs.cpu().numpy()
+
+    # ---- e2e: HOST tensors through the public API: H2D + kernel + D2H of fields and observables ----
+    sync_all()
+    e2e_ms = 0.0
+    hx = host
+    for k in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = ft.ft_hmc_batch(P, pf, hx, seed=20261018, traj=it, chain0=rank * B)    # CPU in -> CPU out
+        e1.record(); torch.cuda.synchronize()
+        e2e_ms += e0.elapsed_time(e1)
+        hx = r["field"]; it += 1
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * a.steps / (float(t) * 1e-3)
+    h2d = B * 2 * L * L * 8
+    d2h = B * 2 * L * L * 8 + B * (5 * 8 + 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_chain): fp64 FMA pipe; HBM term stated beside it ----
+    scratch = torch.zeros(16, dtype=torch.float64, device=dev)
+    import ctypes
+    flop = ctypes.c_double()
+    best = 1e30
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ft._lib.check(lib.fthmc_diag_dfma_probe(scratch.data_ptr(), 20000, 148 * 8, torch.cuda.current_stream().cuda_stream,
+                                                ctypes.byref(flop)))
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    fp64_peak = flop.value / (best * 1e-3) / 1e12
+    kms = float(np.mean(kern_ms))
+    alg_flop = alg_flop_per_chain_traj(a) * B
+    achieved = alg_flop / (kms * 1e-3) / 1e12
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    alg_bytes = B * (2 * L * L * 8 * 2 + 32)
+    roof = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": None, "kernel": "k_chain", "kernel_ms": kms,
+            "peak_source": "fp64 DFMA probe kernel timed in this run (MEASURED_PEAKS.json carries no fp64 figure); "
+                           "nominal B200 fp64 is 37 TFLOP/s",
+            "alg_flop_per_chain_traj": alg_flop_per_chain_traj(a),
+            "hbm_term": {"alg_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "chains_total": world * B, "lattice": [L, L], "beta": a.beta,
+                       "n_layers": a.layers, "tau": a.tau, "nstep": a.nstep, "parallelism": f"chains sharded over {world} GPU(s)",
+                       "momenta": "device Philox4x32-10", "l2": "256 MiB flush between timed steps",
+                       "observables_allreduce": world > 1},
+            "roofline": roof,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clk,
+            "observables": {"plaq": float(obs_h[0] / obs_h[6]), "acc_rate": float(obs_h[3] / obs_h[6]),
+                            "mean_dH": float(obs_h[4] / obs_h[6]), "Q2": float(obs_h[2] / obs_h[6])}}
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -207,6 +207,32 @@ __global__ void k_regularize(const T* __restrict__ in, T* __restrict__ out, long
         out[i] = regularize_t(in[i]);
 }
 
+// fp64 FMA-pipe peak probe (roofline denominator for the resident-chain kernel; MEASURED_PEAKS.json has no
+// fp64 entry).  16 independent DFMA chains per thread; 2*16*iters flop per thread.
+__global__ void __launch_bounds__(256) k_dfma_probe(double* __restrict__ out, int iters) {
+    double a[16];
+    const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-12 * blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;      // keep the chains alive
+}
+
+extern "C" int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out) {
+    if (!scratch || iters <= 0 || blocks <= 0) return fail(FTHMC_E_ARG, "bad probe arguments");
+    k_dfma_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)scratch, iters);
+    g_launches++;
+    CK(cudaGetLastError());
+    if (flop_out) *flop_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------------

@@ -97,3 +97,26 @@ def pack(flow, convention=0, device=None):
                     inv_prec=getattr(pc, "inv_prec", 1e-6), inv_max_iter=getattr(pc, "inv_max_iter", 1000), device=dev)
     _cache[key] = (ver, pf)
     return pf
+
+
+def default_init_raw(n_layers=24, seed=3647):
+    """Raw weights of the reference's random-init flow: `torch.manual_seed(seed)` followed by
+    `make_u1_equiv_layers(n_layers, n_mixture_comps=2, hidden_sizes=[8,8], kernel_size=3)` in fp64
+    (ipynb/ft_hmc.py:519, 310-315).  The reference's `set_weights(layers)` is a no-op on a ModuleList,
+    so "random init" is PyTorch's default Conv2d init, drawn in construction order; this re-draws the
+    same stream (checked bit-for-bit against the reference in tests/test_host_logic.py)."""
+    st = torch.get_rng_state()
+    old = torch.get_default_dtype()
+    try:
+        torch.set_default_dtype(torch.float64)
+        torch.manual_seed(seed)
+        rows = []
+        for _ in range(n_layers):
+            convs = [torch.nn.Conv2d(ci, co, 3, padding=1, stride=1, padding_mode="circular")
+                     for ci, co in ((2, 8), (8, 8), (8, 3))]
+            rows.append(np.concatenate([np.concatenate([c.weight.detach().numpy().ravel(), c.bias.detach().numpy().ravel()])
+                                        for c in convs]))
+    finally:
+        torch.set_default_dtype(old)
+        torch.set_rng_state(st)
+    return np.stack(rows)

@@ -106,6 +106,10 @@ int fthmc_ft_hmc_traj(fthmc_flow_t flow, const double* field_in, double* field_o
                       double* dH, double* exp_mdH, int* acc, double* plaq, double* topo, double* h0, double* h1,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* diagnostic: launch `blocks` x 256 threads of pure fp64 FMA chains (2*16*iters flop per thread); *flop_out (host)
+ * receives the flop count.  Used by bench.py to measure the fp64 roofline denominator on the device. */
+int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);
+
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 unsigned long long fthmc_launch_count(void);
 
