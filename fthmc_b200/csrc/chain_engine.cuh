@@ -144,6 +144,8 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 // ------------------------------------------------------------------------------------------------
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
+//   E::smem()                         base of the chain's shared-memory arena (address space known to nvcc)
+//   E::async_copy(dst_smem, src_global, ndoubles), E::async_commit(), E::async_wait<N>()   (cp.async groups)
 // ------------------------------------------------------------------------------------------------
 struct LayerGeom {
     int mu, off;
@@ -163,22 +165,24 @@ struct EngineParams {
     const int* loff;       // global: per layer off
 };
 
+// Shared-memory arena (doubles).  Flow: X GR | CS UA OUT | A(8V) B(6V) C(6V) | W.   Plain HMC: X GR | S(V).
 FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true) {
     size_t V = (size_t)L0 * L1, LP = L1 + 1;
-    if (!flow) return 2 * L0 * LP * 2 + V + 64 + 4;      // X, GR, one scratch plane
-    return 2 * L0 * LP * 2      // X, GR
-         + V                    // CS
-         + V / 4                // UA
-         + 3 * (V / 4)          // OUT
-         + 8 * V + 6 * V + 6 * V// A, B, C
-         + PACK_DOUBLES + 4     // W (+pad)
-         + 64;                  // reduction scratch
+    if (!flow) return 2 * L0 * LP * 2 + V + 4;
+    return 2 * L0 * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 4;
 }
 
-// per-CTA global workspace (doubles): momenta, x0, y0, saved active links
+// Per-layer block of the per-CTA global workspace written by the forward sweep of ft_force and read
+// back (cp.async) by the reverse sweep: act'(z1) [8V], act'(z2) [6V], cos/sin of the frozen
+// plaquettes [V], (s_1,s_2) of the active sites [2 V/4], pre-update active links [V/4].
+FT_HD size_t engine_layer_ws_doubles(int L0, int L1) {
+    size_t V = (size_t)L0 * L1;
+    return 15 * V + 3 * (V / 4);
+}
+// per-CTA global workspace (doubles): momenta, x0, y0, then nlayers layer blocks
 FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers) {
     size_t V = (size_t)L0 * L1;
-    return 3 * 2 * V + (size_t)nlayers * (V / 4);
+    return 3 * 2 * V + (size_t)nlayers * engine_layer_ws_doubles(L0, L1);
 }
 
 template <class E>
@@ -186,30 +190,38 @@ struct Engine {
     E& ex;
     EngineParams pr;
     int L0, L1, LP, V, VQ;
-    double *X, *GR, *CS, *UA, *OUT, *A, *B, *C, *W;
-    double *wsP, *wsX0, *wsY0, *wsSave;   // global per-CTA workspace
-    int* iters_out;                        // optional global: bisection iterations per layer (diagnostics)
+    int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS;   // arena offsets (doubles)
+    double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
+    size_t layStride;
+    int* iters_out;                                    // optional global: bisection iterations per layer
 
-    FT_HD Engine(E& e, const EngineParams& p, double* smem, double* ws) : ex(e), pr(p) {
+    FT_HD Engine(E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
         L0 = p.L0; L1 = p.L1; LP = L1 + 1; V = L0 * L1; VQ = V / 4;
-        double* s = smem;
-        X = s;   s += 2 * L0 * LP;
-        GR = s;  s += 2 * L0 * LP;
-        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsSave = ws + 6 * V;
+        int o = 0;
+        oX = o;  o += 2 * L0 * LP;
+        oGR = o; o += 2 * L0 * LP;
+        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsLay = ws + 6 * V;
+        layStride = engine_layer_ws_doubles(L0, L1);
         iters_out = nullptr;
-        if (p.nlayers == 0) {               // plain HMC: only a scratch plane is needed
-            A = s; CS = UA = OUT = B = C = W = nullptr;
-            return;
-        }
-        CS = s;  s += V;
-        UA = s;  s += VQ;
-        OUT = s; s += 3 * VQ;
-        s += ((uintptr_t)s & 8) ? 1 : 0;      // 16-byte align the planes/weights
-        A = s;   s += 8 * V;
-        B = s;   s += 6 * V;
-        C = s;   s += 6 * V;
-        W = s;   s += PACK_DOUBLES;
+        oCS = oUA = oOUT = oA = oB = oC = oW = 0;
+        if (p.nlayers == 0) { oS = o; return; }        // plain HMC: only a scratch plane
+        oCS = o;  o += V;
+        oUA = o;  o += VQ;
+        oOUT = o; o += 3 * VQ;
+        o += (o & 1);                                  // 16-byte alignment of the big planes / weights
+        oA = o;   o += 8 * V;
+        oB = o;   o += 6 * V;
+        oC = o;   o += 6 * V;
+        oW = o;   o += PACK_DOUBLES;
+        oS = oB;                                       // Wilson-force scratch plane aliases B
     }
+    FT_HD double* sm(int off) const { return ex.smem() + off; }
+    // layer block pieces in the global workspace
+    FT_HD double* wsD1(int l) const { return wsLay + (size_t)l * layStride; }
+    FT_HD double* wsD2(int l) const { return wsD1(l) + 8 * (size_t)V; }
+    FT_HD double* wsCS(int l) const { return wsD2(l) + 6 * (size_t)V; }
+    FT_HD double* wsSO(int l) const { return wsCS(l) + V; }
+    FT_HD double* wsSV(int l) const { return wsSO(l) + 2 * VQ; }
 
     // ---- geometry ----
     FT_HD LayerGeom geom(int l) const {
@@ -227,20 +239,22 @@ struct Engine {
         if (g.mu == 0) { n0 = r; n1 = co; } else { n0 = co; n1 = r; }
     }
     // plaquette angle; order 0: ipynb/field_transformation.py:118-119, order 1: qed_helpers.py:83-86 / hmc_2dU1.py:114-120
-    FT_HD double plaq(int n0, int n1, int order) const {
+    FT_HD double plaq(const double* X, int n0, int n1, int order) const {
         int n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1p = n1 + 1 == L1 ? 0 : n1 + 1;
         double a = X[xi(0, n0, n1)], b = X[xi(1, n0p, n1)], c = X[xi(0, n0, n1p)], d = X[xi(1, n0, n1)];
         return order == 0 ? ((a + b) - c) - d : ((a - d) - c) + b;
     }
 
     // ---- global <-> shared field copies (global layout (2,L0,L1) contiguous) ----
-    FT_HD void load_field(double* dst, const double* g) {
+    FT_HD void load_field(int off, const double* g) {
+        double* dst = sm(off);
         for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
             int n1 = i % L1, rest = i / L1;
             dst[rest * LP + n1] = g[i];
         }
     }
-    FT_HD void store_field(double* g, const double* src) {
+    FT_HD void store_field(double* g, int off) {
+        const double* src = sm(off);
         for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
             int n1 = i % L1, rest = i / L1;
             g[i] = src[rest * LP + n1];
@@ -248,6 +262,7 @@ struct Engine {
     }
     FT_HD void load_weights(int l) {
         const double* src = pr.wpack + (size_t)l * PACK_DOUBLES;
+        double* W = sm(oW);
         for (int i = ex.tid(); i < PACK_DOUBLES; i += ex.nt()) W[i] = src[i];
     }
 
@@ -256,20 +271,24 @@ struct Engine {
     // =============================================================================================
     // -beta * sum cos P   (order 0: U1GaugeAction, order 1: hmc_2dU1.action)
     FT_PHASE double wilson_action(double beta, int order) {
+        const double* X = sm(oX);
         double acc = 0.0;
-        for (int i = ex.tid(); i < V; i += ex.nt()) acc += cos(plaq(i / L1, i % L1, order));
+        for (int i = ex.tid(); i < V; i += ex.nt()) acc += cos(plaq(X, i / L1, i % L1, order));
         return -beta * ex.sum(acc);
     }
     // floor(0.1 + sum regularize(P) / 2pi)   hmc_2dU1.py:123-124
     FT_PHASE double topo_floor() {
+        const double* X = sm(oX);
         double acc = 0.0;
-        for (int i = ex.tid(); i < V; i += ex.nt()) acc += regularize1(plaq(i / L1, i % L1, 1));
+        for (int i = ex.tid(); i < V; i += ex.nt()) acc += regularize1(plaq(X, i / L1, i % L1, 1));
         return floor(0.1 + ex.sum(acc) / TWO_PI_D);
     }
     // GR = dS/dx of the Wilson action: F0 = beta[sinP(n) - sinP(n-e1)], F1 = beta[sinP(n-e0) - sinP(n)]
     FT_PHASE void wilson_force(double beta, int order) {
-        double* S = A;                                   // scratch plane, pitch L1
-        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(i / L1, i % L1, order));
+        const double* X = sm(oX);
+        double* GR = sm(oGR);
+        double* S = sm(oS);                              // scratch plane, pitch L1
+        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(X, i / L1, i % L1, order));
         ex.sync();
         for (int i = ex.tid(); i < V; i += ex.nt()) {
             int n0 = i / L1, n1 = i % L1;
@@ -284,24 +303,30 @@ struct Engine {
     // =============================================================================================
     // coupling-layer phases (canonical stripe geometry)
     // =============================================================================================
-    // cos/sin of the frozen plaquettes and the raw active plaquette
-    FT_PHASE void ph_planes(const LayerGeom g) {
+    // cos/sin of the frozen plaquettes and the raw active plaquette; cs_save: global copy of CS
+    FT_PHASE void ph_planes(const LayerGeom g, double* cs_save) {
+        const double* X = sm(oX);
+        double* CS = sm(oCS); double* UA = sm(oUA);
         const int T = g.G * g.R, order = pr.conv;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / g.R, r = t - gi * g.R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
-            UA[t] = plaq(n0, n1, order);
+            UA[t] = plaq(X, n0, n1, order);
+#pragma unroll 1
             for (int k = 0; k < 2; ++k) {
                 site(g, r, 4 * gi + 1 + k, n0, n1);
-                double p = plaq(n0, n1, order);
-                CS[(2 * gi + k) * g.R + r] = cos(p);
-                CS[V / 2 + (2 * gi + k) * g.R + r] = sin(p);
+                double p = plaq(X, n0, n1, order);
+                double sp, cp;
+                sincos(p, &sp, &cp);
+                const int i = (2 * gi + k) * g.R + r;
+                CS[i] = cp; CS[V / 2 + i] = sp;
+                if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
             }
         }
     }
 
     // conv1 pre-activations for the 4 columns of group gi at row r.  z[q][o]
-    FT_HD void conv1_z(const LayerGeom& g, int gi, int r, double z[4][NH]) const {
+    FT_HD void conv1_z(const double* CS, const double* W, const LayerGeom& g, int gi, int r, double z[4][NH]) const {
         const int R = g.R;
         int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
         double in[2][3][2];                                  // [k][a][ci]
@@ -333,25 +358,44 @@ struct Engine {
         }
     }
 
-    // h1 = act(conv1) on all columns -> A[o][c][r]
-    FT_PHASE void ph_conv1(const LayerGeom g) {
-        const int T = g.G * g.R, R = g.R, act = pr.act;
+    // h1 = act(conv1) on all columns -> A[o][c][r];  d1_save: act'(z1) to the global layer block
+    FT_PHASE void ph_conv1(const LayerGeom g, double* d1_save) {
+        const double* CS = sm(oCS); const double* W = sm(oW);
+        double* A = sm(oA);
+        const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             double z[4][NH];
-            conv1_z(g, gi, r, z);
+            conv1_z(CS, W, g, gi, r, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int o = 0; o < NH; ++o) {
-                    double h; act_fwd(act, z[q][o], h);
-                    A[(o * g.Cn + 4 * gi + q) * R + r] = h;
+                for (int o = 0; o < NH; ++o) A[(o * Cn + 4 * gi + q) * R + r] = z[q][o];
+            // activation pass as a rolled loop over this thread's own 32 values (keeps the code small:
+            // a fully unrolled exp() per element overflows the instruction cache)
+            const int base = 4 * gi * R + r;
+            if (d1_save) {
+#pragma unroll 4
+                for (int e = 0; e < 4 * NH; ++e) {
+                    const int idx = (e >> 2) * Cn * R + (e & 3) * R + base;
+                    double h, d; act_fwd_der(act, A[idx], h, d);
+                    A[idx] = h; d1_save[idx] = d;
                 }
+            } else {
+#pragma unroll 4
+                for (int e = 0; e < 4 * NH; ++e) {
+                    const int idx = (e >> 2) * Cn * R + (e & 3) * R + base;
+                    double h; act_fwd(act, A[idx], h);
+                    A[idx] = h;
+                }
+            }
         }
     }
 
-    // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r]; optionally act' -> C
-    FT_PHASE void ph_conv2(const LayerGeom g, bool want_der) {
+    // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
+    FT_PHASE void ph_conv2(const LayerGeom g, double* d2_save) {
+        const double* A = sm(oA); const double* W = sm(oW);
+        double* B = sm(oB);
         const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
@@ -389,21 +433,30 @@ struct Engine {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int o = 0; o < NH; ++o) {
-                    int idx = (o * 3 * g.G + 3 * gi + k) * R + r;
-                    if (want_der) {
-                        double h, d; act_fwd_der(act, acc[k][o], h, d);
-                        B[idx] = h; C[idx] = d;
-                    } else {
-                        double h; act_fwd(act, acc[k][o], h);
-                        B[idx] = h;
-                    }
+                for (int o = 0; o < NH; ++o) B[(o * 3 * g.G + 3 * gi + k) * R + r] = acc[k][o];
+            const int base = 3 * gi * R + r, cs = 3 * g.G * R;
+            if (d2_save) {
+#pragma unroll 4
+                for (int e = 0; e < 3 * NH; ++e) {
+                    const int o = e / 3, k = e - 3 * o;
+                    const int idx = o * cs + k * R + base;
+                    double h, d; act_fwd_der(act, B[idx], h, d);
+                    B[idx] = h; d2_save[idx] = d;
                 }
+            } else {
+#pragma unroll 4
+                for (int e = 0; e < 3 * NH; ++e) {
+                    const int o = e / 3, k = e - 3 * o;
+                    const int idx = o * cs + k * R + base;
+                    double h; act_fwd(act, B[idx], h);
+                    B[idx] = h;
+                }
+            }
         }
     }
 
     // conv3 at the active site of task (gi,r): out[0..2] = (s_1, s_2, t)
-    FT_HD void conv3_out(const LayerGeom& g, int gi, int r, double out[NOUT]) const {
+    FT_HD void conv3_out(const double* B, const double* W, const LayerGeom& g, int gi, int r, double out[NOUT]) const {
         const int R = g.R;
         int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
         double o0 = W[OFF_B3 + 0], o1 = W[OFF_B3 + 1], o2 = W[OFF_B3 + 2];
@@ -423,14 +476,16 @@ struct Engine {
     }
 
     // forward transform of the active plaquettes + link update; returns this thread's logJ partial.
-    // save != nullptr: the pre-update active link values are stored there (for the reverse sweep).
-    FT_PHASE double ph_conv3_forward(const LayerGeom g, bool want_logJ, double* save) {
+    // sv/so != nullptr: the pre-update active links and (s_1,s_2) go to the global layer block.
+    FT_PHASE double ph_conv3_forward(const LayerGeom g, bool want_logJ, double* sv, double* so) {
+        const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
+        double* X = sm(oX);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double lj = 0.0;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             double out[NOUT];
-            conv3_out(g, gi, r, out);
+            conv3_out(B, W, g, gi, r, out);
             double u = UA[t];
             double es0 = exp(out[0]), es1 = exp(out[1]);
             double fx1 = mixture_fwd(u, es0, es1, conv);
@@ -439,7 +494,7 @@ struct Engine {
             int n0, n1; site(g, r, 4 * gi, n0, n1);
             int li = xi(g.mu, n0, n1);
             double xo = X[li];
-            if (save) save[t] = xo;
+            if (sv) { sv[t] = xo; so[t] = out[0]; so[T + t] = out[1]; }
             X[li] = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
             if (want_logJ) {
                 double c = cos(u / 2), s = sin(u / 2);
@@ -452,17 +507,18 @@ struct Engine {
         return lj;
     }
 
-    // one coupling layer forward on the resident field; returns logJ (valid on all threads) if asked
-    FT_HD double layer_forward(int l, bool want_logJ, double* save) {
+    // one coupling layer forward on the resident field; returns logJ (valid on all threads) if asked.
+    // save: also write the layer block the reverse sweep of ft_force needs.
+    FT_HD double layer_forward(int l, bool want_logJ, bool save) {
         LayerGeom g = geom(l);
         load_weights(l);
-        ph_planes(g);
+        ph_planes(g, save ? wsCS(l) : nullptr);
         ex.sync();
-        ph_conv1(g);
+        ph_conv1(g, save ? wsD1(l) : nullptr);
         ex.sync();
-        ph_conv2(g, false);
+        ph_conv2(g, save ? wsD2(l) : nullptr);
         ex.sync();
-        double lj = ph_conv3_forward(g, want_logJ, save);
+        double lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
         double tot = want_logJ ? ex.sum(lj) : 0.0;
         ex.sync();
         return tot;
@@ -474,6 +530,8 @@ struct Engine {
     // fire within max_iter=1000 because non-active sites (y=0,f=0) keep halving towards 0 without
     // reaching it, so only the tolerance and max_iter exits exist.
     FT_PHASE double ph_conv3_reverse(const LayerGeom g, bool want_logJ, int* iters) {
+        const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
+        double* X = sm(oX); double* OUT = sm(oOUT); double* A = sm(oA);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double* Y = A; double* ES0 = A + T; double* ES1 = A + 2 * T; double* LO = A + 3 * T; double* HI = A + 4 * T;
         double* MID = A + 5 * T;
@@ -481,7 +539,7 @@ struct Engine {
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             double out[NOUT];
-            conv3_out(g, gi, r, out);
+            conv3_out(B, W, g, gi, r, out);
             OUT[t] = out[0]; OUT[T + t] = out[1];
             ES0[t] = exp(out[0]); ES1[t] = exp(out[1]);
             Y[t] = mod_2pi(UA[t] - out[2], conv);
@@ -526,11 +584,11 @@ struct Engine {
     FT_HD double layer_reverse(int l, bool want_logJ) {
         LayerGeom g = geom(l);
         load_weights(l);
-        ph_planes(g);
+        ph_planes(g, nullptr);
         ex.sync();
-        ph_conv1(g);
+        ph_conv1(g, nullptr);
         ex.sync();
-        ph_conv2(g, false);
+        ph_conv2(g, nullptr);
         ex.sync();
         int iters = 0;
         double lj = ph_conv3_reverse(g, want_logJ, &iters);
@@ -542,31 +600,30 @@ struct Engine {
 
     // =============================================================================================
     // adjoint of one layer: GR holds d/dy on entry, d/dx on exit; X holds y on entry, x on exit.
+    // Nothing of the forward CNN is recomputed: act'(z1), act'(z2), cos/sin of the frozen plaquettes
+    // and (s_1,s_2) come back from the layer block written by the forward sweep.
     // =============================================================================================
-    FT_PHASE void ph_restore(const LayerGeom g, const double* save) {
-        const int T = g.G * g.R, R = g.R;
+    // put the pre-update active links back, then the adjoint of the mixture transform and of -logJ at
+    // the active sites:  OUT <- (s1bar, s2bar, tbar),  UA <- Pbar(active)
+    FT_PHASE void ph_outgrad(const LayerGeom g, const double* sv, const double* so) {
+        double* X = sm(oX); const double* GR = sm(oGR);
+        double* OUT = sm(oOUT); double* UA = sm(oUA);
+        const int T = g.G * g.R, R = g.R, order = pr.conv;
+        // the active plaquette only involves its own active link, so restore + plaquette fuse per task
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
-            X[xi(g.mu, n0, n1)] = save[t];
-        }
-    }
-
-    // conv3 + adjoint of the mixture transform and of -logJ at the active sites:
-    // OUT <- (s1bar, s2bar, tbar), UA <- Pbar(active)
-    FT_PHASE void ph_conv3_adjoint(const LayerGeom g) {
-        const int T = g.G * g.R, R = g.R;
-        for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
-            double out[NOUT];
-            conv3_out(g, gi, r, out);
-            int n0, n1; site(g, r, 4 * gi, n0, n1);
-            double gl = GR[xi(g.mu, n0, n1)];
+            const int li = xi(g.mu, n0, n1);
+            X[li] = sv[t];
+            double gl = GR[li];
             double db = g.mu == 0 ? gl : -gl;                 // delta-bar
-            double u = UA[t];
-            double c = cos(u / 2), s = sin(u / 2), su = sin(u);
+            double u = plaq(X, n0, n1, order);
+            double s0 = so[t], s1 = so[T + t];
+            double c, s;
+            sincos(u / 2, &s, &c);
+            double su = sin(u);
             double c2 = c * c, s2 = s * s;
-            double ep0 = exp(out[0]), em0 = exp(-out[0]), ep1 = exp(out[1]), em1 = exp(-out[1]);
+            double ep0 = exp(s0), em0 = exp(-s0), ep1 = exp(s1), em1 = exp(-s1);
             double e0 = 1.0 / (em0 * c2 + ep0 * s2), e1 = 1.0 / (em1 * c2 + ep1 * s2);   // e^{l_k}
             double sg0 = e0 / (e0 + e1), sg1 = e1 / (e0 + e1);                             // softmax_k l_k
             // w = -1 multiplies the logJ terms (ft_action = S - sum logJ)
@@ -579,8 +636,10 @@ struct Engine {
         }
     }
 
-    // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C)
+    // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C, which holds act'(z2))
     FT_PHASE void ph_conv3T(const LayerGeom g) {
+        const double* OUT = sm(oOUT); const double* W = sm(oW);
+        double* C = sm(oC);
         const int T = g.G * g.R, R = g.R;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
@@ -591,34 +650,33 @@ struct Engine {
             for (int o = 0; o < NOUT; ++o)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) ob[o][a] = OUT[o * T + gi * R + rs[a]];
-            double acc[3][NH];
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                double acc[NH];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+                for (int ci = 0; ci < NH; ++ci) acc[ci] = 0.0;
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci) acc[k][ci] = 0.0;
+                for (int o = 0; o < NOUT; ++o)
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o)
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
+                    for (int a = 0; a < 3; ++a) {
                         const double* w = W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH;
 #pragma unroll
-                        for (int ci = 0; ci < NH; ++ci) acc[k][ci] = fma(w[ci], ob[o][a], acc[k][ci]);
+                        for (int ci = 0; ci < NH; ++ci) acc[ci] = fma(w[ci], ob[o][a], acc[ci]);
                     }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int ci = 0; ci < NH; ++ci) {
                     int idx = (ci * 3 * g.G + 3 * gi + k) * R + r;
-                    C[idx] = acc[k][ci] * C[idx];
+                    C[idx] = acc[ci] * C[idx];
                 }
+            }
         }
     }
 
-    // zbar1 = conv2^T(zbar2) * act'(z1) -> A[ci][c][r]   (z1 recomputed from the frozen planes)
+    // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1))
     FT_PHASE void ph_conv2T(const LayerGeom g) {
-        const int T = g.G * g.R, R = g.R, G = g.G, act = pr.act;
+        const double* C = sm(oC); const double* W = sm(oW);
+        double* A = sm(oA);
+        const int T = g.G * g.R, R = g.R, G = g.G;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             int gn = gi + 1 == G ? 0 : gi + 1;
@@ -653,18 +711,20 @@ struct Engine {
                             }
                         }
             }
-            double z[4][NH];
-            conv1_z(g, gi, r, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci)
-                    A[(ci * g.Cn + 4 * gi + q) * R + r] = acc[q][ci] * act_der(act, z[q][ci]);
+                for (int ci = 0; ci < NH; ++ci) {
+                    const int idx = (ci * g.Cn + 4 * gi + q) * R + r;
+                    A[idx] = acc[q][ci] * A[idx];
+                }
         }
     }
 
     // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar on the lattice (PB, pitch LP)
-    FT_PHASE void ph_conv1T(const LayerGeom g, double* PB) {
+    FT_PHASE void ph_conv1T(const LayerGeom g, int oPB) {
+        const double* A = sm(oA); const double* W = sm(oW); const double* CS = sm(oCS); const double* UA = sm(oUA);
+        double* PB = sm(oPB);
         const int T = g.G * g.R, R = g.R, Cn = g.Cn;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
@@ -696,7 +756,9 @@ struct Engine {
     }
 
     // GR += plaquette^T(Pbar)
-    FT_PHASE void ph_scatter(const double* PB) {
+    FT_PHASE void ph_scatter(int oPB) {
+        const double* PB = sm(oPB);
+        double* GR = sm(oGR);
         for (int i = ex.tid(); i < V; i += ex.nt()) {
             int n0 = i / L1, n1 = i - n0 * L1;
             int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
@@ -706,38 +768,43 @@ struct Engine {
         }
     }
 
-    FT_HD void layer_adjoint(int l, const double* save) {
+    // cp.async prefetch of layer l's block pieces; group order is always [d2 -> C, d1 -> A, cs -> CS]
+    FT_HD void prefetch_d2(int l) { ex.async_copy(sm(oC), wsD2(l), 6 * V); ex.async_commit(); }
+    FT_HD void prefetch_d1_cs(int l) {
+        ex.async_copy(sm(oA), wsD1(l), 8 * V); ex.async_commit();
+        ex.async_copy(sm(oCS), wsCS(l), V); ex.async_commit();
+    }
+
+    // pending cp.async groups on entry: [d2(l), d1(l), cs(l)]; on exit: the same for l-1 (if l > 0)
+    FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
         load_weights(l);
-        ph_restore(g, save);
-        ex.sync();
-        ph_planes(g);
-        ex.sync();
-        ph_conv1(g);
-        ex.sync();
-        ph_conv2(g, true);
-        ex.sync();
-        ph_conv3_adjoint(g);
+        ph_outgrad(g, wsSV(l), wsSO(l));
+        ex.template async_wait<2>();          // d2(l) landed in C
         ex.sync();
         ph_conv3T(g);
+        ex.template async_wait<1>();          // d1(l) landed in A
         ex.sync();
         ph_conv2T(g);
         ex.sync();
-        double* PB = B;                  // h2 is dead
-        ph_conv1T(g, PB);
+        if (l > 0) { prefetch_d2(l - 1); ex.template async_wait<1>(); }   // C is free; cs(l) must have landed
+        else ex.template async_wait<0>();
         ex.sync();
-        ph_scatter(PB);
+        ph_conv1T(g, oB);                     // B (h2 of the forward sweep) is dead: Pbar plane
+        ex.sync();
+        if (l > 0) prefetch_d1_cs(l - 1);     // A and CS are free
+        ph_scatter(oB);
         ex.sync();
     }
 
     // =============================================================================================
     // chain programs on the resident field X
     // =============================================================================================
-    // X <- F(X); returns sum of logJ (if asked).  save_base: per-layer saved active links (or null)
-    FT_HD double flow_forward(bool want_logJ, double* save_base, double* layer_logJ = nullptr) {
+    // X <- F(X); returns sum of logJ (if asked).  save: write the layer blocks for the reverse sweep
+    FT_HD double flow_forward(bool want_logJ, bool save, double* layer_logJ = nullptr) {
         double tot = 0.0;
         for (int l = 0; l < pr.nlayers; ++l) {
-            double lj = layer_forward(l, want_logJ, save_base ? save_base + (size_t)l * VQ : nullptr);
+            double lj = layer_forward(l, want_logJ, save);
             tot += lj;
             if (layer_logJ && ex.tid() == 0) layer_logJ[l] = lj;
         }
@@ -754,17 +821,20 @@ struct Engine {
     }
     // ft_action (ipynb/ft_hmc.py:230-238): X <- F(X), returns S(F(x)) - sum logJ; *s_plain = S(F(x))
     FT_HD double ft_action(double beta, double* s_plain = nullptr) {
-        double lj = flow_forward(true, nullptr);
+        double lj = flow_forward(true, false);
         double s = wilson_action(beta, pr.conv);
         if (s_plain) *s_plain = s;
         return s - lj;
     }
     // ft_force (ipynb/ft_hmc.py:240-249): GR <- d/dx [S(F(x)) - sum logJ]; X is preserved.
     FT_HD void ft_force(double beta) {
-        flow_forward(false, wsSave);
-        ex.sync();                        // saved links are read back through global memory
-        wilson_force(beta, pr.conv);
-        for (int l = pr.nlayers - 1; l >= 0; --l) layer_adjoint(l, wsSave + (size_t)l * VQ);
+        flow_forward(false, true);
+        ex.sync();                        // the layer blocks are read back through global memory
+        const int last = pr.nlayers - 1;
+        prefetch_d2(last);
+        prefetch_d1_cs(last);
+        wilson_force(beta, pr.conv);      // scratch plane = B
+        for (int l = last; l >= 0; --l) layer_adjoint(l);
     }
 
     // elementwise helpers on the link field (skip the pitch padding)
@@ -818,16 +888,18 @@ template <class E, class ForceFn>
 FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, ForceFn force) {
     auto& ex = en.ex;
     const double hdt = 0.5 * dt;
-    en.for_links([&](int si, int gi) { en.X[si] = en.X[si] + hdt * P[gi]; });
+    double* X = en.sm(en.oX);
+    const double* GR = en.sm(en.oGR);
+    en.for_links([&](int si, int gi) { X[si] = X[si] + hdt * P[gi]; });
     ex.sync();
     for (int s = 0; s < nstep; ++s) {
         force();
         const bool last = s == nstep - 1;
         const double step = last ? hdt : dt;
         en.for_links([&](int si, int gi) {
-            double pn = P[gi] + (-dt) * en.GR[si];
+            double pn = P[gi] + (-dt) * GR[si];
             P[gi] = pn;
-            en.X[si] = en.X[si] + step * pn;
+            X[si] = X[si] + step * pn;
         });
         ex.sync();
     }
@@ -839,10 +911,11 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     auto& ex = en.ex;
     const int V = en.V;
     double* P = en.wsP;
-    en.load_field(en.X, io.field_in);
+    double* X = en.sm(en.oX);
+    en.load_field(en.oX, io.field_in);
     ex.sync();
     en.flow_reverse(false);                                     // x = ft_flow_inv(field)
-    en.for_links([&](int si, int gi) { en.wsX0[gi] = en.X[si]; });
+    en.for_links([&](int si, int gi) { en.wsX0[gi] = X[si]; });
     if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
     else philox_momenta(en, io, P);
     ex.sync();
@@ -851,12 +924,12 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     k0 = ex.sum(k0);
     double s0_plain;
     double h0 = en.ft_action(io.beta, &s0_plain) + 0.5 * k0;    // X <- y0 = F(x)
-    en.for_links([&](int si, int gi) { en.wsY0[gi] = en.X[si]; });
+    en.for_links([&](int si, int gi) { en.wsY0[gi] = X[si]; });
     ex.sync();
-    en.for_links([&](int si, int gi) { en.X[si] = en.wsX0[gi]; });
+    en.for_links([&](int si, int gi) { X[si] = en.wsX0[gi]; });
     ex.sync();
     leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.ft_force(io.beta); });
-    en.for_links([&](int si, int gi) { en.X[si] = regularize1(en.X[si]); });
+    en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;
     for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
@@ -869,11 +942,11 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     bool acc = u < e;
     if (!acc) {                                                  // newfield = ft_flow(x) = y0
         ex.sync();
-        en.for_links([&](int si, int gi) { en.X[si] = en.wsY0[gi]; });
+        en.for_links([&](int si, int gi) { X[si] = en.wsY0[gi]; });
     }
     ex.sync();
     double q = en.topo_floor();
-    en.store_field(io.field_out, en.X);
+    en.store_field(io.field_out, en.oX);
     if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
     if (ex.tid() == 0) {
         if (io.out_dH) *io.out_dH = dH;
@@ -893,7 +966,8 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     auto& ex = en.ex;
     const int V = en.V;
     double* P = en.wsP;
-    en.load_field(en.X, io.field_in);
+    double* X = en.sm(en.oX);
+    en.load_field(en.oX, io.field_in);
     if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
     else philox_momenta(en, io, P);
     ex.sync();
@@ -903,7 +977,7 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     double s0 = en.wilson_action(io.beta, 1);
     double h0 = s0 + 0.5 * k0;
     leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.wilson_force(io.beta, 1); });
-    en.for_links([&](int si, int gi) { en.X[si] = regularize1(en.X[si]); });
+    en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;
     for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
@@ -916,11 +990,11 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     bool acc = u < e;
     if (!acc) {
         ex.sync();
-        en.load_field(en.X, io.field_in);                        // newx = x (bit-identical input)
+        en.load_field(en.oX, io.field_in);                        // newx = x (bit-identical input)
     }
     ex.sync();
     double q = en.topo_floor();
-    en.store_field(io.field_out, en.X);
+    en.store_field(io.field_out, en.oX);
     if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
     if (ex.tid() == 0) {
         if (io.out_dH) *io.out_dH = dH;

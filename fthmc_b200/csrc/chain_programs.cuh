@@ -37,8 +37,8 @@ struct ChainArgs {
 };
 
 template <class E>
-FT_HD void run_chain(E& ex, const ChainArgs& a, double* smem, double* ws, int b) {
-    Engine<E> en(ex, a.pr, smem, ws);
+FT_HD void run_chain(E& ex, const ChainArgs& a, double* ws, int b) {
+    Engine<E> en(ex, a.pr, ws);
     const size_t fs = (size_t)2 * en.V;
     const double* fin = a.field_in + (size_t)b * fs;
     double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
@@ -46,42 +46,42 @@ FT_HD void run_chain(E& ex, const ChainArgs& a, double* smem, double* ws, int b)
     double* llj = a.layer_logJ ? a.layer_logJ + (size_t)b * a.pr.nlayers : nullptr;
     switch (a.mode) {
     case MODE_FLOW_FWD: {
-        en.load_field(en.X, fin); ex.sync();
-        double lj = en.flow_forward(a.s_out != nullptr || llj != nullptr, nullptr, llj);
-        en.store_field(fout, en.X);
+        en.load_field(en.oX, fin); ex.sync();
+        double lj = en.flow_forward(a.s_out != nullptr || llj != nullptr, false, llj);
+        en.store_field(fout, en.oX);
         if (a.s_out && ex.tid() == 0) a.s_out[b] = lj;
         ex.sync();
     } break;
     case MODE_FLOW_INV: {
-        en.load_field(en.X, fin); ex.sync();
+        en.load_field(en.oX, fin); ex.sync();
         double lj = en.flow_reverse(a.s_out != nullptr || llj != nullptr, llj);
-        en.store_field(fout, en.X);
+        en.store_field(fout, en.oX);
         if (a.s_out && ex.tid() == 0) a.s_out[b] = lj;
         ex.sync();
     } break;
     case MODE_FT_ACTION: {
-        en.load_field(en.X, fin); ex.sync();
+        en.load_field(en.oX, fin); ex.sync();
         double s = en.ft_action(a.beta);
         if (ex.tid() == 0) a.s_out[b] = s;
-        if (fout) en.store_field(fout, en.X);
+        if (fout) en.store_field(fout, en.oX);
         ex.sync();
     } break;
     case MODE_FT_FORCE: {
-        en.load_field(en.X, fin); ex.sync();
+        en.load_field(en.oX, fin); ex.sync();
         en.ft_force(a.beta);
-        en.store_field(fout, en.GR);
+        en.store_field(fout, en.oGR);
         ex.sync();
     } break;
     case MODE_FT_LEAPFROG:
     case MODE_LEAPFROG: {
-        en.load_field(en.X, fin);
+        en.load_field(en.oX, fin);
         for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) en.wsP[i] = a.p_in[(size_t)b * fs + i];
         ex.sync();
         if (a.mode == MODE_FT_LEAPFROG)
             leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.ft_force(a.beta); });
         else
             leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
-        en.store_field(fout, en.X);
+        en.store_field(fout, en.oX);
         for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) a.p_out[(size_t)b * fs + i] = en.wsP[i];
         ex.sync();
     } break;

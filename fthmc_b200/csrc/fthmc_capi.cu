@@ -41,7 +41,35 @@ extern "C" unsigned long long fthmc_launch_count(void) { return g_launches.load(
 // CTA execution policy for the chain engine
 // ------------------------------------------------------------------------------------------------
 struct CtaExec {
-    double* red;   // 64 doubles of shared scratch
+    double* red;   // 64 doubles of shared scratch (the first 64 doubles of the dynamic shared memory)
+    // base of the engine's arena.  Naming the extern __shared__ symbol here (instead of carrying a
+    // generic pointer in the engine) lets nvcc emit LDS/STS rather than generic LD/ST in every phase.
+    __host__ __device__ double* smem() const {
+#ifdef __CUDA_ARCH__
+        extern __shared__ __align__(16) double fthmc_dyn_smem[];
+        return fthmc_dyn_smem + 64;
+#else
+        return nullptr;
+#endif
+    }
+    // cooperative 16-byte cp.async (LDGSTS) copy global -> shared; n doubles, both 16-byte aligned
+    __host__ __device__ void async_copy(double* dst, const double* src, int n) const {
+#ifdef __CUDA_ARCH__
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 8u * i), "l"(src + i) : "memory");
+#endif
+    }
+    __host__ __device__ void async_commit() const {
+#ifdef __CUDA_ARCH__
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+    }
+    template <int N> __host__ __device__ void async_wait() const {
+#ifdef __CUDA_ARCH__
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+    }
     __host__ __device__ int tid() const {
 #ifdef __CUDA_ARCH__
         return threadIdx.x;
@@ -94,10 +122,10 @@ struct CtaExec {
 };
 
 __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    CtaExec ex{ smem };
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    CtaExec ex{ fthmc_dyn_smem };
     double* ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(ex, a, smem + 64, ws, b);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(ex, a, ws, b);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -3,12 +3,18 @@
 // indexing, the weight packing and the hand-derived adjoint can be checked against the oracle
 // without a GPU.  Nothing in the product package loads this library.
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "../../fthmc_b200/csrc/chain_programs.cuh"
 #include "../../fthmc_b200/csrc/weight_pack.h"
 
 namespace {
 struct SerialExec {
+    double* arena;
+    double* smem() const { return arena; }
+    void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
+    void async_commit() const {}
+    template <int N> void async_wait() const {}
     int tid() const { return 0; }
     int nt() const { return 1; }
     void sync() const {}
@@ -26,7 +32,7 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
     if (L0 % 4 || L1 % 4) return -1;
     std::vector<double> pack((size_t)nlayers * PACK_DOUBLES);
     for (int l = 0; l < nlayers; ++l) pack_layer(raw + (size_t)l * RAW_DOUBLES, mu[l], pack.data() + (size_t)l * PACK_DOUBLES);
-    std::vector<double> smem(engine_smem_doubles(L0, L1) + 8), ws(engine_ws_doubles(L0, L1, nlayers) + 8);
+    std::vector<double> smem(engine_smem_doubles(L0, L1, nlayers > 0) + 8), ws(engine_ws_doubles(L0, L1, nlayers) + 8);
     ChainArgs a{};
     a.mode = mode; a.B = B;
     a.pr.L0 = L0; a.pr.L1 = L1; a.pr.nlayers = nlayers; a.pr.act = act; a.pr.conv = conv;
@@ -36,7 +42,7 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
     a.s_out = s_out; a.layer_logJ = layer_logJ; a.iters = iters;
     a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
     a.seed = seed; a.traj = traj; a.chain0 = 0;
-    SerialExec ex;
-    for (int b = 0; b < B; ++b) run_chain(ex, a, smem.data(), ws.data(), b);
+    SerialExec ex{ smem.data() };
+    for (int b = 0; b < B; ++b) run_chain(ex, a, ws.data(), b);
     return 0;
 }
