@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define FT_HD __host__ __device__ __forceinline__
@@ -78,9 +79,57 @@ FT_HD double regularize1(double f) {
     return TWO_PI_D * (g - floor(g) - 0.5);
 }
 
+// e^x for |x| <= 708 with ~1 ulp error: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on
+// |r| <= 0.347 (remainder 4e-18), scaling through the exponent bits.  About half the instructions of
+// the library exp(): the SiLU evaluations are a quarter of the trajectory's run time.
+FT_HD double exp_fast(double x) {
+    x = x < -708.0 ? -708.0 : (x > 708.0 ? 708.0 : x);
+    const double t = x * 1.4426950408889634074;
+    const double n = (t + 6755399441055744.0) - 6755399441055744.0;          // rint(t)
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                                       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const long long bits = ((long long)n + 1023LL) << 52;                      // 2^n, n in [-1022, 1022]
+    double sc;
+#ifdef __CUDA_ARCH__
+    sc = __longlong_as_double(bits);
+#else
+    memcpy(&sc, &bits, sizeof(sc));
+#endif
+    return p * sc;
+}
+
+// 1/d for d >= 1 (two Newton steps on the hardware seed); host: plain division
+FT_HD double rcp_ge1(double d) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / d;
+#endif
+}
+
 FT_HD void act_fwd(int act, double z, double& h) {
     if (act == ACT_SILU) {
-        h = z / (1.0 + exp(-z));
+        h = z * rcp_ge1(1.0 + exp_fast(-z));
     } else if (act == ACT_LEAKY) {
         h = z > 0.0 ? z : 0.01 * z;
     } else {
@@ -91,7 +140,7 @@ FT_HD void act_fwd(int act, double z, double& h) {
 // activation and its derivative
 FT_HD void act_fwd_der(int act, double z, double& h, double& d) {
     if (act == ACT_SILU) {
-        double sg = 1.0 / (1.0 + exp(-z));
+        double sg = rcp_ge1(1.0 + exp_fast(-z));
         h = z * sg;
         d = sg * (1.0 + z * (1.0 - sg));
     } else if (act == ACT_LEAKY) {
@@ -101,12 +150,6 @@ FT_HD void act_fwd_der(int act, double z, double& h, double& d) {
         h = z > 0.0 ? z : 0.0;
         d = z > 0.0 ? 1.0 : 0.0;
     }
-}
-
-FT_HD double act_der(int act, double z) {
-    double h, d;
-    act_fwd_der(act, z, h, d);
-    return d;
 }
 
 // mean_k mod(2 atan(e^{s_k} tan(x/2)))   (ipynb/field_transformation.py:249-257), es_k = e^{s_k}
@@ -169,7 +212,7 @@ struct EngineParams {
 FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true) {
     size_t V = (size_t)L0 * L1, LP = L1 + 1;
     if (!flow) return 2 * L0 * LP * 2 + V + 4;
-    return 2 * L0 * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 4;
+    return 2 * L0 * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 32 + 4;
 }
 
 // Per-layer block of the per-CTA global workspace written by the forward sweep of ft_force and read
@@ -190,7 +233,7 @@ struct Engine {
     E& ex;
     EngineParams pr;
     int L0, L1, LP, V, VQ;
-    int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS;   // arena offsets (doubles)
+    int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
     double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
     size_t layStride;
     int* iters_out;                                    // optional global: bisection iterations per layer
@@ -203,7 +246,7 @@ struct Engine {
         wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsLay = ws + 6 * V;
         layStride = engine_layer_ws_doubles(L0, L1);
         iters_out = nullptr;
-        oCS = oUA = oOUT = oA = oB = oC = oW = 0;
+        oCS = oUA = oOUT = oA = oB = oC = oW = oTab = 0;
         if (p.nlayers == 0) { oS = o; return; }        // plain HMC: only a scratch plane
         oCS = o;  o += V;
         oUA = o;  o += VQ;
@@ -213,7 +256,14 @@ struct Engine {
         oB = o;   o += 6 * V;
         oC = o;   o += 6 * V;
         oW = o;   o += PACK_DOUBLES;
-        oS = oB;                                       // Wilson-force scratch plane aliases B
+        oTab = o; o += 32;                             // per-layer (mu, off) bytes, MAX_LAYERS = 128
+        oS = oUA;                                      // Wilson-force scratch plane = UA+OUT (V doubles, contiguous)
+    }
+    // copy the per-layer mask parameters into shared memory once per kernel (global-latency off the layer loop)
+    FT_HD void load_geom_table() {
+        unsigned char* tab = reinterpret_cast<unsigned char*>(sm(oTab));
+        for (int l = ex.tid(); l < pr.nlayers; l += ex.nt()) { tab[l] = (unsigned char)pr.lmu[l]; tab[128 + l] = (unsigned char)pr.loff[l]; }
+        ex.sync();
     }
     FT_HD double* sm(int off) const { return ex.smem() + off; }
     // layer block pieces in the global workspace
@@ -226,7 +276,8 @@ struct Engine {
     // ---- geometry ----
     FT_HD LayerGeom geom(int l) const {
         LayerGeom g;
-        g.mu = pr.lmu[l]; g.off = pr.loff[l];
+        const unsigned char* tab = reinterpret_cast<const unsigned char*>(sm(oTab));
+        g.mu = tab[l]; g.off = tab[128 + l];
         g.R = g.mu == 0 ? L0 : L1;
         g.Cn = g.mu == 0 ? L1 : L0;
         g.G = g.Cn / 4;
@@ -260,10 +311,12 @@ struct Engine {
             g[i] = src[rest * LP + n1];
         }
     }
-    FT_HD void load_weights(int l) {
-        const double* src = pr.wpack + (size_t)l * PACK_DOUBLES;
-        double* W = sm(oW);
-        for (int i = ex.tid(); i < PACK_DOUBLES; i += ex.nt()) W[i] = src[i];
+    // stage layer l's weights (cp.async, one commit group): the forward part [0,OFF_W3T) for the
+    // forward/reverse sweeps, the transposed part [OFF_W3T,PACK) for the adjoint sweep
+    FT_HD void issue_weights(int l, bool transposed) {
+        const int lo = transposed ? OFF_W3T : 0, n = transposed ? PACK_DOUBLES - OFF_W3T : OFF_W3T;
+        if (l >= 0) ex.async_copy(sm(oW) + lo, pr.wpack + (size_t)l * PACK_DOUBLES + lo, n);
+        ex.async_commit();
     }
 
     // =============================================================================================
@@ -511,8 +564,9 @@ struct Engine {
     // save: also write the layer block the reverse sweep of ft_force needs.
     FT_HD double layer_forward(int l, bool want_logJ, bool save) {
         LayerGeom g = geom(l);
-        load_weights(l);
+        issue_weights(l, false);              // lands while the plaquette planes are computed
         ph_planes(g, save ? wsCS(l) : nullptr);
+        ex.template async_wait<0>();
         ex.sync();
         ph_conv1(g, save ? wsD1(l) : nullptr);
         ex.sync();
@@ -583,8 +637,9 @@ struct Engine {
 
     FT_HD double layer_reverse(int l, bool want_logJ) {
         LayerGeom g = geom(l);
-        load_weights(l);
+        issue_weights(l, false);
         ph_planes(g, nullptr);
+        ex.template async_wait<0>();
         ex.sync();
         ph_conv1(g, nullptr);
         ex.sync();
@@ -637,9 +692,9 @@ struct Engine {
     }
 
     // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C, which holds act'(z2))
-    FT_PHASE void ph_conv3T(const LayerGeom g) {
+    FT_PHASE void ph_conv3T(const LayerGeom g, int oZ) {
         const double* OUT = sm(oOUT); const double* W = sm(oW);
-        double* C = sm(oC);
+        double* C = sm(oZ);
         const int T = g.G * g.R, R = g.R;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
@@ -673,8 +728,8 @@ struct Engine {
     }
 
     // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1))
-    FT_PHASE void ph_conv2T(const LayerGeom g) {
-        const double* C = sm(oC); const double* W = sm(oW);
+    FT_PHASE void ph_conv2T(const LayerGeom g, int oZ) {
+        const double* C = sm(oZ); const double* W = sm(oW);
         double* A = sm(oA);
         const int T = g.G * g.R, R = g.R, G = g.G;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
@@ -711,6 +766,7 @@ struct Engine {
                             }
                         }
             }
+            ex.template async_wait<1>();          // this thread's own act'(z1) elements have landed in A
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -722,9 +778,10 @@ struct Engine {
     }
 
     // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar on the lattice (PB, pitch LP)
-    FT_PHASE void ph_conv1T(const LayerGeom g, int oPB) {
+    FT_PHASE void ph_conv1T(const LayerGeom g) {
         const double* A = sm(oA); const double* W = sm(oW); const double* CS = sm(oCS); const double* UA = sm(oUA);
-        double* PB = sm(oPB);
+        double* PB = sm(oW);                  // Pbar plane (pitch L1) lives in the unused forward-weight slots
+        const int LP = L1;
         const int T = g.G * g.R, R = g.R, Cn = g.Cn;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
@@ -748,6 +805,7 @@ struct Engine {
                             gc = fma(w[0], v, gc); gs = fma(w[1], v, gs);
                         }
                 }
+                ex.template async_wait<1>();      // this thread's own cos/sin elements have landed in CS
                 double cp = CS[(2 * gi + k) * R + r], sp = CS[V / 2 + (2 * gi + k) * R + r];
                 site(g, r, c, n0, n1);
                 PB[n0 * LP + n1] = -sp * gc + cp * gs;
@@ -756,9 +814,10 @@ struct Engine {
     }
 
     // GR += plaquette^T(Pbar)
-    FT_PHASE void ph_scatter(int oPB) {
-        const double* PB = sm(oPB);
+    FT_PHASE void ph_scatter() {
+        const double* PB = sm(oW);
         double* GR = sm(oGR);
+        const int LP = L1;
         for (int i = ex.tid(); i < V; i += ex.nt()) {
             int n0 = i / L1, n1 = i - n0 * L1;
             int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
@@ -768,32 +827,67 @@ struct Engine {
         }
     }
 
-    // cp.async prefetch of layer l's block pieces; group order is always [d2 -> C, d1 -> A, cs -> CS]
-    FT_HD void prefetch_d2(int l) { ex.async_copy(sm(oC), wsD2(l), 6 * V); ex.async_commit(); }
-    FT_HD void prefetch_d1_cs(int l) {
-        ex.async_copy(sm(oA), wsD1(l), 8 * V); ex.async_commit();
-        ex.async_copy(sm(oCS), wsCS(l), V); ex.async_commit();
+    // ---- cp.async prefetch of the layer blocks for the adjoint sweep ----
+    // d2 (act'(z2)) is copied cooperatively (a block barrier precedes its use); d1 (act'(z1)) and the
+    // frozen cos/sin are copied element-wise by the thread that will consume them, so their waits sit
+    // right before the final multiply inside ph_conv2T / ph_conv1T and need no barrier.
+    // Every issue_* commits exactly one group (empty when l < 0) to keep the wait counts uniform.
+    FT_HD int zbuf(int l) const { return (l & 1) ? oB : oC; }
+    FT_HD void issue_d2(int l) {
+        if (l >= 0) ex.async_copy(sm(zbuf(l)), wsD2(l), 6 * V);
+        ex.async_commit();
+    }
+    FT_HD void issue_d1(int l) {
+        if (l >= 0) {
+            const LayerGeom g = geom(l);
+            double* A = sm(oA); const double* src = wsD1(l);
+            const int T = g.G * g.R, R = g.R;
+            for (int t = ex.tid(); t < T; t += ex.nt()) {
+                const int gi = t / R, r = t - gi * R;
+#pragma unroll 8
+                for (int e = 0; e < 4 * NH; ++e) {
+                    const int idx = ((e >> 2) * g.Cn + 4 * gi + (e & 3)) * R + r;
+                    ex.async_copy8(A + idx, src + idx);
+                }
+            }
+        }
+        ex.async_commit();
+    }
+    FT_HD void issue_cs(int l) {
+        if (l >= 0) {
+            const LayerGeom g = geom(l);
+            double* CS = sm(oCS); const double* src = wsCS(l);
+            const int T = g.G * g.R, R = g.R;
+            for (int t = ex.tid(); t < T; t += ex.nt()) {
+                const int gi = t / R, r = t - gi * R;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int i = (2 * gi + k) * R + r;
+                    ex.async_copy8(CS + i, src + i);
+                    ex.async_copy8(CS + V / 2 + i, src + V / 2 + i);
+                }
+            }
+        }
+        ex.async_commit();
     }
 
-    // pending cp.async groups on entry: [d2(l), d1(l), cs(l)]; on exit: the same for l-1 (if l > 0)
+    // cp.async groups pending on entry, oldest first: [d2(l), d2(l-1), Wt(l), d1(l), cs(l)]
     FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
-        load_weights(l);
         ph_outgrad(g, wsSV(l), wsSO(l));
-        ex.template async_wait<2>();          // d2(l) landed in C
+        ex.template async_wait<2>();          // d2(l), d2(l-1), Wt(l) have landed
         ex.sync();
-        ph_conv3T(g);
-        ex.template async_wait<1>();          // d1(l) landed in A
+        ph_conv3T(g, zbuf(l));
         ex.sync();
-        ph_conv2T(g);
+        ph_conv2T(g, zbuf(l));                // waits for d1(l) after its MAC loop
         ex.sync();
-        if (l > 0) { prefetch_d2(l - 1); ex.template async_wait<1>(); }   // C is free; cs(l) must have landed
-        else ex.template async_wait<0>();
+        issue_d2(l - 2);                      // zbuf(l) is free again          pending: [cs(l), d2(l-2)]
+        ph_conv1T(g);                         // waits for cs(l) after its MAC loop
         ex.sync();
-        ph_conv1T(g, oB);                     // B (h2 of the forward sweep) is dead: Pbar plane
-        ex.sync();
-        if (l > 0) prefetch_d1_cs(l - 1);     // A and CS are free
-        ph_scatter(oB);
+        issue_weights(l - 1, true);           // W(transposed), A and CS are free
+        issue_d1(l - 1);
+        issue_cs(l - 1);                      // pending: [d2(l-2), Wt(l-1), d1(l-1), cs(l-1)]
+        ph_scatter();
         ex.sync();
     }
 
@@ -831,10 +925,14 @@ struct Engine {
         flow_forward(false, true);
         ex.sync();                        // the layer blocks are read back through global memory
         const int last = pr.nlayers - 1;
-        prefetch_d2(last);
-        prefetch_d1_cs(last);
-        wilson_force(beta, pr.conv);      // scratch plane = B
+        issue_d2(last);
+        issue_d2(last - 1);
+        issue_weights(last, true);
+        issue_d1(last);
+        issue_cs(last);
+        wilson_force(beta, pr.conv);      // scratch plane = UA+OUT
         for (int l = last; l >= 0; --l) layer_adjoint(l);
+        ex.template async_wait<0>();
     }
 
     // elementwise helpers on the link field (skip the pitch padding)

@@ -43,6 +43,7 @@ FT_HD void run_chain(E& ex, const ChainArgs& a, double* ws, int b) {
     const double* fin = a.field_in + (size_t)b * fs;
     double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
     en.iters_out = a.iters ? a.iters + (size_t)b * a.pr.nlayers : nullptr;
+    if (a.pr.nlayers > 0) en.load_geom_table();
     double* llj = a.layer_logJ ? a.layer_logJ + (size_t)b * a.pr.nlayers : nullptr;
     switch (a.mode) {
     case MODE_FLOW_FWD: {

@@ -60,6 +60,12 @@ struct CtaExec {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 8u * i), "l"(src + i) : "memory");
 #endif
     }
+    // 8-byte cp.async of one element (used when a thread fetches exactly what it will consume)
+    __host__ __device__ void async_copy8(double* dst, const double* src) const {
+#ifdef __CUDA_ARCH__
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+    }
     __host__ __device__ void async_commit() const {
 #ifdef __CUDA_ARCH__
         asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -310,6 +316,8 @@ static int check_lattice(int B, int L0, int L1, bool flow) {
     if (L0 % 4 || L1 % 4) return fail(FTHMC_E_LATTICE, "L0 and L1 must be multiples of 4 (4-periodic stripe masks)");
     DevInfo& d = devinfo();
     if (!d.ok) return fail(FTHMC_E_ARG, "no CUDA device");
+    if (flow && (size_t)L0 * L1 > (size_t)OFF_W3T)
+        return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
     if (chain_smem_bytes(L0, L1, flow) > (size_t)d.smem_optin)
         return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
     return 0;
@@ -429,6 +437,7 @@ extern "C" int fthmc_flow_pack(const double* raw_host, int n_layers, const int* 
                                int hidden0, int hidden1, int n_mix, int ksize, int activation, int convention,
                                double inv_tol, int inv_max_iter, fthmc_flow_t* out) {
     if (!raw_host || !mu_host || !off_host || !out || n_layers <= 0) return fail(FTHMC_E_ARG, "null pointer or n_layers <= 0");
+    if (n_layers > 128) return fail(FTHMC_E_ARG, "at most 128 coupling layers");
     if (hidden0 != NH || hidden1 != NH || n_mix != NK || ksize != 3)
         return fail(FTHMC_E_NETSHAPE, "only the reference CNN shape is built: hidden_sizes=[8,8], n_mixture_comps=2, kernel_size=3");
     if (activation < 0 || activation > 2) return fail(FTHMC_E_ARG, "activation must be silu(0), leaky_relu(1) or relu(2)");
