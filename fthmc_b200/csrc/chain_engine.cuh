@@ -230,7 +230,8 @@ FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers) {
 
 template <class E>
 struct Engine {
-    E& ex;
+    E ex;                 // by value: the engine object itself lives in shared memory on the device, so
+                          // that the noinline phases read its members at shared-memory latency
     EngineParams pr;
     int L0, L1, LP, V, VQ;
     int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
@@ -238,7 +239,7 @@ struct Engine {
     size_t layStride;
     int* iters_out;                                    // optional global: bisection iterations per layer
 
-    FT_HD Engine(E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
+    FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
         L0 = p.L0; L1 = p.L1; LP = L1 + 1; V = L0 * L1; VQ = V / 4;
         int o = 0;
         oX = o;  o += 2 * L0 * LP;

@@ -36,14 +36,16 @@ struct ChainArgs {
     size_t ws_stride;         // doubles per CTA
 };
 
+// `en` is constructed once per CTA (in shared memory on the device) by the caller
 template <class E>
-FT_HD void run_chain(E& ex, const ChainArgs& a, double* ws, int b) {
-    Engine<E> en(ex, a.pr, ws);
+FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
+    E& ex = en.ex;
     const size_t fs = (size_t)2 * en.V;
     const double* fin = a.field_in + (size_t)b * fs;
     double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
-    en.iters_out = a.iters ? a.iters + (size_t)b * a.pr.nlayers : nullptr;
-    if (a.pr.nlayers > 0) en.load_geom_table();
+    ex.sync();
+    if (ex.tid() == 0) en.iters_out = a.iters ? a.iters + (size_t)b * a.pr.nlayers : nullptr;
+    ex.sync();
     double* llj = a.layer_logJ ? a.layer_logJ + (size_t)b * a.pr.nlayers : nullptr;
     switch (a.mode) {
     case MODE_FLOW_FWD: {

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -129,9 +130,16 @@ struct CtaExec {
 
 __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
-    CtaExec ex{ fthmc_dyn_smem };
-    double* ws = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(ex, a, ws, b);
+    // the engine object lives in (static) shared memory: its members are read by every noinline phase
+    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<CtaExec>)];
+    Engine<CtaExec>* en = reinterpret_cast<Engine<CtaExec>*>(en_buf);
+    if (threadIdx.x == 0) {
+        CtaExec ex{ fthmc_dyn_smem };
+        new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
+    }
+    __syncthreads();
+    if (a.pr.nlayers > 0) en->load_geom_table();
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(*en, a, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -299,12 +307,22 @@ static int chain_threads(int L0, int L1, bool flow) {
 }
 static size_t chain_smem_bytes(int L0, int L1, bool flow) { return (engine_smem_doubles(L0, L1, flow) + 64) * sizeof(double); }
 
+// static shared memory of k_chain (the engine object), which counts against the per-block opt-in limit
+static int chain_static_smem() {
+    static int v = -1;
+    if (v < 0) {
+        cudaFuncAttributes fa;
+        v = cudaFuncGetAttributes(&fa, k_chain) == cudaSuccess ? (int)fa.sharedSizeBytes : 1024;
+    }
+    return v;
+}
+
 // grid of the persistent kernel: one CTA per chain up to what is co-resident on the device
 static int chain_grid(int B, int L0, int L1, bool flow, int* occ_out = nullptr) {
     DevInfo& d = devinfo();
     int occ = 1;
     size_t smem = chain_smem_bytes(L0, L1, flow);
-    cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin);
+    cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem());
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain, chain_threads(L0, L1, flow), smem) != cudaSuccess || occ < 1) occ = 1;
     if (occ_out) *occ_out = occ;
     long long g = (long long)d.sm * occ;
@@ -318,7 +336,7 @@ static int check_lattice(int B, int L0, int L1, bool flow) {
     if (!d.ok) return fail(FTHMC_E_ARG, "no CUDA device");
     if (flow && (size_t)L0 * L1 > (size_t)OFF_W3T)
         return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
-    if (chain_smem_bytes(L0, L1, flow) > (size_t)d.smem_optin)
+    if (chain_smem_bytes(L0, L1, flow) + chain_static_smem() > (size_t)d.smem_optin)
         return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
     return 0;
 }

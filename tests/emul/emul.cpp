@@ -44,6 +44,8 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
     a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
     a.seed = seed; a.traj = traj; a.chain0 = 0;
     SerialExec ex{ smem.data() };
-    for (int b = 0; b < B; ++b) run_chain(ex, a, ws.data(), b);
+    Engine<SerialExec> en(ex, a.pr, ws.data());
+    if (nlayers > 0) en.load_geom_table();
+    for (int b = 0; b < B; ++b) run_chain(en, a, b);
     return 0;
 }
