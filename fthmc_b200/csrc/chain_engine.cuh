@@ -32,7 +32,18 @@
 #define FT_PHASE
 #endif
 
+// Optional per-phase cycle accounting (development builds only: -DFT_PROFILE).  E must then provide
+// clock() and prof_add(id, cycles).
+#ifdef FT_PROFILE
+#define FT_T(id, ...) do { long long t0_ = ex.clock(); __VA_ARGS__; ex.prof_add(id, ex.clock() - t0_); } while (0)
+#else
+#define FT_T(id, ...) do { __VA_ARGS__; } while (0)
+#endif
+
 namespace fthmc {
+
+enum ProfId { PF_PLANES = 0, PF_CONV1, PF_CONV2, PF_CONV3F, PF_CONV3R, PF_OUTGRAD, PF_CONV3T, PF_CONV2T, PF_CONV1T,
+              PF_SCATTER, PF_ISSUE, PF_WFORCE, PF_LEAP, PF_MISC, PF_N };
 
 // ---- network shape (every reference config: hidden_sizes=[8,8], n_mixture_comps=2, kernel 3) ----
 constexpr int NH = 8;          // hidden channels of both hidden layers
@@ -127,29 +138,59 @@ FT_HD double rcp_ge1(double d) {
 #endif
 }
 
-FT_HD void act_fwd(int act, double z, double& h) {
-    if (act == ACT_SILU) {
-        h = z * rcp_ge1(1.0 + exp_fast(-z));
-    } else if (act == ACT_LEAKY) {
-        h = z > 0.0 ? z : 0.01 * z;
-    } else {
-        h = z > 0.0 ? z : 0.0;
-    }
+// activation (and derivative) with the kind as a compile-time parameter: the element loops below are
+// unrolled and must stay branch-free so that several exp chains interleave in one warp
+template <int ACT> FT_HD void act_fwd_t(double z, double& h) {
+    if (ACT == ACT_SILU) h = z * rcp_ge1(1.0 + exp_fast(-z));
+    else if (ACT == ACT_LEAKY) h = z > 0.0 ? z : 0.01 * z;
+    else h = z > 0.0 ? z : 0.0;
 }
-
-// activation and its derivative
-FT_HD void act_fwd_der(int act, double z, double& h, double& d) {
-    if (act == ACT_SILU) {
+template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
+    if (ACT == ACT_SILU) {
         double sg = rcp_ge1(1.0 + exp_fast(-z));
         h = z * sg;
         d = sg * (1.0 + z * (1.0 - sg));
-    } else if (act == ACT_LEAKY) {
+    } else if (ACT == ACT_LEAKY) {
         h = z > 0.0 ? z : 0.01 * z;
         d = z > 0.0 ? 1.0 : 0.01;
     } else {
         h = z > 0.0 ? z : 0.0;
         d = z > 0.0 ? 1.0 : 0.0;
     }
+}
+// in-place activation of n of this thread's own values buf[i0 + (e / inner) * s_outer + (e % inner) * s_inner];
+// dsave != nullptr: the derivative goes to the same index of the global layer block
+template <int ACT, int N, int INNER> FT_HD void act_pass(double* buf, double* dsave, int i0, int s_outer, int s_inner) {
+    // blocks of U elements: all loads, then U independent chains, then all stores (a load after a store
+    // to the same array would otherwise serialise the chains)
+    constexpr int U = 4;
+    static_assert(N % U == 0, "element count must be a multiple of the block");
+#pragma unroll 1
+    for (int e0 = 0; e0 < N; e0 += U) {
+        int idx[U]; double z[U], h[U], d[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int e = e0 + j;
+            idx[j] = i0 + (e / INNER) * s_outer + (e % INNER) * s_inner;
+            z[j] = buf[idx[j]];
+        }
+        if (dsave) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) act_fwd_der_t<ACT>(z[j], h[j], d[j]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) { buf[idx[j]] = h[j]; dsave[idx[j]] = d[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) act_fwd_t<ACT>(z[j], h[j]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) buf[idx[j]] = h[j];
+        }
+    }
+}
+template <int N, int INNER> FT_HD void act_pass_any(int act, double* buf, double* dsave, int i0, int s_outer, int s_inner) {
+    if (act == ACT_SILU) act_pass<ACT_SILU, N, INNER>(buf, dsave, i0, s_outer, s_inner);
+    else if (act == ACT_LEAKY) act_pass<ACT_LEAKY, N, INNER>(buf, dsave, i0, s_outer, s_inner);
+    else act_pass<ACT_RELU, N, INNER>(buf, dsave, i0, s_outer, s_inner);
 }
 
 // mean_k mod(2 atan(e^{s_k} tan(x/2)))   (ipynb/field_transformation.py:249-257), es_k = e^{s_k}
@@ -425,24 +466,9 @@ struct Engine {
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int o = 0; o < NH; ++o) A[(o * Cn + 4 * gi + q) * R + r] = z[q][o];
-            // activation pass as a rolled loop over this thread's own 32 values (keeps the code small:
-            // a fully unrolled exp() per element overflows the instruction cache)
-            const int base = 4 * gi * R + r;
-            if (d1_save) {
-#pragma unroll 4
-                for (int e = 0; e < 4 * NH; ++e) {
-                    const int idx = (e >> 2) * Cn * R + (e & 3) * R + base;
-                    double h, d; act_fwd_der(act, A[idx], h, d);
-                    A[idx] = h; d1_save[idx] = d;
-                }
-            } else {
-#pragma unroll 4
-                for (int e = 0; e < 4 * NH; ++e) {
-                    const int idx = (e >> 2) * Cn * R + (e & 3) * R + base;
-                    double h; act_fwd(act, A[idx], h);
-                    A[idx] = h;
-                }
-            }
+            // activation pass as a partially unrolled loop over this thread's own 32 values (a fully
+            // unrolled exp() per element overflows the instruction cache); element e -> channel e/4, column e%4
+            act_pass_any<4 * NH, 4>(act, A, d1_save, 4 * gi * R + r, Cn * R, R);
         }
     }
 
@@ -488,24 +514,7 @@ struct Engine {
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int o = 0; o < NH; ++o) B[(o * 3 * g.G + 3 * gi + k) * R + r] = acc[k][o];
-            const int base = 3 * gi * R + r, cs = 3 * g.G * R;
-            if (d2_save) {
-#pragma unroll 4
-                for (int e = 0; e < 3 * NH; ++e) {
-                    const int o = e / 3, k = e - 3 * o;
-                    const int idx = o * cs + k * R + base;
-                    double h, d; act_fwd_der(act, B[idx], h, d);
-                    B[idx] = h; d2_save[idx] = d;
-                }
-            } else {
-#pragma unroll 4
-                for (int e = 0; e < 3 * NH; ++e) {
-                    const int o = e / 3, k = e - 3 * o;
-                    const int idx = o * cs + k * R + base;
-                    double h; act_fwd(act, B[idx], h);
-                    B[idx] = h;
-                }
-            }
+            act_pass_any<3 * NH, 3>(act, B, d2_save, 3 * gi * R + r, 3 * g.G * R, R);
         }
     }
 
@@ -565,17 +574,16 @@ struct Engine {
     // save: also write the layer block the reverse sweep of ft_force needs.
     FT_HD double layer_forward(int l, bool want_logJ, bool save) {
         LayerGeom g = geom(l);
-        issue_weights(l, false);              // lands while the plaquette planes are computed
-        ph_planes(g, save ? wsCS(l) : nullptr);
-        ex.template async_wait<0>();
-        ex.sync();
-        ph_conv1(g, save ? wsD1(l) : nullptr);
-        ex.sync();
-        ph_conv2(g, save ? wsD2(l) : nullptr);
-        ex.sync();
-        double lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
-        double tot = want_logJ ? ex.sum(lj) : 0.0;
-        ex.sync();
+        double lj = 0.0, tot = 0.0;
+        FT_T(PF_PLANES, issue_weights(l, false);              // lands while the plaquette planes are computed
+             ph_planes(g, save ? wsCS(l) : nullptr);
+             ex.template async_wait<0>();
+             ex.sync());
+        FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr); ex.sync());
+        FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr); ex.sync());
+        FT_T(PF_CONV3F, lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
+             tot = want_logJ ? ex.sum(lj) : 0.0;
+             ex.sync());
         return tot;
     }
 
@@ -638,19 +646,18 @@ struct Engine {
 
     FT_HD double layer_reverse(int l, bool want_logJ) {
         LayerGeom g = geom(l);
-        issue_weights(l, false);
-        ph_planes(g, nullptr);
-        ex.template async_wait<0>();
-        ex.sync();
-        ph_conv1(g, nullptr);
-        ex.sync();
-        ph_conv2(g, nullptr);
-        ex.sync();
+        FT_T(PF_PLANES, issue_weights(l, false);
+             ph_planes(g, nullptr);
+             ex.template async_wait<0>();
+             ex.sync());
+        FT_T(PF_CONV1, ph_conv1(g, nullptr); ex.sync());
+        FT_T(PF_CONV2, ph_conv2(g, nullptr); ex.sync());
         int iters = 0;
-        double lj = ph_conv3_reverse(g, want_logJ, &iters);
-        if (iters_out && ex.tid() == 0) iters_out[l] = iters;
-        double tot = want_logJ ? ex.sum(lj) : 0.0;
-        ex.sync();
+        double lj = 0.0, tot = 0.0;
+        FT_T(PF_CONV3R, lj = ph_conv3_reverse(g, want_logJ, &iters);
+             if (iters_out && ex.tid() == 0) iters_out[l] = iters;
+             tot = want_logJ ? ex.sum(lj) : 0.0;
+             ex.sync());
         return tot;
     }
 
@@ -875,21 +882,19 @@ struct Engine {
     // cp.async groups pending on entry, oldest first: [d2(l), d2(l-1), Wt(l), d1(l), cs(l)]
     FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
-        ph_outgrad(g, wsSV(l), wsSO(l));
-        ex.template async_wait<2>();          // d2(l), d2(l-1), Wt(l) have landed
-        ex.sync();
-        ph_conv3T(g, zbuf(l));
-        ex.sync();
-        ph_conv2T(g, zbuf(l));                // waits for d1(l) after its MAC loop
-        ex.sync();
-        issue_d2(l - 2);                      // zbuf(l) is free again          pending: [cs(l), d2(l-2)]
-        ph_conv1T(g);                         // waits for cs(l) after its MAC loop
-        ex.sync();
-        issue_weights(l - 1, true);           // W(transposed), A and CS are free
-        issue_d1(l - 1);
-        issue_cs(l - 1);                      // pending: [d2(l-2), Wt(l-1), d1(l-1), cs(l-1)]
-        ph_scatter();
-        ex.sync();
+        FT_T(PF_OUTGRAD, ph_outgrad(g, wsSV(l), wsSO(l));
+             ex.template async_wait<2>();          // d2(l), d2(l-1), Wt(l) have landed
+             ex.sync());
+        FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
+        FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
+             ex.sync());
+        FT_T(PF_ISSUE, issue_d2(l - 2));           // zbuf(l) is free again          pending: [cs(l), d2(l-2)]
+        FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
+             ex.sync());
+        FT_T(PF_ISSUE, issue_weights(l - 1, true); // W(transposed), A and CS are free
+             issue_d1(l - 1);
+             issue_cs(l - 1));                     // pending: [d2(l-2), Wt(l-1), d1(l-1), cs(l-1)]
+        FT_T(PF_SCATTER, ph_scatter(); ex.sync());
     }
 
     // =============================================================================================
@@ -926,12 +931,12 @@ struct Engine {
         flow_forward(false, true);
         ex.sync();                        // the layer blocks are read back through global memory
         const int last = pr.nlayers - 1;
-        issue_d2(last);
-        issue_d2(last - 1);
-        issue_weights(last, true);
-        issue_d1(last);
-        issue_cs(last);
-        wilson_force(beta, pr.conv);      // scratch plane = UA+OUT
+        FT_T(PF_ISSUE, issue_d2(last);
+             issue_d2(last - 1);
+             issue_weights(last, true);
+             issue_d1(last);
+             issue_cs(last));
+        FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         for (int l = last; l >= 0; --l) layer_adjoint(l);
         ex.template async_wait<0>();
     }

@@ -41,7 +41,15 @@ extern "C" unsigned long long fthmc_launch_count(void) { return g_launches.load(
 // ------------------------------------------------------------------------------------------------
 // CTA execution policy for the chain engine
 // ------------------------------------------------------------------------------------------------
+#ifdef FT_PROFILE
+__device__ unsigned long long g_prof[32];
+#endif
+
 struct CtaExec {
+#ifdef FT_PROFILE
+    __device__ long long clock() const { return clock64(); }
+    __device__ void prof_add(int id, long long c) const { if (threadIdx.x == 0) atomicAdd(&g_prof[id], (unsigned long long)c); }
+#endif
     double* red;   // 64 doubles of shared scratch (the first 64 doubles of the dynamic shared memory)
     // base of the engine's arena.  Naming the extern __shared__ symbol here (instead of carrying a
     // generic pointer in the engine) lets nvcc emit LDS/STS rather than generic LD/ST in every phase.
@@ -265,6 +273,14 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* __restrict__ out, in
     for (int i = 0; i < 16; ++i) s += a[i];
     if (s == 123.456) out[0] = s;      // keep the chains alive
 }
+
+#ifdef FT_PROFILE
+extern "C" int fthmc_diag_profile(unsigned long long* out32_host, int reset) {
+    if (out32_host) cudaMemcpyFromSymbol(out32_host, g_prof, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out) {
     if (!scratch || iters <= 0 || blocks <= 0) return fail(FTHMC_E_ARG, "bad probe arguments");
