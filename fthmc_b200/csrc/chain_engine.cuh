@@ -43,7 +43,7 @@
 namespace fthmc {
 
 enum ProfId { PF_PLANES = 0, PF_CONV1, PF_CONV2, PF_CONV3F, PF_CONV3R, PF_OUTGRAD, PF_CONV3T, PF_CONV2T, PF_CONV1T,
-              PF_SCATTER, PF_ISSUE, PF_WFORCE, PF_LEAP, PF_MISC, PF_N };
+              PF_SCATTER, PF_ISSUE, PF_WFORCE, PF_LEAP, PF_MISC, PF_C2_MAC, PF_C2_ACT, PF_C1_MAC, PF_C1_ACT, PF_C2T_MAC, PF_C2T_MUL, PF_N };
 
 // ---- network shape (every reference config: hidden_sizes=[8,8], n_mixture_comps=2, kernel 3) ----
 constexpr int NH = 8;          // hidden channels of both hidden layers
@@ -72,16 +72,22 @@ enum Activation { ACT_SILU = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 // scalar helpers
 // ------------------------------------------------------------------------------------------------
 
-// torch.remainder(x, 2pi) (fmod, then +2pi if negative); convention 1: remainder(x+pi,2pi)-pi.
+// x - floor(x/2pi)*2pi in [0,2pi): what torch.remainder(x, 2pi) returns (fmod, then +2pi if negative).
+// One fma against the double 2pi is exact whenever the quotient is right (the remainder of a double by a
+// double is representable); the two fix-ups catch a quotient that rounded across an integer.  The
+// library fmod() is a bit-serial loop of ~100 instructions and sat on every active site and on every
+// bisection iteration.
+FT_HD double rem_2pi(double x) {
+    const double k = floor(x * 0.15915494309189535);      // 1/(2pi)
+    double r = fma(-k, TWO_PI_D, x);
+    if (r < 0.0) r += TWO_PI_D;
+    if (r >= TWO_PI_D) r -= TWO_PI_D;
+    return r;
+}
+// torch_mod: convention 0 -> [0,2pi) (ipynb/field_transformation.py:17-18); 1 -> remainder(x+pi,2pi)-pi
 FT_HD double mod_2pi(double x, int conv) {
-    if (conv == 0) {
-        double r = fmod(x, TWO_PI_D);
-        if (r != 0.0 && r < 0.0) r += TWO_PI_D;
-        return r;
-    }
-    double r = fmod(x + PI_D, TWO_PI_D);
-    if (r != 0.0 && r < 0.0) r += TWO_PI_D;
-    return r - PI_D;
+    if (conv == 0) return rem_2pi(x);
+    return rem_2pi(x + PI_D) - PI_D;
 }
 
 // hmc_2dU1.py:127-129
@@ -94,7 +100,7 @@ FT_HD double regularize1(double f) {
 // |r| <= 0.347 (remainder 4e-18), scaling through the exponent bits.  About half the instructions of
 // the library exp(): the SiLU evaluations are a quarter of the trajectory's run time.
 FT_HD double exp_fast(double x) {
-    x = x < -708.0 ? -708.0 : (x > 708.0 ? 708.0 : x);
+    x = fmin(fmax(x, -708.0), 708.0);
     const double t = x * 1.4426950408889634074;
     const double n = (t + 6755399441055744.0) - 6755399441055744.0;          // rint(t)
     double r = fma(n, -6.93147180369123816490e-01, x);
@@ -149,7 +155,7 @@ template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
     if (ACT == ACT_SILU) {
         double sg = rcp_ge1(1.0 + exp_fast(-z));
         h = z * sg;
-        d = sg * (1.0 + z * (1.0 - sg));
+        d = fma(sg, fma(-z, sg, z), sg);          // sg * (1 + z * (1 - sg))
     } else if (ACT == ACT_LEAKY) {
         h = z > 0.0 ? z : 0.01 * z;
         d = z > 0.0 ? 1.0 : 0.01;
@@ -158,22 +164,17 @@ template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
         d = z > 0.0 ? 1.0 : 0.0;
     }
 }
-// in-place activation of n of this thread's own values buf[i0 + (e / inner) * s_outer + (e % inner) * s_inner];
-// dsave != nullptr: the derivative goes to the same index of the global layer block
-template <int ACT, int N, int INNER> FT_HD void act_pass(double* buf, double* dsave, int i0, int s_outer, int s_inner) {
-    // blocks of U elements: all loads, then U independent chains, then all stores (a load after a store
-    // to the same array would otherwise serialise the chains)
+// in-place activation of N of this thread's own values buf[index(e)], e = 0..N-1; dsave != nullptr: the
+// derivative goes to the same index of the global layer block.  Blocks of U elements: all loads, then U
+// independent chains, then all stores (a load after a store to the same array would serialise them).
+template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double* dsave, IndexFn index) {
     constexpr int U = 4;
     static_assert(N % U == 0, "element count must be a multiple of the block");
 #pragma unroll 1
     for (int e0 = 0; e0 < N; e0 += U) {
         int idx[U]; double z[U], h[U], d[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int e = e0 + j;
-            idx[j] = i0 + (e / INNER) * s_outer + (e % INNER) * s_inner;
-            z[j] = buf[idx[j]];
-        }
+        for (int j = 0; j < U; ++j) { idx[j] = index(e0 + j); z[j] = buf[idx[j]]; }
         if (dsave) {
 #pragma unroll
             for (int j = 0; j < U; ++j) act_fwd_der_t<ACT>(z[j], h[j], d[j]);
@@ -187,11 +188,15 @@ template <int ACT, int N, int INNER> FT_HD void act_pass(double* buf, double* ds
         }
     }
 }
-template <int N, int INNER> FT_HD void act_pass_any(int act, double* buf, double* dsave, int i0, int s_outer, int s_inner) {
-    if (act == ACT_SILU) act_pass<ACT_SILU, N, INNER>(buf, dsave, i0, s_outer, s_inner);
-    else if (act == ACT_LEAKY) act_pass<ACT_LEAKY, N, INNER>(buf, dsave, i0, s_outer, s_inner);
-    else act_pass<ACT_RELU, N, INNER>(buf, dsave, i0, s_outer, s_inner);
+template <int N, class IndexFn> FT_HD void act_pass_any(int act, double* buf, double* dsave, IndexFn index) {
+    if (act == ACT_SILU) act_pass<ACT_SILU, N>(buf, dsave, index);
+    else if (act == ACT_LEAKY) act_pass<ACT_LEAKY, N>(buf, dsave, index);
+    else act_pass<ACT_RELU, N>(buf, dsave, index);
 }
+
+struct alignas(16) dbl2 { double x, y; };
+FT_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
+FT_HD void st2(double* p, double x, double y) { dbl2 v; v.x = x; v.y = y; *reinterpret_cast<dbl2*>(p) = v; }
 
 // mean_k mod(2 atan(e^{s_k} tan(x/2)))   (ipynb/field_transformation.py:249-257), es_k = e^{s_k}
 FT_HD double mixture_fwd(double x, double es0, double es1, int conv) {
@@ -460,16 +465,38 @@ struct Engine {
         const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
+#ifdef FT_PROFILE
+            long long tp0 = ex.clock();
+#endif
             double z[4][NH];
             conv1_z(CS, W, g, gi, r, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int o = 0; o < NH; ++o) A[(o * Cn + 4 * gi + q) * R + r] = z[q][o];
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C1_MAC, ex.clock() - tp0); tp0 = ex.clock();
+#endif
             // activation pass as a partially unrolled loop over this thread's own 32 values (a fully
             // unrolled exp() per element overflows the instruction cache); element e -> channel e/4, column e%4
-            act_pass_any<4 * NH, 4>(act, A, d1_save, 4 * gi * R + r, Cn * R, R);
+            const int i0 = 4 * gi * R + r, so = Cn * R;
+            act_pass_any<4 * NH>(act, A, d1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C1_ACT, ex.clock() - tp0);
+#endif
         }
+    }
+
+    // task decomposition of the two big convolutions: t -> (stripe group gi, channel half h, row pair rp).
+    // A thread owns rows {2rp, 2rp+1} and 4 of the 8 channels: every weight it loads (128-bit) feeds both
+    // rows, every input feeds up to 9 taps x 4 channels, and the two halves of a warp read the same inputs
+    // (broadcast).  This keeps the shared-memory pipe under the fp64 pipe.
+    FT_HD void task2(const LayerGeom& g, int t, int& gi, int& h, int& r0) const {
+        const int R = g.R, hr = R >> 1;
+        gi = t / R;
+        const int rem = t - gi * R;
+        h = rem / hr;
+        r0 = 2 * (rem - h * hr);
     }
 
     // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
@@ -478,43 +505,64 @@ struct Engine {
         double* B = sm(oB);
         const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
-            int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
+            int gi, h, r0;
+            task2(g, t, gi, h, r0);
+            const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
             int cc[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) { int c = 4 * gi - 2 + j; cc[j] = c < 0 ? c + Cn : (c >= Cn ? c - Cn : c); }
-            double acc[3][NH];
+            for (int j = 0; j < 5; ++j) { int c = 4 * gi - 2 + j; cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            double acc[2][3][4];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int o = 0; o < 4; ++o) {
+                const double bv = W[OFF_B2 + 4 * h + o];
 #pragma unroll
-                for (int o = 0; o < NH; ++o) acc[k][o] = W[OFF_B2 + o];
+                for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc[dr][k][o] = bv;
+            }
+#ifdef FT_PROFILE
+            long long tp0 = ex.clock();
+#endif
 #pragma unroll 1
             for (int ci = 0; ci < NH; ++ci) {
-                double in[3][5];
+                double in[4][5];
                 const double* Ap = A + ci * Cn * R;
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) in[a][j] = Ap[cc[j] * R + rr[a]];
-                const double* wc = W + OFF_W2F + ci * 9 * NH;
+                for (int j = 0; j < 5; ++j) {
+                    const double* col = Ap + cc[j];
+                    in[0][j] = col[rm];
+                    const dbl2 m = ld2(col + r0);
+                    in[1][j] = m.x; in[2][j] = m.y;
+                    in[3][j] = col[rp];
+                }
+                const double* wc = W + OFF_W2F + ci * 9 * NH + 4 * h;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
-                        const double* w = wc + (a * 3 + b) * NH;
+                        const dbl2 w01 = ld2(wc + (a * 3 + b) * NH), w23 = ld2(wc + (a * 3 + b) * NH + 2);
+                        const double w[4] = { w01.x, w01.y, w23.x, w23.y };
 #pragma unroll
-                        for (int o = 0; o < NH; ++o) {
-                            double wv = w[o];
+                        for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) acc[k][o] = fma(wv, in[a][k + b], acc[k][o]);
-                        }
+                            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                                for (int o = 0; o < 4; ++o) acc[dr][k][o] = fma(w[o], in[dr + a][k + b], acc[dr][k][o]);
                     }
             }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_MAC, ex.clock() - tp0); tp0 = ex.clock();
+#endif
+            const int cs = 3 * g.G * R, i0 = (4 * h * 3 * g.G + 3 * gi) * R + r0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int o = 0; o < 4; ++o)
 #pragma unroll
-                for (int o = 0; o < NH; ++o) B[(o * 3 * g.G + 3 * gi + k) * R + r] = acc[k][o];
-            act_pass_any<3 * NH, 3>(act, B, d2_save, 3 * gi * R + r, 3 * g.G * R, R);
+                for (int k = 0; k < 3; ++k) st2(B + i0 + o * cs + k * R, acc[0][k][o], acc[1][k][o]);
+            // element e -> (channel e/6, column (e/2)%3, row e%2)
+            act_pass_any<24>(act, B, d2_save, [=](int e) { return i0 + (e / 6) * cs + ((e >> 1) % 3) * R + (e & 1); });
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_ACT, ex.clock() - tp0);
+#endif
         }
     }
 
@@ -735,103 +783,132 @@ struct Engine {
         }
     }
 
-    // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1))
+    // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1)); same task shape as ph_conv2
     FT_PHASE void ph_conv2T(const LayerGeom g, int oZ) {
         const double* C = sm(oZ); const double* W = sm(oW);
         double* A = sm(oA);
         const int T = g.G * g.R, R = g.R, G = g.G;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
-            int gn = gi + 1 == G ? 0 : gi + 1;
-            int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
+            int gi, h, r0;
+            task2(g, t, gi, h, r0);
+            const int gn = gi + 1 == G ? 0 : gi + 1;
+            const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
             // source column slots j=0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1,4g,4g+1,4g+3,4g+4
-            int sc[5] = { 3 * gi, 3 * gi + 1, 3 * gi + 2, 3 * gn, 3 * gn + 1 };
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
             const int CO[5] = { -1, 0, 1, 3, 4 };                                // column offsets from 4g
-            double acc[4][NH];
+#ifdef FT_PROFILE
+            long long tp0 = ex.clock();
+#endif
+            double acc[2][4][4];                                                 // [row][column q][channel]
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci) acc[q][ci] = 0.0;
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = 0.0;
 #pragma unroll 1
             for (int o = 0; o < NH; ++o) {
                 const double* Cp = C + o * 3 * G * R;
-                double zb[3][5];
+                double zb[4][5];                                                 // rows r0-1 .. r0+2
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) zb[a][j] = Cp[sc[j] * R + rs[a]];
+                for (int j = 0; j < 5; ++j) {
+                    const double* col = Cp + sc[j];
+                    zb[0][j] = col[rm];
+                    const dbl2 m = ld2(col + r0);
+                    zb[1][j] = m.x; zb[2][j] = m.y;
+                    zb[3][j] = col[rp];
+                }
+                const double* wo = W + OFF_W2T + o * 9 * NH + 4 * h;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int j = 0; j < 5; ++j)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int b = q - CO[j] + 1;           // src column = col - b + 1
+                            const int b = q - CO[j] + 1;           // source column = column - b + 1
                             if (b >= 0 && b <= 2) {
-                                const double* w = W + OFF_W2T + ((o * 3 + a) * 3 + b) * NH;
+                                const dbl2 w01 = ld2(wo + (a * 3 + b) * NH), w23 = ld2(wo + (a * 3 + b) * NH + 2);
+                                const double w[4] = { w01.x, w01.y, w23.x, w23.y };
+                                // output row r0+dr reads source row r0+dr-a+1 == zb[dr - a + 2]
 #pragma unroll
-                                for (int ci = 0; ci < NH; ++ci) acc[q][ci] = fma(w[ci], zb[a][j], acc[q][ci]);
+                                for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+                                    for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = fma(w[ci], zb[dr - a + 2][j], acc[dr][q][ci]);
                             }
                         }
             }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2T_MAC, ex.clock() - tp0); tp0 = ex.clock();
+#endif
             ex.template async_wait<1>();          // this thread's own act'(z1) elements have landed in A
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci) {
-                    const int idx = (ci * g.Cn + 4 * gi + q) * R + r;
-                    A[idx] = acc[q][ci] * A[idx];
+                for (int ci = 0; ci < 4; ++ci) {
+                    double* p = A + ((4 * h + ci) * g.Cn + 4 * gi + q) * R + r0;
+                    const dbl2 d = ld2(p);
+                    st2(p, acc[0][q][ci] * d.x, acc[1][q][ci] * d.y);
                 }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2T_MUL, ex.clock() - tp0);
+#endif
         }
     }
 
-    // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar on the lattice (PB, pitch LP)
+    // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar in the canonical layout
+    // PB[c][r] (the unused forward-weight slots of W: V <= OFF_W3T doubles)
     FT_PHASE void ph_conv1T(const LayerGeom g) {
         const double* A = sm(oA); const double* W = sm(oW); const double* CS = sm(oCS); const double* UA = sm(oUA);
-        double* PB = sm(oW);                  // Pbar plane (pitch L1) lives in the unused forward-weight slots
-        const int LP = L1;
+        double* PB = sm(oW);
         const int T = g.G * g.R, R = g.R, Cn = g.Cn;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
-            int n0, n1;
-            site(g, r, 4 * gi, n0, n1);     PB[n0 * LP + n1] = UA[t];
-            site(g, r, 4 * gi + 3, n0, n1); PB[n0 * LP + n1] = 0.0;
+            double gc[2] = { 0.0, 0.0 }, gs[2] = { 0.0, 0.0 };
+#pragma unroll 2
+            for (int o = 0; o < NH; ++o) {
+                double v[3][4];                                                   // rows r-a+1, columns 4g..4g+3
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[a][q] = A[(o * Cn + 4 * gi + q) * R + rs[a]];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const dbl2 w = ld2(W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {                             // frozen column 4g+1+k reads column 4g+1+k-b+1
+                            gc[k] = fma(w.x, v[a][k + 2 - b], gc[k]);
+                            gs[k] = fma(w.y, v[a][k + 2 - b], gs[k]);
+                        }
+                    }
+            }
+            PB[(4 * gi) * R + r] = UA[t];
+            PB[(4 * gi + 3) * R + r] = 0.0;
+            ex.template async_wait<1>();          // this thread's own cos/sin elements have landed in CS
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int c = 4 * gi + 1 + k;
-                double gc = 0.0, gs = 0.0;
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const int cs = c - b + 1;                                  // 4g .. 4g+3: always in range
-#pragma unroll 2
-                    for (int o = 0; o < NH; ++o)
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                            double v = A[(o * Cn + cs) * R + rs[a]];
-                            const double* w = W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2;
-                            gc = fma(w[0], v, gc); gs = fma(w[1], v, gs);
-                        }
-                }
-                ex.template async_wait<1>();      // this thread's own cos/sin elements have landed in CS
                 double cp = CS[(2 * gi + k) * R + r], sp = CS[V / 2 + (2 * gi + k) * R + r];
-                site(g, r, c, n0, n1);
-                PB[n0 * LP + n1] = -sp * gc + cp * gs;
+                PB[(4 * gi + 1 + k) * R + r] = -sp * gc[k] + cp * gs[k];
             }
         }
     }
 
-    // GR += plaquette^T(Pbar)
-    FT_PHASE void ph_scatter() {
+    // GR += plaquette^T(Pbar); threads run along the stripe direction r (conflict-free on PB and on the padded GR)
+    FT_PHASE void ph_scatter(const LayerGeom g) {
         const double* PB = sm(oW);
         double* GR = sm(oGR);
-        const int LP = L1;
+        const int R = g.R, Cn = g.Cn;
         for (int i = ex.tid(); i < V; i += ex.nt()) {
-            int n0 = i / L1, n1 = i - n0 * L1;
-            int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
-            double pb = PB[n0 * LP + n1];
-            GR[xi(0, n0, n1)] += pb - PB[n0 * LP + n1m];
-            GR[xi(1, n0, n1)] += PB[n0m * LP + n1] - pb;
+            const int c = i / R, r = i - c * R;
+            const int cm = c == 0 ? Cn - 1 : c - 1, rm = r == 0 ? R - 1 : r - 1;
+            const double pb = PB[i], pmc = PB[cm * R + r], pmr = PB[c * R + rm];
+            int n0, n1; site(g, r, c, n0, n1);
+            // mu=0: (n0,n1)=(r,c+off): P(n-e1)=pmc, P(n-e0)=pmr;  mu=1: (n0,n1)=(c+off,r): P(n-e1)=pmr, P(n-e0)=pmc
+            const double pm1 = g.mu == 0 ? pmc : pmr, pm0 = g.mu == 0 ? pmr : pmc;
+            GR[xi(0, n0, n1)] += pb - pm1;
+            GR[xi(1, n0, n1)] += pm0 - pb;
         }
     }
 
@@ -851,11 +928,12 @@ struct Engine {
             double* A = sm(oA); const double* src = wsD1(l);
             const int T = g.G * g.R, R = g.R;
             for (int t = ex.tid(); t < T; t += ex.nt()) {
-                const int gi = t / R, r = t - gi * R;
+                int gi, h, r0;
+                task2(g, t, gi, h, r0);
 #pragma unroll 8
-                for (int e = 0; e < 4 * NH; ++e) {
-                    const int idx = ((e >> 2) * g.Cn + 4 * gi + (e & 3)) * R + r;
-                    ex.async_copy8(A + idx, src + idx);
+                for (int e = 0; e < 16; ++e) {                      // (channel e/4, column e%4), rows r0, r0+1
+                    const int idx = ((4 * h + (e >> 2)) * g.Cn + 4 * gi + (e & 3)) * R + r0;
+                    ex.async_copy16(A + idx, src + idx);
                 }
             }
         }
@@ -894,7 +972,7 @@ struct Engine {
         FT_T(PF_ISSUE, issue_weights(l - 1, true); // W(transposed), A and CS are free
              issue_d1(l - 1);
              issue_cs(l - 1));                     // pending: [d2(l-2), Wt(l-1), d1(l-1), cs(l-1)]
-        FT_T(PF_SCATTER, ph_scatter(); ex.sync());
+        FT_T(PF_SCATTER, ph_scatter(g); ex.sync());
     }
 
     // =============================================================================================

@@ -75,6 +75,12 @@ struct CtaExec {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 #endif
     }
+    // 16-byte cp.async of one aligned pair
+    __host__ __device__ void async_copy16(double* dst, const double* src) const {
+#ifdef __CUDA_ARCH__
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+    }
     __host__ __device__ void async_commit() const {
 #ifdef __CUDA_ARCH__
         asm volatile("cp.async.commit_group;\n" ::: "memory");

@@ -14,6 +14,7 @@ struct SerialExec {
     double* smem() const { return arena; }
     void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
     void async_copy8(double* dst, const double* src) const { *dst = *src; }
+    void async_copy16(double* dst, const double* src) const { dst[0] = src[0]; dst[1] = src[1]; }
     void async_commit() const {}
     template <int N> void async_wait() const {}
     int tid() const { return 0; }
