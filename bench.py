@@ -198,15 +198,13 @@ def run_ours(a):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
     obs = torch.zeros(7, dtype=torch.float64, device=dev)
 
+    from fthmc_b200 import shard
+    chain0, _ = shard.chain_partition(world * B, rank, world)
+
     def step(xin, it):
         """one trajectory for every chain + the observables reduction (all-reduced when N>1)"""
-        r = ft.ft_hmc_batch(P, pf, xin, seed=20261018, traj=it, chain0=rank * B)
-        q = r["topo"]
-        o = torch.stack([r["plaq"].sum(), q.sum(), (q * q).sum(), r["acc"].double().sum(), r["dH"].sum(),
-                         r["exp_mdH"].sum(), torch.tensor(float(B), device=q.device)])
-        if world > 1:
-            dist.all_reduce(o)
-        return r, o
+        r = ft.ft_hmc_batch(P, pf, xin, seed=20261018, traj=it, chain0=chain0)
+        return r, shard.allreduce_observables(shard.local_observable_sums(r))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -227,13 +225,9 @@ def run_ours(a):
     for k in range(a.steps):
         flush.zero_()
         ev[k][0].record()
-        r = ft.ft_hmc_batch(P, pf, x, seed=20261018, traj=it, chain0=rank * B)
+        r = ft.ft_hmc_batch(P, pf, x, seed=20261018, traj=it, chain0=chain0)
         ev[k][1].record()                                   # the dominant kernel alone
-        q = r["topo"]
-        obs = torch.stack([r["plaq"].sum(), q.sum(), (q * q).sum(), r["acc"].double().sum(), r["dH"].sum(),
-                           r["exp_mdH"].sum(), torch.tensor(float(B), device=dev)])
-        if world > 1:
-            dist.all_reduce(obs)
+        obs = shard.allreduce_observables(shard.local_observable_sums(r))
         ev[k][2].record()
         x = r["field"]; it += 1
     sync_all()
@@ -256,7 +250,7 @@ def run_ours(a):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = ft.ft_hmc_batch(P, pf, hx, seed=20261018, traj=it, chain0=rank * B)    # CPU in -> CPU out
+        r = ft.ft_hmc_batch(P, pf, hx, seed=20261018, traj=it, chain0=chain0)    # CPU in -> CPU out
         e1.record(); torch.cuda.synchronize()
         e2e_ms += e0.elapsed_time(e1)
         hx = r["field"]; it += 1
@@ -291,8 +285,15 @@ def run_ours(a):
     peaks = measured_peaks()
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     alg_bytes = B * (2 * L * L * 8 * 2 + 32)
+    traffic = None          # measured DRAM bytes per launch: ncu --set full capture of the same kernel, scaled per chain
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if (a.L, a.layers, a.nstep) == (32, 24, 10):
+            traffic = tj["dram_bytes_per_chain_traj"] * B
+    except Exception:
+        pass
     roof = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": None, "kernel": "k_chain", "kernel_ms": kms,
+            "traffic": traffic, "kernel": "k_chain", "kernel_ms": kms,
             "peak_source": "fp64 DFMA probe kernel timed in this run (MEASURED_PEAKS.json carries no fp64 figure); "
                            "nominal B200 fp64 is 37 TFLOP/s",
             "alg_flop_per_chain_traj": alg_flop_per_chain_traj(a),
