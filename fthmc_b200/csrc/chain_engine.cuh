@@ -235,12 +235,24 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
 //   E::smem()                         base of the chain's shared-memory arena (address space known to nvcc)
 //   E::async_copy(dst_smem, src_global, ndoubles), E::async_commit(), E::async_wait<N>()   (cp.async groups)
+//
+// Cluster mode (E::kCluster, lattices too large for one SM: L = 64 .. 128).  A thread-block cluster of nr =
+// E::nranks() CTAs owns one chain.  The link field X and the gradient GR are split by lattice row blocks
+// (rank k holds n0 in [k*H, (k+1)*H), H = L0/nr); the per-layer planes (CS, UA, OUT, A, B, C, Pbar) are split
+// by canonical column blocks (rank k holds the stripe groups [k*G, (k+1)*G) of the current layer), so every
+// convolution tap is local except the two halo columns conv2 / conv2^T need from the neighbouring rank:
+// those are pushed through distributed shared memory (E::peer) into a halo buffer before the phase.
+// X/GR accesses that fall outside the own row block go through E::peer directly.  E::sync, E::sum and
+// E::maxv are cluster-wide in this mode.  With kCluster == false everything below compiles to the
+// single-CTA code (rank 0 of 1).
 // ------------------------------------------------------------------------------------------------
 struct LayerGeom {
     int mu, off;
     int R;     // sites along the stripes
-    int Cn;    // sites across the stripes (multiple of 4)
-    int G;     // Cn / 4 stripe groups
+    int Cn;    // sites across the stripes held by this rank (multiple of 4); all of them without a cluster
+    int G;     // Cn / 4 stripe groups held by this rank
+    int CnG;   // sites across the stripes of the whole lattice
+    int c0;    // first canonical column of this rank (before the shift by off)
 };
 
 struct EngineParams {
@@ -254,24 +266,25 @@ struct EngineParams {
     const int* loff;       // global: per layer off
 };
 
-// Shared-memory arena (doubles).  Flow: X GR | CS UA OUT | A(8V) B(6V) C(6V) | W.   Plain HMC: X GR | S(V).
-FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true) {
-    size_t V = (size_t)L0 * L1, LP = L1 + 1;
-    if (!flow) return 2 * L0 * LP * 2 + V + 4;
-    return 2 * L0 * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 32 + 4;
+// Shared-memory arena (doubles) of one rank; V = sites per rank.  Flow: X GR | CS UA OUT | A(8V) B(6V) C(6V) | W.
+// Plain HMC: X GR | S(V).
+FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true, int nr = 1) {
+    size_t V = (size_t)L0 * L1 / nr, LP = L1 + 1, H = L0 / nr;
+    if (!flow) return 2 * H * LP * 2 + V + 4;
+    return 2 * H * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 32 + 4;
 }
 
 // Per-layer block of the per-CTA global workspace written by the forward sweep of ft_force and read
 // back (cp.async) by the reverse sweep: act'(z1) [8V], act'(z2) [6V], cos/sin of the frozen
 // plaquettes [V], (s_1,s_2) of the active sites [2 V/4], pre-update active links [V/4].
-FT_HD size_t engine_layer_ws_doubles(int L0, int L1) {
-    size_t V = (size_t)L0 * L1;
+FT_HD size_t engine_layer_ws_doubles(int L0, int L1, int nr = 1) {
+    size_t V = (size_t)L0 * L1 / nr;
     return 15 * V + 3 * (V / 4);
 }
-// per-CTA global workspace (doubles): momenta, x0, y0, then nlayers layer blocks
-FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers) {
+// per-chain global workspace (doubles): momenta, x0, y0 (whole lattice), then for every rank nlayers layer blocks
+FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers, int nr = 1) {
     size_t V = (size_t)L0 * L1;
-    return 3 * 2 * V + (size_t)nlayers * engine_layer_ws_doubles(L0, L1);
+    return 3 * 2 * V + (size_t)nr * nlayers * engine_layer_ws_doubles(L0, L1, nr);
 }
 
 template <class E>
@@ -279,19 +292,23 @@ struct Engine {
     E ex;                 // by value: the engine object itself lives in shared memory on the device, so
                           // that the noinline phases read its members at shared-memory latency
     EngineParams pr;
-    int L0, L1, LP, V, VQ;
+    static constexpr bool CL = E::kCluster;
+    int L0, L1, LP, V, VQ;          // V, VQ: sites per rank (the whole lattice without a cluster)
+    int Vg, nr, rk, H;              // whole-lattice volume, ranks in the cluster, own rank, lattice rows per rank
     int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
     double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
     size_t layStride;
     int* iters_out;                                    // optional global: bisection iterations per layer
 
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
-        L0 = p.L0; L1 = p.L1; LP = L1 + 1; V = L0 * L1; VQ = V / 4;
+        L0 = p.L0; L1 = p.L1; LP = L1 + 1; Vg = L0 * L1;
+        nr = ex.nranks(); rk = ex.rank(); H = L0 / nr; V = Vg / nr; VQ = V / 4;
         int o = 0;
-        oX = o;  o += 2 * L0 * LP;
-        oGR = o; o += 2 * L0 * LP;
-        wsP = ws; wsX0 = ws + 2 * V; wsY0 = ws + 4 * V; wsLay = ws + 6 * V;
-        layStride = engine_layer_ws_doubles(L0, L1);
+        oX = o;  o += 2 * H * LP;
+        oGR = o; o += 2 * H * LP;
+        layStride = engine_layer_ws_doubles(L0, L1, nr);
+        wsP = ws; wsX0 = ws + 2 * Vg; wsY0 = ws + 4 * Vg;
+        wsLay = ws + 6 * (size_t)Vg + (size_t)rk * p.nlayers * layStride;
         iters_out = nullptr;
         oCS = oUA = oOUT = oA = oB = oC = oW = oTab = 0;
         if (p.nlayers == 0) { oS = o; return; }        // plain HMC: only a scratch plane
@@ -326,36 +343,60 @@ struct Engine {
         const unsigned char* tab = reinterpret_cast<const unsigned char*>(sm(oTab));
         g.mu = tab[l]; g.off = tab[128 + l];
         g.R = g.mu == 0 ? L0 : L1;
-        g.Cn = g.mu == 0 ? L1 : L0;
+        g.CnG = g.mu == 0 ? L1 : L0;
+        g.Cn = CL ? g.CnG / nr : g.CnG;
         g.G = g.Cn / 4;
+        g.c0 = CL ? rk * g.Cn : 0;
         return g;
     }
-    FT_HD int xi(int mu, int n0, int n1) const { return (mu * L0 + n0) * LP + n1; }
-    // canonical (row r, shifted column c) -> lattice site
+    // element (mu, n0, n1) of a link-shaped array (X at base oX, GR at base oGR).  Without a cluster: a plain
+    // shared-memory address; with one: the owner rank's copy, through distributed shared memory if it is not ours.
+    FT_HD double* xat(int base, int mu, int n0, int n1) const {
+        if constexpr (!CL) {
+            return sm(base) + (mu * L0 + n0) * LP + n1;
+        } else {
+            const int owner = n0 / H;
+            double* p = sm(base) + (mu * H + (n0 - owner * H)) * LP + n1;
+            return owner == rk ? p : ex.peer(p, owner);
+        }
+    }
+    // canonical (row r, shifted column c of this rank) -> lattice site
     FT_HD void site(const LayerGeom& g, int r, int c, int& n0, int& n1) const {
-        int co = c + g.off; if (co >= g.Cn) co -= g.Cn;
+        int co = c + g.c0 + g.off; if (co >= g.CnG) co -= g.CnG;
         if (g.mu == 0) { n0 = r; n1 = co; } else { n0 = co; n1 = r; }
     }
     // plaquette angle; order 0: ipynb/field_transformation.py:118-119, order 1: qed_helpers.py:83-86 / hmc_2dU1.py:114-120
-    FT_HD double plaq(const double* X, int n0, int n1, int order) const {
+    FT_HD double plaq(int base, int n0, int n1, int order) const {
         int n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1p = n1 + 1 == L1 ? 0 : n1 + 1;
-        double a = X[xi(0, n0, n1)], b = X[xi(1, n0p, n1)], c = X[xi(0, n0, n1p)], d = X[xi(1, n0, n1)];
+        double a = *xat(base, 0, n0, n1), b = *xat(base, 1, n0p, n1), c = *xat(base, 0, n0, n1p), d = *xat(base, 1, n0, n1);
         return order == 0 ? ((a + b) - c) - d : ((a - d) - c) + b;
+    }
+    // i-th link of this rank (i in [0, 2V)) -> index si in the rank's X/GR arrays and gi in the global (2,L0,L1) layout
+    FT_HD void link_map(int i, int& si, int& gi) const {
+        const int n1 = i % L1, rest = i / L1;            // rest = mu*H + local row
+        si = rest * LP + n1;
+        if constexpr (!CL) gi = i;
+        else gi = (rest + (rest >= H ? L0 - H : 0) + rk * H) * L1 + n1;
+    }
+    // i-th site of this rank (i in [0, V)) -> lattice coordinates
+    FT_HD void site_map(int i, int& n0, int& n1) const {
+        n0 = i / L1; n1 = i - n0 * L1;
+        if constexpr (CL) n0 += rk * H;
     }
 
     // ---- global <-> shared field copies (global layout (2,L0,L1) contiguous) ----
     FT_HD void load_field(int off, const double* g) {
         double* dst = sm(off);
         for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
-            int n1 = i % L1, rest = i / L1;
-            dst[rest * LP + n1] = g[i];
+            int si, gi; link_map(i, si, gi);
+            dst[si] = g[gi];
         }
     }
     FT_HD void store_field(double* g, int off) {
         const double* src = sm(off);
         for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
-            int n1 = i % L1, rest = i / L1;
-            g[i] = src[rest * LP + n1];
+            int si, gi; link_map(i, si, gi);
+            g[gi] = src[si];
         }
     }
     // stage layer l's weights (cp.async, one commit group): the forward part [0,OFF_W3T) for the
@@ -371,31 +412,40 @@ struct Engine {
     // =============================================================================================
     // -beta * sum cos P   (order 0: U1GaugeAction, order 1: hmc_2dU1.action)
     FT_PHASE double wilson_action(double beta, int order) {
-        const double* X = sm(oX);
         double acc = 0.0;
-        for (int i = ex.tid(); i < V; i += ex.nt()) acc += cos(plaq(X, i / L1, i % L1, order));
+        for (int i = ex.tid(); i < V; i += ex.nt()) { int n0, n1; site_map(i, n0, n1); acc += cos(plaq(oX, n0, n1, order)); }
         return -beta * ex.sum(acc);
     }
     // floor(0.1 + sum regularize(P) / 2pi)   hmc_2dU1.py:123-124
     FT_PHASE double topo_floor() {
-        const double* X = sm(oX);
         double acc = 0.0;
-        for (int i = ex.tid(); i < V; i += ex.nt()) acc += regularize1(plaq(X, i / L1, i % L1, 1));
+        for (int i = ex.tid(); i < V; i += ex.nt()) { int n0, n1; site_map(i, n0, n1); acc += regularize1(plaq(oX, n0, n1, 1)); }
         return floor(0.1 + ex.sum(acc) / TWO_PI_D);
     }
     // GR = dS/dx of the Wilson action: F0 = beta[sinP(n) - sinP(n-e1)], F1 = beta[sinP(n-e0) - sinP(n)]
     FT_PHASE void wilson_force(double beta, int order) {
-        const double* X = sm(oX);
-        double* GR = sm(oGR);
+        if constexpr (CL) {
+            // the sin(P) plane would need a row halo from the neighbouring rank: recompute the two shifted
+            // plaquettes instead (three sines per site; this phase is well under 1% of a force evaluation)
+            for (int i = ex.tid(); i < V; i += ex.nt()) {
+                int n0, n1; site_map(i, n0, n1);
+                const int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+                const double s = sin(plaq(oX, n0, n1, order)), s1 = sin(plaq(oX, n0, n1m, order)), s0 = sin(plaq(oX, n0m, n1, order));
+                *xat(oGR, 0, n0, n1) = beta * (s - s1);
+                *xat(oGR, 1, n0, n1) = beta * (s0 - s);
+            }
+            ex.sync();
+            return;
+        }
         double* S = sm(oS);                              // scratch plane, pitch L1
-        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(X, i / L1, i % L1, order));
+        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(oX, i / L1, i % L1, order));
         ex.sync();
         for (int i = ex.tid(); i < V; i += ex.nt()) {
             int n0 = i / L1, n1 = i % L1;
             int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
             double s = S[i];
-            GR[xi(0, n0, n1)] = beta * (s - S[n0 * L1 + n1m]);
-            GR[xi(1, n0, n1)] = beta * (S[n0m * L1 + n1] - s);
+            *xat(oGR, 0, n0, n1) = beta * (s - S[n0 * L1 + n1m]);
+            *xat(oGR, 1, n0, n1) = beta * (S[n0m * L1 + n1] - s);
         }
         ex.sync();
     }
@@ -405,17 +455,16 @@ struct Engine {
     // =============================================================================================
     // cos/sin of the frozen plaquettes and the raw active plaquette; cs_save: global copy of CS
     FT_PHASE void ph_planes(const LayerGeom g, double* cs_save) {
-        const double* X = sm(oX);
         double* CS = sm(oCS); double* UA = sm(oUA);
         const int T = g.G * g.R, order = pr.conv;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / g.R, r = t - gi * g.R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
-            UA[t] = plaq(X, n0, n1, order);
+            UA[t] = plaq(oX, n0, n1, order);
 #pragma unroll 1
             for (int k = 0; k < 2; ++k) {
                 site(g, r, 4 * gi + 1 + k, n0, n1);
-                double p = plaq(X, n0, n1, order);
+                double p = plaq(oX, n0, n1, order);
                 double sp, cp;
                 sincos(p, &sp, &cp);
                 const int i = (2 * gi + k) * g.R + r;
@@ -487,6 +536,32 @@ struct Engine {
         }
     }
 
+    // ---- cluster halos (distributed shared memory pushes; no-ops without a cluster) ----
+    // conv2 of the right neighbour's first group reads our last two columns of h1: AH[ci][j][r] in its arena C
+    FT_HD void push_halo_h1(const LayerGeom& g) {
+        if constexpr (CL) {
+            const double* A = sm(oA);
+            double* dst = ex.peer(sm(oC), rk + 1 == nr ? 0 : rk + 1);
+            const int R = g.R, n = NH * 2 * R;
+            for (int i = ex.tid(); i < n; i += ex.nt()) {
+                const int ci = i / (2 * R), rem = i - ci * 2 * R, j = rem / R, r = rem - j * R;
+                dst[i] = A[(ci * g.Cn + g.Cn - 2 + j) * R + r];
+            }
+        }
+    }
+    // conv2^T of the left neighbour's last group reads columns k = 0, 1 of our first group of zbar2: ZH[o][j][r] in its arena C
+    FT_HD void push_halo_zbar2(const LayerGeom& g, int oZ) {
+        if constexpr (CL) {
+            const double* Z = sm(oZ);
+            double* dst = ex.peer(sm(oC), rk == 0 ? nr - 1 : rk - 1);
+            const int R = g.R, n = NH * 2 * R;
+            for (int i = ex.tid(); i < n; i += ex.nt()) {
+                const int o = i / (2 * R), rem = i - o * 2 * R, j = rem / R, r = rem - j * R;
+                dst[i] = Z[(o * 3 * g.G + j) * R + r];
+            }
+        }
+    }
+
     // task decomposition of the two big convolutions: t -> (stripe group gi, channel half h, row pair rp).
     // A thread owns rows {2rp, 2rp+1} and 4 of the 8 channels: every weight it loads (128-bit) feeds both
     // rows, every input feeds up to 9 taps x 4 channels, and the two halves of a warp read the same inputs
@@ -508,9 +583,15 @@ struct Engine {
             int gi, h, r0;
             task2(g, t, gi, h, r0);
             const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
-            int cc[5];
+            // input columns 4g-2 .. 4g+2: offset of channel 0 from A, and the channel stride.  In cluster mode the
+            // two columns left of the rank's first group sit in the halo buffer AH[ci][j][r] (arena C)
+            int cc[5], cst[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) { int c = 4 * gi - 2 + j; cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            for (int j = 0; j < 5; ++j) {
+                int c = 4 * gi - 2 + j;
+                if (CL && c < 0) { cc[j] = (oC - oA) + (c + 2) * R; cst[j] = 2 * R; }
+                else { cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; cst[j] = Cn * R; }
+            }
             double acc[2][3][4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
@@ -526,10 +607,9 @@ struct Engine {
 #pragma unroll 1
             for (int ci = 0; ci < NH; ++ci) {
                 double in[4][5];
-                const double* Ap = A + ci * Cn * R;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    const double* col = Ap + cc[j];
+                    const double* col = A + cc[j] + ci * (CL ? cst[j] : Cn * R);
                     in[0][j] = col[rm];
                     const dbl2 m = ld2(col + r0);
                     in[1][j] = m.x; in[2][j] = m.y;
@@ -590,7 +670,6 @@ struct Engine {
     // sv/so != nullptr: the pre-update active links and (s_1,s_2) go to the global layer block.
     FT_PHASE double ph_conv3_forward(const LayerGeom g, bool want_logJ, double* sv, double* so) {
         const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
-        double* X = sm(oX);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double lj = 0.0;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
@@ -603,10 +682,10 @@ struct Engine {
             double newp = mod_2pi(fx1 + out[2], conv);
             double delta = newp - u;
             int n0, n1; site(g, r, 4 * gi, n0, n1);
-            int li = xi(g.mu, n0, n1);
-            double xo = X[li];
+            double* xl = xat(oX, g.mu, n0, n1);
+            double xo = *xl;
             if (sv) { sv[t] = xo; so[t] = out[0]; so[T + t] = out[1]; }
-            X[li] = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
+            *xl = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
             if (want_logJ) {
                 double c = cos(u / 2), s = sin(u / 2);
                 double l0 = -log(exp(-out[0]) * (c * c) + es0 * (s * s));
@@ -628,6 +707,7 @@ struct Engine {
              ex.template async_wait<0>();
              ex.sync());
         FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr); ex.sync());
+        if constexpr (CL) { push_halo_h1(g); ex.sync(); }
         FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr); ex.sync());
         FT_T(PF_CONV3F, lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
              tot = want_logJ ? ex.sum(lj) : 0.0;
@@ -642,7 +722,7 @@ struct Engine {
     // reaching it, so only the tolerance and max_iter exits exist.
     FT_PHASE double ph_conv3_reverse(const LayerGeom g, bool want_logJ, int* iters) {
         const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
-        double* X = sm(oX); double* OUT = sm(oOUT); double* A = sm(oA);
+        double* OUT = sm(oOUT); double* A = sm(oA);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double* Y = A; double* ES0 = A + T; double* ES1 = A + 2 * T; double* LO = A + 3 * T; double* HI = A + 4 * T;
         double* MID = A + 5 * T;
@@ -679,8 +759,8 @@ struct Engine {
             double x1 = MID[t];
             double delta = x1 - UA[t];
             int n0, n1; site(g, r, 4 * gi, n0, n1);
-            int li = xi(g.mu, n0, n1);
-            X[li] = mod_2pi((g.mu == 0 ? delta : -delta) + X[li], conv);
+            double* xl = xat(oX, g.mu, n0, n1);
+            *xl = mod_2pi((g.mu == 0 ? delta : -delta) + *xl, conv);
             if (want_logJ) {
                 double c = cos(x1 / 2), s = sin(x1 / 2);
                 double l0 = -log(exp(-OUT[t]) * (c * c) + ES0[t] * (s * s));
@@ -699,6 +779,7 @@ struct Engine {
              ex.template async_wait<0>();
              ex.sync());
         FT_T(PF_CONV1, ph_conv1(g, nullptr); ex.sync());
+        if constexpr (CL) { push_halo_h1(g); ex.sync(); }
         FT_T(PF_CONV2, ph_conv2(g, nullptr); ex.sync());
         int iters = 0;
         double lj = 0.0, tot = 0.0;
@@ -717,18 +798,16 @@ struct Engine {
     // put the pre-update active links back, then the adjoint of the mixture transform and of -logJ at
     // the active sites:  OUT <- (s1bar, s2bar, tbar),  UA <- Pbar(active)
     FT_PHASE void ph_outgrad(const LayerGeom g, const double* sv, const double* so) {
-        double* X = sm(oX); const double* GR = sm(oGR);
         double* OUT = sm(oOUT); double* UA = sm(oUA);
         const int T = g.G * g.R, R = g.R, order = pr.conv;
         // the active plaquette only involves its own active link, so restore + plaquette fuse per task
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
-            const int li = xi(g.mu, n0, n1);
-            X[li] = sv[t];
-            double gl = GR[li];
+            *xat(oX, g.mu, n0, n1) = sv[t];
+            double gl = *xat(oGR, g.mu, n0, n1);
             double db = g.mu == 0 ? gl : -gl;                 // delta-bar
-            double u = plaq(X, n0, n1, order);
+            double u = plaq(oX, n0, n1, order);
             double s0 = so[t], s1 = so[T + t];
             double c, s;
             sincos(u / 2, &s, &c);
@@ -794,7 +873,12 @@ struct Engine {
             const int gn = gi + 1 == G ? 0 : gi + 1;
             const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
             // source column slots j=0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1,4g,4g+1,4g+3,4g+4
-            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
+            // In cluster mode the two columns right of the rank's last group sit in the halo buffer ZH[o][j][r] (arena C;
+            // the d2 prefetch is single-buffered in B there)
+            const bool hal = CL && gi + 1 == G;
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R,
+                                hal ? (oC - oZ) : 3 * gn * R, hal ? (oC - oZ) + R : (3 * gn + 1) * R };
+            const int sst = hal ? 2 * R : 3 * G * R;           // channel stride of slots 3, 4
             const int CO[5] = { -1, 0, 1, 3, 4 };                                // column offsets from 4g
 #ifdef FT_PROFILE
             long long tp0 = ex.clock();
@@ -808,11 +892,10 @@ struct Engine {
                     for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = 0.0;
 #pragma unroll 1
             for (int o = 0; o < NH; ++o) {
-                const double* Cp = C + o * 3 * G * R;
                 double zb[4][5];                                                 // rows r0-1 .. r0+2
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    const double* col = Cp + sc[j];
+                    const double* col = C + sc[j] + o * ((CL && j >= 3) ? sst : 3 * G * R);
                     zb[0][j] = col[rm];
                     const dbl2 m = ld2(col + r0);
                     zb[1][j] = m.x; zb[2][j] = m.y;
@@ -898,17 +981,17 @@ struct Engine {
     // GR += plaquette^T(Pbar); threads run along the stripe direction r (conflict-free on PB and on the padded GR)
     FT_PHASE void ph_scatter(const LayerGeom g) {
         const double* PB = sm(oW);
-        double* GR = sm(oGR);
         const int R = g.R, Cn = g.Cn;
         for (int i = ex.tid(); i < V; i += ex.nt()) {
             const int c = i / R, r = i - c * R;
+            // the column left of a rank's first column is the passive column of the previous group: Pbar == 0 there
             const int cm = c == 0 ? Cn - 1 : c - 1, rm = r == 0 ? R - 1 : r - 1;
-            const double pb = PB[i], pmc = PB[cm * R + r], pmr = PB[c * R + rm];
+            const double pb = PB[i], pmc = (CL && c == 0) ? 0.0 : PB[cm * R + r], pmr = PB[c * R + rm];
             int n0, n1; site(g, r, c, n0, n1);
             // mu=0: (n0,n1)=(r,c+off): P(n-e1)=pmc, P(n-e0)=pmr;  mu=1: (n0,n1)=(c+off,r): P(n-e1)=pmr, P(n-e0)=pmc
             const double pm1 = g.mu == 0 ? pmc : pmr, pm0 = g.mu == 0 ? pmr : pmc;
-            GR[xi(0, n0, n1)] += pb - pm1;
-            GR[xi(1, n0, n1)] += pm0 - pb;
+            *xat(oGR, 0, n0, n1) += pb - pm1;
+            *xat(oGR, 1, n0, n1) += pm0 - pb;
         }
     }
 
@@ -917,7 +1000,8 @@ struct Engine {
     // frozen cos/sin are copied element-wise by the thread that will consume them, so their waits sit
     // right before the final multiply inside ph_conv2T / ph_conv1T and need no barrier.
     // Every issue_* commits exactly one group (empty when l < 0) to keep the wait counts uniform.
-    FT_HD int zbuf(int l) const { return (l & 1) ? oB : oC; }
+    // cluster mode: single buffer (B), fetched one layer ahead; arena C holds the halos
+    FT_HD int zbuf(int l) const { return CL ? oB : ((l & 1) ? oB : oC); }
     FT_HD void issue_d2(int l) {
         if (l >= 0) ex.async_copy(sm(zbuf(l)), wsD2(l), 6 * V);
         ex.async_commit();
@@ -964,9 +1048,10 @@ struct Engine {
              ex.template async_wait<2>();          // d2(l), d2(l-1), Wt(l) have landed
              ex.sync());
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
+        if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.sync());
-        FT_T(PF_ISSUE, issue_d2(l - 2));           // zbuf(l) is free again          pending: [cs(l), d2(l-2)]
+        FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again       pending: [cs(l), d2(l-2)]
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
              ex.sync());
         FT_T(PF_ISSUE, issue_weights(l - 1, true); // W(transposed), A and CS are free
@@ -1010,7 +1095,7 @@ struct Engine {
         ex.sync();                        // the layer blocks are read back through global memory
         const int last = pr.nlayers - 1;
         FT_T(PF_ISSUE, issue_d2(last);
-             issue_d2(last - 1);
+             issue_d2(CL ? -1 : last - 1);
              issue_weights(last, true);
              issue_d1(last);
              issue_cs(last));
@@ -1022,8 +1107,8 @@ struct Engine {
     // elementwise helpers on the link field (skip the pitch padding)
     template <class F> FT_HD void for_links(F f) {
         for (int i = ex.tid(); i < 2 * V; i += ex.nt()) {
-            int n1 = i % L1, rest = i / L1;
-            f(rest * LP + n1, i);
+            int si, gi; link_map(i, si, gi);
+            f(si, gi);
         }
     }
 };
@@ -1047,8 +1132,11 @@ struct TrajIO {
 template <class E>
 FT_HD void philox_momenta(Engine<E>& en, const TrajIO& io, double* P) {
     Philox ph{ (uint32_t)io.seed, (uint32_t)(io.seed >> 32) };
-    const int n = 2 * en.V;
-    for (int j = en.ex.tid(); j < n / 2; j += en.ex.nt()) {
+    // each rank draws the momenta of its own links; the counter is the global pair index, so the stream does
+    // not depend on the decomposition (pairs never straddle a lattice row: L1 is even)
+    for (int jl = en.ex.tid(); jl < en.V; jl += en.ex.nt()) {
+        int si, gi; en.link_map(2 * jl, si, gi);
+        const int j = gi >> 1;
         uint32_t r[4];
         ph.gen((uint32_t)j, (uint32_t)io.traj, (uint32_t)io.chain, (uint32_t)(io.chain >> 32) ^ 0x5EEDu, r);
         double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
@@ -1091,18 +1179,18 @@ FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, For
 template <class E>
 FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     auto& ex = en.ex;
-    const int V = en.V;
+    const int V = en.Vg;
     double* P = en.wsP;
     double* X = en.sm(en.oX);
     en.load_field(en.oX, io.field_in);
     ex.sync();
     en.flow_reverse(false);                                     // x = ft_flow_inv(field)
     en.for_links([&](int si, int gi) { en.wsX0[gi] = X[si]; });
-    if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
+    if (io.p_in) en.for_links([&](int, int gi) { P[gi] = io.p_in[gi]; });
     else philox_momenta(en, io, P);
     ex.sync();
     double k0 = 0.0;
-    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k0 += P[i] * P[i];
+    en.for_links([&](int, int gi) { k0 += P[gi] * P[gi]; });
     k0 = ex.sum(k0);
     double s0_plain;
     double h0 = en.ft_action(io.beta, &s0_plain) + 0.5 * k0;    // X <- y0 = F(x)
@@ -1114,7 +1202,7 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;
-    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
+    en.for_links([&](int, int gi) { k1 += P[gi] * P[gi]; });
     k1 = ex.sum(k1);
     double s1_plain;
     double h1 = en.ft_action(io.beta, &s1_plain) + 0.5 * k1;    // X <- F(xr)
@@ -1129,8 +1217,8 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     ex.sync();
     double q = en.topo_floor();
     en.store_field(io.field_out, en.oX);
-    if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
-    if (ex.tid() == 0) {
+    if (io.p_out) en.for_links([&](int, int gi) { io.p_out[gi] = P[gi]; });
+    if (ex.tid() == 0 && en.rk == 0) {
         if (io.out_dH) *io.out_dH = dH;
         if (io.out_expmdH) *io.out_expmdH = e;
         if (io.out_acc) *io.out_acc = acc ? 1 : 0;
@@ -1146,15 +1234,15 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
 template <class E>
 FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     auto& ex = en.ex;
-    const int V = en.V;
+    const int V = en.Vg;
     double* P = en.wsP;
     double* X = en.sm(en.oX);
     en.load_field(en.oX, io.field_in);
-    if (io.p_in) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) P[i] = io.p_in[i]; }
+    if (io.p_in) en.for_links([&](int, int gi) { P[gi] = io.p_in[gi]; });
     else philox_momenta(en, io, P);
     ex.sync();
     double k0 = 0.0;
-    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k0 += P[i] * P[i];
+    en.for_links([&](int, int gi) { k0 += P[gi] * P[gi]; });
     k0 = ex.sum(k0);
     double s0 = en.wilson_action(io.beta, 1);
     double h0 = s0 + 0.5 * k0;
@@ -1162,7 +1250,7 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;
-    for (int i = ex.tid(); i < 2 * V; i += ex.nt()) k1 += P[i] * P[i];
+    en.for_links([&](int, int gi) { k1 += P[gi] * P[gi]; });
     k1 = ex.sum(k1);
     double s1 = en.wilson_action(io.beta, 1);
     double h1 = s1 + 0.5 * k1;
@@ -1177,8 +1265,8 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     ex.sync();
     double q = en.topo_floor();
     en.store_field(io.field_out, en.oX);
-    if (io.p_out) { for (int i = ex.tid(); i < 2 * V; i += ex.nt()) io.p_out[i] = P[i]; }
-    if (ex.tid() == 0) {
+    if (io.p_out) en.for_links([&](int, int gi) { io.p_out[gi] = P[gi]; });
+    if (ex.tid() == 0 && en.rk == 0) {
         if (io.out_dH) *io.out_dH = dH;
         if (io.out_expmdH) *io.out_expmdH = e;
         if (io.out_acc) *io.out_acc = acc ? 1 : 0;

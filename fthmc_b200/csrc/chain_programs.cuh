@@ -40,7 +40,7 @@ struct ChainArgs {
 template <class E>
 FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
     E& ex = en.ex;
-    const size_t fs = (size_t)2 * en.V;
+    const size_t fs = (size_t)2 * en.Vg;
     const double* fin = a.field_in + (size_t)b * fs;
     double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
     ex.sync();
@@ -78,14 +78,14 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
     case MODE_FT_LEAPFROG:
     case MODE_LEAPFROG: {
         en.load_field(en.oX, fin);
-        for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) en.wsP[i] = a.p_in[(size_t)b * fs + i];
+        en.for_links([&](int, int gi) { en.wsP[gi] = a.p_in[(size_t)b * fs + gi]; });
         ex.sync();
         if (a.mode == MODE_FT_LEAPFROG)
             leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.ft_force(a.beta); });
         else
             leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
         en.store_field(fout, en.oX);
-        for (int i = ex.tid(); i < 2 * en.V; i += ex.nt()) a.p_out[(size_t)b * fs + i] = en.wsP[i];
+        en.for_links([&](int, int gi) { a.p_out[(size_t)b * fs + gi] = en.wsP[gi]; });
         ex.sync();
     } break;
     case MODE_FT_HMC:

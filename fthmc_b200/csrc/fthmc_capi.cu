@@ -7,6 +7,7 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false (FMAs are written
 // explicitly in the convolutions; elementwise updates keep the reference's separate mul/add rounding).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -46,6 +47,10 @@ __device__ unsigned long long g_prof[32];
 #endif
 
 struct CtaExec {
+    static constexpr bool kCluster = false;
+    __host__ __device__ int rank() const { return 0; }
+    __host__ __device__ int nranks() const { return 1; }
+    __host__ __device__ double* peer(double* p, int) const { return p; }
 #ifdef FT_PROFILE
     __device__ long long clock() const { return clock64(); }
     __device__ void prof_add(int id, long long c) const { if (threadIdx.x == 0) atomicAdd(&g_prof[id], (unsigned long long)c); }
@@ -141,6 +146,61 @@ struct CtaExec {
 #endif
     }
 };
+
+// One thread-block cluster per chain (lattices beyond one SM's shared memory): same engine, kCluster code path.
+// sync / sum / maxv are cluster-wide; peer() maps a pointer into this CTA's arena to the same offset in a peer's.
+struct ClusterExec : CtaExec {
+    static constexpr bool kCluster = true;
+#ifdef __CUDA_ARCH__
+    __device__ int rank() const { return (int)cooperative_groups::this_cluster().block_rank(); }
+    __device__ int nranks() const { return (int)cooperative_groups::this_cluster().num_blocks(); }
+    __device__ double* peer(double* p, int r) const { return cooperative_groups::this_cluster().map_shared_rank(p, (unsigned)r); }
+    __device__ void sync() const { cooperative_groups::this_cluster().sync(); }
+    // CTA stage as in CtaExec, then every rank pushes its partial into slot [32 + own rank] of every rank
+    template <bool MAX> __device__ double reduce(double v) const {
+        auto cl = cooperative_groups::this_cluster();
+        const int nr = (int)cl.num_blocks(), rk = (int)cl.block_rank();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = MAX ? fmax(v, w) : v + w; }
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) red[w] = v;
+        __syncthreads();
+        double t = red[0];
+        for (int i = 1; i < nw; ++i) t = MAX ? fmax(t, red[i]) : t + red[i];
+        if ((int)threadIdx.x < nr) cl.map_shared_rank(red, threadIdx.x)[32 + rk] = t;
+        cl.sync();
+        double tot = red[32];
+        for (int i = 1; i < nr; ++i) tot = MAX ? fmax(tot, red[32 + i]) : tot + red[32 + i];   // rank order: identical on every rank
+        cl.sync();
+        return tot;
+    }
+    __device__ double sum(double v) const { return reduce<false>(v); }
+    __device__ double maxv(double v) const { return reduce<true>(v); }
+#else
+    int rank() const { return 0; }
+    int nranks() const { return 1; }
+    double* peer(double* p, int) const { return p; }
+    void sync() const {}
+    double sum(double v) const { return v; }
+    double maxv(double v) const { return v; }
+#endif
+};
+
+__global__ void __launch_bounds__(256, 1) k_chain_cluster(const ChainArgs a) {
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<ClusterExec>)];
+    Engine<ClusterExec>* en = reinterpret_cast<Engine<ClusterExec>*>(en_buf);
+    auto cl = cooperative_groups::this_cluster();
+    const int nr = (int)cl.num_blocks(), cid = blockIdx.x / nr, ncl = gridDim.x / nr;
+    if (threadIdx.x == 0) {
+        ClusterExec ex; ex.red = fthmc_dyn_smem;
+        new (en) Engine<ClusterExec>(ex, a.pr, a.ws + (size_t)cid * a.ws_stride);
+    }
+    __syncthreads();
+    if (a.pr.nlayers > 0) en->load_geom_table();
+    for (int b = cid; b < a.B; b += ncl) run_chain(*en, a, b);
+    cl.sync();                                   // no CTA may exit while a peer can still address its shared memory
+}
 
 __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
@@ -322,59 +382,88 @@ static DevInfo& devinfo() {
     return d;
 }
 
-static int chain_threads(int L0, int L1, bool flow) {
-    int tasks = flow ? (L0 * L1) / 4 : L0 * L1;
+static int chain_threads(int L0, int L1, bool flow, int nr) {
+    int tasks = (flow ? (L0 * L1) / 4 : L0 * L1) / nr;
     int nt = ((tasks + 31) / 32) * 32;
     return nt < 32 ? 32 : (nt > 256 ? 256 : nt);
 }
-static size_t chain_smem_bytes(int L0, int L1, bool flow) { return (engine_smem_doubles(L0, L1, flow) + 64) * sizeof(double); }
+static size_t chain_smem_bytes(int L0, int L1, bool flow, int nr) { return (engine_smem_doubles(L0, L1, flow, nr) + 64) * sizeof(double); }
 
-// static shared memory of k_chain (the engine object), which counts against the per-block opt-in limit
-static int chain_static_smem() {
-    static int v = -1;
-    if (v < 0) {
+// static shared memory of the chain kernels (the engine object), which counts against the per-block opt-in limit
+static int chain_static_smem(bool cluster) {
+    static int v[2] = { -1, -1 };
+    if (v[cluster] < 0) {
         cudaFuncAttributes fa;
-        v = cudaFuncGetAttributes(&fa, k_chain) == cudaSuccess ? (int)fa.sharedSizeBytes : 1024;
+        cudaError_t e = cluster ? cudaFuncGetAttributes(&fa, k_chain_cluster) : cudaFuncGetAttributes(&fa, k_chain);
+        v[cluster] = e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024;
     }
-    return v;
+    return v[cluster];
 }
 
-// grid of the persistent kernel: one CTA per chain up to what is co-resident on the device
-static int chain_grid(int B, int L0, int L1, bool flow, int* occ_out = nullptr) {
+// Ranks (CTAs of one thread-block cluster) a chain is spread over: 1 when the lattice fits one SM's shared memory,
+// otherwise the smallest cluster size <= 16 that divides the stripe groups of both orientations and fits.  0: none.
+static int chain_ranks(int L0, int L1, bool flow) {
     DevInfo& d = devinfo();
-    int occ = 1;
-    size_t smem = chain_smem_bytes(L0, L1, flow);
-    cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem());
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain, chain_threads(L0, L1, flow), smem) != cudaSuccess || occ < 1) occ = 1;
-    if (occ_out) *occ_out = occ;
-    long long g = (long long)d.sm * occ;
-    return (int)(B < g ? B : g);
+    for (int nr = 1; nr <= 16; ++nr) {
+        if ((L0 / 4) % nr || (L1 / 4) % nr) continue;
+        if (flow && (size_t)L0 * L1 / nr > (size_t)OFF_W3T) continue;     // Pbar plane aliases the forward weights
+        if (chain_smem_bytes(L0, L1, flow, nr) + chain_static_smem(nr > 1) > (size_t)d.smem_optin) continue;
+        return nr;
+    }
+    return 0;
 }
 
-static int check_lattice(int B, int L0, int L1, bool flow) {
+// number of chains (CTAs, or clusters) resident at once on the device
+static int chain_resident(int L0, int L1, bool flow, int nr) {
+    DevInfo& d = devinfo();
+    const size_t smem = chain_smem_bytes(L0, L1, flow, nr);
+    const int nt = chain_threads(L0, L1, flow, nr);
+    if (nr == 1) {
+        int occ = 1;
+        cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(false));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain, nt, smem) != cudaSuccess || occ < 1) occ = 1;
+        return d.sm * occ;
+    }
+    cudaFuncSetAttribute(k_chain_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(true));
+    cudaFuncSetAttribute(k_chain_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nr); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_chain_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    return ncl;
+}
+
+static int check_lattice(int B, int L0, int L1, bool flow, int* nr_out) {
     if (B <= 0 || L0 <= 0 || L1 <= 0) return fail(FTHMC_E_ARG, "B, L0, L1 must be positive");
     if (L0 % 4 || L1 % 4) return fail(FTHMC_E_LATTICE, "L0 and L1 must be multiples of 4 (4-periodic stripe masks)");
     DevInfo& d = devinfo();
     if (!d.ok) return fail(FTHMC_E_ARG, "no CUDA device");
-    if (flow && (size_t)L0 * L1 > (size_t)OFF_W3T)
-        return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
-    if (chain_smem_bytes(L0, L1, flow) + chain_static_smem() > (size_t)d.smem_optin)
-        return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path on this device");
+    const int nr = chain_ranks(L0, L1, flow);
+    if (nr == 0)
+        return fail(FTHMC_E_LATTICE, "lattice too large for the shared-memory-resident chain path (one SM, or a cluster of up to 16 SMs) on this device");
+    *nr_out = nr;
     return 0;
 }
 
 extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
-    if (B <= 0 || L0 <= 0 || L1 <= 0) return 0;
+    if (B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
     DevInfo& d = devinfo();
-    // upper bound on the persistent grid: co-resident CTAs cannot exceed 32 per SM
-    long long g = (long long)(d.sm > 0 ? d.sm : 148) * 32;
+    int nr = chain_ranks(L0, L1, flow != nullptr);
+    if (nr == 0) nr = 1;
+    // upper bound on the chains resident at once: 32 CTAs per SM without a cluster, one CTA per SM with one
+    long long g = nr == 1 ? (long long)(d.sm > 0 ? d.sm : 148) * 32 : (long long)(d.sm > 0 ? d.sm : 148) / nr;
     if (B < g) g = B;
-    return (size_t)g * engine_ws_doubles(L0, L1, flow ? flow->n_layers : 0) * sizeof(double) + 256;
+    if (g < 1) g = 1;
+    return (size_t)g * engine_ws_doubles(L0, L1, flow ? flow->n_layers : 0, nr) * sizeof(double) + 256;
 }
 
 static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
     const bool has_flow = flow != nullptr;
-    int rc = check_lattice(a.B, L0, L1, has_flow);
+    int nr = 1;
+    int rc = check_lattice(a.B, L0, L1, has_flow, &nr);
     if (rc) return rc;
     a.pr.L0 = L0; a.pr.L1 = L1;
     if (has_flow) {
@@ -385,13 +474,26 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
         a.pr.nlayers = 0; a.pr.act = 0; a.pr.conv = 0; a.pr.inv_tol = 0; a.pr.inv_max_iter = 0;
         a.pr.wpack = nullptr; a.pr.lmu = nullptr; a.pr.loff = nullptr;
     }
-    const int grid = chain_grid(a.B, L0, L1, has_flow);
-    a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers);
-    const size_t need = (size_t)grid * a.ws_stride * sizeof(double);
+    int res = chain_resident(L0, L1, has_flow, nr);
+    if (res < 1) return fail(FTHMC_E_LATTICE, "the device cannot co-schedule a thread-block cluster of the size this lattice needs");
+    const int chains = a.B < res ? a.B : res;
+    a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers, nr);
+    const size_t need = (size_t)chains * a.ws_stride * sizeof(double);
     if (!ws || ws_bytes < need) return fail(FTHMC_E_WORKSPACE, "workspace null or smaller than fthmc_workspace_bytes()");
-    if (((uintptr_t)ws) & 7) return fail(FTHMC_E_WORKSPACE, "workspace must be 8-byte aligned");
+    if (((uintptr_t)ws) & 15) return fail(FTHMC_E_WORKSPACE, "workspace must be 16-byte aligned");
     a.ws = (double*)ws;
-    k_chain<<<grid, chain_threads(L0, L1, has_flow), chain_smem_bytes(L0, L1, has_flow), (cudaStream_t)stream>>>(a);
+    const int nt = chain_threads(L0, L1, has_flow, nr);
+    const size_t smem = chain_smem_bytes(L0, L1, has_flow, nr);
+    if (nr == 1) {
+        k_chain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(chains * nr); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_chain_cluster, a));
+    }
     g_launches++;
     CK(cudaGetLastError());
     return 0;

@@ -2,14 +2,20 @@
 // The engine's phases are correct for any thread count; here they run with one "thread" so the
 // indexing, the weight packing and the hand-derived adjoint can be checked against the oracle
 // without a GPU.  Nothing in the product package loads this library.
+#include <barrier>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "../../fthmc_b200/csrc/chain_programs.cuh"
 #include "../../fthmc_b200/csrc/weight_pack.h"
 
 namespace {
 struct SerialExec {
+    static constexpr bool kCluster = false;
+    int rank() const { return 0; }
+    int nranks() const { return 1; }
+    double* peer(double* p, int) const { return p; }
     double* arena;
     double* smem() const { return arena; }
     void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
@@ -48,5 +54,87 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
     Engine<SerialExec> en(ex, a.pr, ws.data());
     if (nlayers > 0) en.load_geom_table();
     for (int b = 0; b < B; ++b) run_chain(en, a, b);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Cluster mode: nr host threads stand in for the nr CTAs of a thread-block cluster (one "thread" per
+// CTA), std::barrier for the cluster barrier, plain pointers into the other ranks' arenas for
+// distributed shared memory.  Exercises the decomposition (row-block X/GR, column-block planes,
+// halo pushes, cluster-wide reductions) of the kCluster code path without a GPU.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ClusterShared {
+    int nr;
+    std::vector<double*> arenas;
+    std::barrier<> bar;
+    std::vector<double> slots;
+    ClusterShared(int n) : nr(n), arenas(n), bar(n), slots(n) {}
+};
+struct ThreadExec {
+    static constexpr bool kCluster = true;
+    ClusterShared* sh;
+    int rk;
+    int rank() const { return rk; }
+    int nranks() const { return sh->nr; }
+    double* smem() const { return sh->arenas[rk]; }
+    double* peer(double* p, int r) const { return sh->arenas[r] + (p - sh->arenas[rk]); }
+    void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
+    void async_copy8(double* dst, const double* src) const { *dst = *src; }
+    void async_copy16(double* dst, const double* src) const { dst[0] = src[0]; dst[1] = src[1]; }
+    void async_commit() const {}
+    template <int N> void async_wait() const {}
+    int tid() const { return 0; }
+    int nt() const { return 1; }
+    void sync() const { sh->bar.arrive_and_wait(); }
+    double sum(double v) const {
+        sh->slots[rk] = v; sh->bar.arrive_and_wait();
+        double t = 0.0; for (int i = 0; i < sh->nr; ++i) t += sh->slots[i];
+        sh->bar.arrive_and_wait();
+        return t;
+    }
+    double maxv(double v) const {
+        sh->slots[rk] = v; sh->bar.arrive_and_wait();
+        double t = sh->slots[0]; for (int i = 1; i < sh->nr; ++i) t = t > sh->slots[i] ? t : sh->slots[i];
+        sh->bar.arrive_and_wait();
+        return t;
+    }
+};
+}
+
+extern "C" int emul_run_cluster(int nr, int mode, int B, int L0, int L1, int nlayers, const double* raw, const int* mu, const int* off,
+                                int act, int conv, double tol, int max_iter, double beta, double dt, int nstep,
+                                const double* field_in, const double* p_in, const double* u_in, double* field_out, double* p_out,
+                                double* s_out, double* layer_logJ, int* iters, double* expmdH, int* acc, double* plaq, double* topo,
+                                double* h0, double* h1, unsigned long long seed, unsigned long long traj) {
+    using namespace fthmc;
+    if (L0 % 4 || L1 % 4 || nr < 1 || (L0 / 4) % nr || (L1 / 4) % nr) return -1;
+    if (nlayers > 0 && (size_t)L0 * L1 / nr > (size_t)OFF_W3T) return -2;
+    std::vector<double> pack((size_t)nlayers * PACK_DOUBLES);
+    for (int l = 0; l < nlayers; ++l) pack_layer(raw + (size_t)l * RAW_DOUBLES, mu[l], pack.data() + (size_t)l * PACK_DOUBLES);
+    const size_t asz = engine_smem_doubles(L0, L1, nlayers > 0, nr) + 8;
+    std::vector<std::vector<double>> arenas(nr, std::vector<double>(asz));
+    std::vector<double> ws(engine_ws_doubles(L0, L1, nlayers, nr) + 8);
+    ChainArgs a{};
+    a.mode = mode; a.B = B;
+    a.pr.L0 = L0; a.pr.L1 = L1; a.pr.nlayers = nlayers; a.pr.act = act; a.pr.conv = conv;
+    a.pr.inv_tol = tol; a.pr.inv_max_iter = max_iter; a.pr.wpack = pack.data(); a.pr.lmu = mu; a.pr.loff = off;
+    a.beta = beta; a.dt = dt; a.nstep = nstep;
+    a.field_in = field_in; a.p_in = p_in; a.u_in = u_in; a.field_out = field_out; a.p_out = p_out;
+    a.s_out = s_out; a.layer_logJ = layer_logJ; a.iters = iters;
+    a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
+    a.seed = seed; a.traj = traj; a.chain0 = 0;
+    ClusterShared sh(nr);
+    for (int r = 0; r < nr; ++r) sh.arenas[r] = arenas[r].data();
+    std::vector<std::thread> th;
+    for (int r = 0; r < nr; ++r)
+        th.emplace_back([&, r]() {
+            ThreadExec ex{ &sh, r };
+            Engine<ThreadExec> en(ex, a.pr, ws.data());
+            if (nlayers > 0) en.load_geom_table();
+            for (int b = 0; b < B; ++b) run_chain(en, a, b);
+        });
+    for (auto& t : th) t.join();
     return 0;
 }

@@ -19,7 +19,7 @@ ACTS = dict(silu=0, swish=0, leaky_relu=1, relu=2)
 def build(force=False):
     deps = [SRC] + [os.path.join(CSRC, f) for f in ("chain_engine.cuh", "chain_programs.cuh", "weight_pack.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC",
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off", "-mfma", "-shared", "-fPIC",
                                "-o", LIB, SRC])
     return LIB
 
@@ -32,6 +32,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.emul_run.restype = ctypes.c_int
+        _lib.emul_run_cluster.restype = ctypes.c_int
     return _lib
 
 
@@ -40,8 +41,9 @@ def _p(a, ct=ctypes.c_double):
 
 
 def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, act="silu", conv=0,
-        tol=1e-6, max_iter=1000, mu=None, off=None, seed=0, traj=0):
-    """field: (B,2,L0,L1) float64.  Returns a dict of outputs."""
+        tol=1e-6, max_iter=1000, mu=None, off=None, seed=0, traj=0, nranks=0):
+    """field: (B,2,L0,L1) float64.  Returns a dict of outputs.  nranks >= 1: the cluster code path of the
+    engine with that many ranks (host threads standing in for the CTAs of a thread-block cluster)."""
     field = np.ascontiguousarray(field, dtype=np.float64)
     B, _, L0, L1 = field.shape
     raw = np.ascontiguousarray(raw_weights, dtype=np.float64) if raw_weights is not None else np.zeros((0, 955))
@@ -53,7 +55,8 @@ def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, 
                plaq=np.zeros(B), topo=np.zeros(B), h0=np.zeros(B), h1=np.zeros(B))
     p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
-    rc = lib().emul_run(MODES[mode], B, L0, L1, n, _p(raw), _p(mu, ctypes.c_int), _p(off, ctypes.c_int),
+    fn = lib().emul_run if nranks == 0 else (lambda *args: lib().emul_run_cluster(nranks, *args))
+    rc = fn(MODES[mode], B, L0, L1, n, _p(raw), _p(mu, ctypes.c_int), _p(off, ctypes.c_int),
                         ACTS[act], conv, ctypes.c_double(tol), max_iter, ctypes.c_double(beta), ctypes.c_double(dt),
                         nstep, _p(field), _p(p), _p(u), _p(out["field"]), _p(out["p"]), _p(out["s"]),
                         _p(out["layer_logJ"]), _p(out["iters"], ctypes.c_int), _p(out["expmdH"]),

@@ -113,3 +113,44 @@ def test_thousand_trajectories_bit_exact_decisions(golden):
     assert np.max(np.abs(o["s"] - g["dH"])) < 1e-8
     assert np.array_equal(o["acc"].astype(bool), g["acc"]) and np.array_equal(o["topo"], g["topo"])
     assert np.max(np.abs(o["field"].sum(axis=(1, 2, 3)) - g["field_sum"])) < 1e-7
+
+
+# ---------------------------------------------------------------- cluster decomposition (L = 64 .. 128 path)
+@pytest.mark.parametrize("name,nranks", [("ft_L8_n8", 2), ("ft_L16_b6", 2), ("ft_L16_b6", 4), ("ft_L32_b4", 8)])
+def test_cluster_ranks_match_golden(golden, name, nranks):
+    """The kCluster code path (row-block X/GR, column-block planes, halo pushes, cluster-wide reductions) with host
+    threads standing in for the CTAs of a cluster: same golden vectors, same tolerances as the single-CTA path."""
+    g = golden(name)
+    x, w, beta = g["x"], g["weights"], float(g["beta"])
+    o = E.run("flow_fwd", w, x, nranks=nranks)
+    assert np.max(np.abs(o["field"] - g["flow_fwd"])) < 1e-12
+    assert np.max(np.abs(o["layer_logJ"] - g["layer_logJ"].T)) < 1e-11
+    assert relerr(E.run("ft_action", w, x, beta=beta, nranks=nranks)["s"], g["ft_action"]) < 1e-12
+    assert relerr(E.run("ft_force", w, x, beta=beta, nranks=nranks)["field"], g["ft_force"]) < 1e-11
+    o = E.run("flow_inv", w, g["flow_fwd"], nranks=nranks)
+    assert np.max(np.abs(o["field"] - g["flow_inv_of_fwd"])) < 1e-11
+    o = E.run("ft_hmc", w, g["traj_x"], beta=beta, dt=float(g["dt"]), nstep=int(g["nstep"]), p=g["traj_p"], u=g["traj_u"],
+              nranks=nranks)
+    assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["traj_acc"]) and np.array_equal(o["topo"], g["traj_topo"])
+    assert np.max(np.abs(o["field"] - g["traj_out"])) < 1e-8
+
+
+def test_cluster_decomposition_is_invisible():
+    """Same chain, 1 / 2 / 3 ranks, rectangular lattice, device-RNG mode: fields bit-identical (only the order of
+    the action sums changes), plain HMC included."""
+    import torch
+    from oracle import fthmc_oracle as O
+    flow = O.random_flow(n_layers=6, seed=2, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()])
+                                    for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    torch.manual_seed(9)
+    x = torch.empty(2, 2, 24, 12).uniform_(-np.pi, np.pi).numpy()
+    ref = E.run("ft_hmc", raw, x, beta=3.0, dt=0.05, nstep=4, seed=5, traj=1)
+    refp = E.run("hmc", None, x, beta=3.0, dt=0.05, nstep=4, seed=5, traj=1)
+    for nr in (1, 3):
+        o = E.run("ft_hmc", raw, x, beta=3.0, dt=0.05, nstep=4, seed=5, traj=1, nranks=nr)
+        assert np.array_equal(o["field"], ref["field"]) and np.max(np.abs(o["s"] - ref["s"])) < 1e-10
+        assert np.array_equal(o["topo"], ref["topo"]) and np.array_equal(o["acc"], ref["acc"])
+        o = E.run("hmc", None, x, beta=3.0, dt=0.05, nstep=4, seed=5, traj=1, nranks=nr)
+        assert np.array_equal(o["field"], refp["field"]) and np.max(np.abs(o["s"] - refp["s"])) < 1e-10

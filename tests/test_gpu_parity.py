@@ -291,6 +291,46 @@ def test_full_size_properties_L32():
     assert float(torch.max(torch.abs(xb - x[:8]))) < 1e-9 and float(torch.max(torch.abs(pb + p))) < 1e-9
 
 
+# ---------------------------------------------------------------- cluster / DSMEM path (lattices beyond one SM)
+def _raw_of(flow):
+    return np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                     for lw in flow.layers])
+
+
+@pytest.mark.parametrize("L,layers,B", [(64, 8, 3), (48, 4, 2), (128, 24, 2)])
+def test_cluster_path_vs_oracle(L, layers, B):
+    """BASELINE config 4 (L=128, 24 layers; one 16-CTA cluster per chain) and smaller cluster sizes against the oracle:
+    flow, log-det, ft_action, ft_force to 1e-10, inverse decision-for-decision, a teacher-forced trajectory."""
+    flow = O.random_flow(n_layers=layers, seed=3647)
+    pf = ft.PackedFlow(_raw_of(flow))
+    gen = torch.Generator().manual_seed(L)
+    x = (torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi
+    P = ft.Param(beta=6.0, lat=(L, L), tau=0.3, nstep=3)
+    y, lj = O.ft_flow_logJ(flow, x)
+    yg, ljg = ft.ft_flow(pf, x.cuda(), with_logJ=True)
+    assert np.max(np.abs(yg.cpu().numpy() - y.numpy())) < 1e-11
+    assert relerr(ljg.cpu().numpy(), lj.numpy()) < REL
+    assert relerr(ft.ft_action(P, pf, x).numpy(), O.ft_action(6.0, flow, x).numpy()) < REL
+    assert relerr(ft.ft_force(P, pf, x).numpy(), O.ft_force(6.0, flow, x).numpy()) < REL
+    xi = O.ft_flow_inv(flow, y[:1])
+    assert np.max(np.abs(ft.ft_flow_inv(pf, y[:1]).numpy() - xi.numpy())) < 1e-10
+    p = torch.randn(1, 2, L, L, generator=gen, dtype=torch.float64)
+    u = torch.rand(1, generator=gen, dtype=torch.float64)
+    dH, e, acc, new = O.ft_hmc(6.0, P.dt, P.nstep, flow, y[:1], p=p, u=u[0])
+    r = ft.ft_hmc_batch(P, pf, y[:1], p, u)
+    assert abs(float(r["dH"][0]) - dH) < 1e-8 and bool(r["acc"][0]) == bool(acc)
+    assert np.max(np.abs(r["field"].numpy() - new.numpy())) < 1e-8
+    assert float(r["topo"][0]) == float(O.topocharge(new[0]))
+    # plain HMC on the same lattice (cluster for L=128) and batch > resident clusters
+    r1 = ft.hmc_batch(P, x, seed=3, traj=1)
+    xs = torch.cat([x] * 6)
+    r2 = ft.hmc_batch(P, xs, seed=3, traj=1)
+    assert torch.equal(r2["field"][:B], r1["field"])
+    xo, po = O.leapfrog(6.0, P.dt, P.nstep, x[0], p[0])
+    xg, pg = ft.leapfrog(P, x[0], p[0])
+    assert np.max(np.abs(xg.numpy() - xo.numpy())) < 1e-11 and np.max(np.abs(pg.numpy() - po.numpy())) < 1e-11
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
@@ -301,7 +341,7 @@ def test_errors_are_loud():
                     for lw in flow.layers])
     pf = ft.PackedFlow(raw)
     with pytest.raises(ft.FthmcError) as e:
-        ft.ft_flow(pf, torch.zeros(1, 2, 64, 64))       # does not fit one SM's shared memory
+        ft.ft_flow(pf, torch.zeros(1, 2, 256, 256))     # beyond a 16-CTA cluster's shared memory
     assert e.value.code == -2
     with pytest.raises(ft.FthmcError):
         ft.PackedFlow(np.zeros((2, 900)))
