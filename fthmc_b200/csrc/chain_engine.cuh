@@ -234,7 +234,10 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
 //   E::smem()                         base of the chain's shared-memory arena (address space known to nvcc)
-//   E::async_copy(dst_smem, src_global, ndoubles), E::async_commit(), E::async_wait<N>()   (cp.async groups)
+//   E::bar_init(n)                    n transaction barriers (mbarrier) for the bulk copies below
+//   E::bulk_load(bar, dst_smem, src_global, ndoubles)   ONE thread: TMA bulk copy (cp.async.bulk) completing on `bar`
+//   E::bar_wait(bar, parity)          all threads: wait for the phase of `bar` with that parity
+//   E::proxy_fence()                  generic-proxy writes before it become visible to later bulk copies
 //
 // Cluster mode (E::kCluster, lattices too large for one SM: L = 64 .. 128).  A thread-block cluster of nr =
 // E::nranks() CTAs owns one chain.  The link field X and the gradient GR are split by lattice row blocks
@@ -299,6 +302,10 @@ struct Engine {
     double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
     size_t layStride;
     int* iters_out;                                    // optional global: bisection iterations per layer
+    // transaction barriers of the bulk (TMA) copies.  barcnt[b] counts completed uses: the k-th use of a barrier is
+    // waited with parity k & 1.  Thread 0 advances a counter only after a block barrier that follows every thread's wait.
+    enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, NBAR };
+    int barcnt[NBAR];
 
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
         L0 = p.L0; L1 = p.L1; LP = L1 + 1; Vg = L0 * L1;
@@ -307,6 +314,7 @@ struct Engine {
         oX = o;  o += 2 * H * LP;
         oGR = o; o += 2 * H * LP;
         layStride = engine_layer_ws_doubles(L0, L1, nr);
+        for (int b = 0; b < NBAR; ++b) barcnt[b] = 0;
         wsP = ws; wsX0 = ws + 2 * Vg; wsY0 = ws + 4 * Vg;
         wsLay = ws + 6 * (size_t)Vg + (size_t)rk * p.nlayers * layStride;
         iters_out = nullptr;
@@ -403,9 +411,10 @@ struct Engine {
     // forward/reverse sweeps, the transposed part [OFF_W3T,PACK) for the adjoint sweep
     FT_HD void issue_weights(int l, bool transposed) {
         const int lo = transposed ? OFF_W3T : 0, n = transposed ? PACK_DOUBLES - OFF_W3T : OFF_W3T;
-        if (l >= 0) ex.async_copy(sm(oW) + lo, pr.wpack + (size_t)l * PACK_DOUBLES + lo, n);
-        ex.async_commit();
+        if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_W, sm(oW) + lo, pr.wpack + (size_t)l * PACK_DOUBLES + lo, n);
     }
+    FT_HD void wait_bar(int b) const { ex.bar_wait(b, barcnt[b] & 1); }
+    FT_HD void advance_bar(int b) { if (ex.tid() == 0) barcnt[b] = barcnt[b] + 1; }
 
     // =============================================================================================
     // plain Wilson action pieces on the resident field
@@ -607,9 +616,10 @@ struct Engine {
 #pragma unroll 1
             for (int ci = 0; ci < NH; ++ci) {
                 double in[4][5];
+                const double* Ap = A + ci * Cn * R;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    const double* col = A + cc[j] + ci * (CL ? cst[j] : Cn * R);
+                    const double* col = CL ? A + cc[j] + ci * cst[j] : Ap + cc[j];
                     in[0][j] = col[rm];
                     const dbl2 m = ld2(col + r0);
                     in[1][j] = m.x; in[2][j] = m.y;
@@ -704,8 +714,9 @@ struct Engine {
         double lj = 0.0, tot = 0.0;
         FT_T(PF_PLANES, issue_weights(l, false);              // lands while the plaquette planes are computed
              ph_planes(g, save ? wsCS(l) : nullptr);
-             ex.template async_wait<0>();
-             ex.sync());
+             wait_bar(BAR_W);
+             ex.sync();
+             advance_bar(BAR_W));
         FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr); ex.sync());
         if constexpr (CL) { push_halo_h1(g); ex.sync(); }
         FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr); ex.sync());
@@ -776,8 +787,9 @@ struct Engine {
         LayerGeom g = geom(l);
         FT_T(PF_PLANES, issue_weights(l, false);
              ph_planes(g, nullptr);
-             ex.template async_wait<0>();
-             ex.sync());
+             wait_bar(BAR_W);
+             ex.sync();
+             advance_bar(BAR_W));
         FT_T(PF_CONV1, ph_conv1(g, nullptr); ex.sync());
         if constexpr (CL) { push_halo_h1(g); ex.sync(); }
         FT_T(PF_CONV2, ph_conv2(g, nullptr); ex.sync());
@@ -892,10 +904,11 @@ struct Engine {
                     for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = 0.0;
 #pragma unroll 1
             for (int o = 0; o < NH; ++o) {
+                const double* Cp = C + o * 3 * G * R;
                 double zb[4][5];                                                 // rows r0-1 .. r0+2
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    const double* col = C + sc[j] + o * ((CL && j >= 3) ? sst : 3 * G * R);
+                    const double* col = (CL && j >= 3) ? C + sc[j] + o * sst : Cp + sc[j];
                     zb[0][j] = col[rm];
                     const dbl2 m = ld2(col + r0);
                     zb[1][j] = m.x; zb[2][j] = m.y;
@@ -923,7 +936,7 @@ struct Engine {
 #ifdef FT_PROFILE
             ex.prof_add(PF_C2T_MAC, ex.clock() - tp0); tp0 = ex.clock();
 #endif
-            ex.template async_wait<1>();          // this thread's own act'(z1) elements have landed in A
+            wait_bar(BAR_D1);                     // act'(z1) has landed in A
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -969,7 +982,7 @@ struct Engine {
             }
             PB[(4 * gi) * R + r] = UA[t];
             PB[(4 * gi + 3) * R + r] = 0.0;
-            ex.template async_wait<1>();          // this thread's own cos/sin elements have landed in CS
+            wait_bar(BAR_CS);                     // the frozen cos/sin have landed in CS
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 double cp = CS[(2 * gi + k) * R + r], sp = CS[V / 2 + (2 * gi + k) * R + r];
@@ -995,68 +1008,37 @@ struct Engine {
         }
     }
 
-    // ---- cp.async prefetch of the layer blocks for the adjoint sweep ----
-    // d2 (act'(z2)) is copied cooperatively (a block barrier precedes its use); d1 (act'(z1)) and the
-    // frozen cos/sin are copied element-wise by the thread that will consume them, so their waits sit
-    // right before the final multiply inside ph_conv2T / ph_conv1T and need no barrier.
-    // Every issue_* commits exactly one group (empty when l < 0) to keep the wait counts uniform.
-    // cluster mode: single buffer (B), fetched one layer ahead; arena C holds the halos
+    // ---- bulk (TMA) prefetch of the layer blocks for the adjoint sweep ----
+    // Every block is contiguous in the workspace and lands at the same layout in shared memory, so each is ONE
+    // cp.async.bulk issued by thread 0 and completed on its own transaction barrier: act'(z2) -> B or C (double
+    // buffered, two layers ahead), act'(z1) -> A, frozen cos/sin -> CS, transposed weights -> W.  The waits sit
+    // right before the first use (d1 / cs: after the MAC loops of ph_conv2T / ph_conv1T).
+    // cluster mode: act'(z2) is single-buffered in B, one layer ahead; arena C holds the halos
     FT_HD int zbuf(int l) const { return CL ? oB : ((l & 1) ? oB : oC); }
-    FT_HD void issue_d2(int l) {
-        if (l >= 0) ex.async_copy(sm(zbuf(l)), wsD2(l), 6 * V);
-        ex.async_commit();
-    }
-    FT_HD void issue_d1(int l) {
-        if (l >= 0) {
-            const LayerGeom g = geom(l);
-            double* A = sm(oA); const double* src = wsD1(l);
-            const int T = g.G * g.R, R = g.R;
-            for (int t = ex.tid(); t < T; t += ex.nt()) {
-                int gi, h, r0;
-                task2(g, t, gi, h, r0);
-#pragma unroll 8
-                for (int e = 0; e < 16; ++e) {                      // (channel e/4, column e%4), rows r0, r0+1
-                    const int idx = ((4 * h + (e >> 2)) * g.Cn + 4 * gi + (e & 3)) * R + r0;
-                    ex.async_copy16(A + idx, src + idx);
-                }
-            }
-        }
-        ex.async_commit();
-    }
-    FT_HD void issue_cs(int l) {
-        if (l >= 0) {
-            const LayerGeom g = geom(l);
-            double* CS = sm(oCS); const double* src = wsCS(l);
-            const int T = g.G * g.R, R = g.R;
-            for (int t = ex.tid(); t < T; t += ex.nt()) {
-                const int gi = t / R, r = t - gi * R;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int i = (2 * gi + k) * R + r;
-                    ex.async_copy8(CS + i, src + i);
-                    ex.async_copy8(CS + V / 2 + i, src + V / 2 + i);
-                }
-            }
-        }
-        ex.async_commit();
-    }
+    FT_HD int zbar(int l) const { return zbuf(l) == oB ? BAR_D2B : BAR_D2C; }
+    FT_HD void issue_d2(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(zbar(l), sm(zbuf(l)), wsD2(l), 6 * V); }
+    FT_HD void issue_d1(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_D1, sm(oA), wsD1(l), 8 * V); }
+    FT_HD void issue_cs(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_CS, sm(oCS), wsCS(l), V); }
 
-    // cp.async groups pending on entry, oldest first: [d2(l), d2(l-1), Wt(l), d1(l), cs(l)]
+    // in flight on entry: d2(l) [, d2(l-1)], Wt(l), d1(l), cs(l)
     FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
         FT_T(PF_OUTGRAD, ph_outgrad(g, wsSV(l), wsSO(l));
-             ex.template async_wait<2>();          // d2(l), d2(l-1), Wt(l) have landed
-             ex.sync());
+             wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
+             ex.sync();
+             advance_bar(zbar(l)); advance_bar(BAR_W));
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
-             ex.sync());
-        FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again       pending: [cs(l), d2(l-2)]
+             ex.sync();
+             advance_bar(BAR_D1));
+        FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
-             ex.sync());
+             ex.sync();
+             advance_bar(BAR_CS));
         FT_T(PF_ISSUE, issue_weights(l - 1, true); // W(transposed), A and CS are free
              issue_d1(l - 1);
-             issue_cs(l - 1));                     // pending: [d2(l-2), Wt(l-1), d1(l-1), cs(l-1)]
+             issue_cs(l - 1));
         FT_T(PF_SCATTER, ph_scatter(g); ex.sync());
     }
 
@@ -1092,7 +1074,8 @@ struct Engine {
     // ft_force (ipynb/ft_hmc.py:240-249): GR <- d/dx [S(F(x)) - sum logJ]; X is preserved.
     FT_HD void ft_force(double beta) {
         flow_forward(false, true);
-        ex.sync();                        // the layer blocks are read back through global memory
+        ex.proxy_fence();                 // the layer blocks just written are read back by bulk copies (async proxy)
+        ex.sync();
         const int last = pr.nlayers - 1;
         FT_T(PF_ISSUE, issue_d2(last);
              issue_d2(CL ? -1 : last - 1);
@@ -1101,7 +1084,6 @@ struct Engine {
              issue_cs(last));
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         for (int l = last; l >= 0; --l) layer_adjoint(l);
-        ex.template async_wait<0>();
     }
 
     // elementwise helpers on the link field (skip the pitch padding)

@@ -66,34 +66,46 @@ struct CtaExec {
         return nullptr;
 #endif
     }
-    // cooperative 16-byte cp.async (LDGSTS) copy global -> shared; n doubles, both 16-byte aligned
-    __host__ __device__ void async_copy(double* dst, const double* src, int n) const {
+    // transaction barriers (mbarrier) live in the last 8 doubles of the 64-double scratch block
+    __host__ __device__ void bar_init(int n) const {
 #ifdef __CUDA_ARCH__
-        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-        for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 8u * i), "l"(src + i) : "memory");
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < n; ++i)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(red + 56 + i)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
 #endif
     }
-    // 8-byte cp.async of one element (used when a thread fetches exactly what it will consume)
-    __host__ __device__ void async_copy8(double* dst, const double* src) const {
+    // ONE thread: TMA bulk copy global -> shared (n doubles; both addresses and the byte count multiples of 16),
+    // completing on barrier `bar`
+    __host__ __device__ void bulk_load(int bar, double* dst, const double* src, int n) const {
 #ifdef __CUDA_ARCH__
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(red + 56 + bar), d = (unsigned)__cvta_generic_to_shared(dst);
+        const unsigned bytes = 8u * (unsigned)n;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(d), "l"(src), "r"(bytes), "r"(mb) : "memory");
 #endif
     }
-    // 16-byte cp.async of one aligned pair
-    __host__ __device__ void async_copy16(double* dst, const double* src) const {
+    __host__ __device__ void bar_wait(int bar, int parity) const {
 #ifdef __CUDA_ARCH__
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(red + 56 + bar);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(mb), "r"((unsigned)parity) : "memory");
 #endif
     }
-    __host__ __device__ void async_commit() const {
+    // make this thread's earlier generic-proxy writes (global or shared) visible to later async-proxy (bulk copy) reads
+    __host__ __device__ void proxy_fence() const {
 #ifdef __CUDA_ARCH__
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-    }
-    template <int N> __host__ __device__ void async_wait() const {
-#ifdef __CUDA_ARCH__
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
 #endif
     }
     __host__ __device__ int tid() const {
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_cluster(const ChainArgs a) {
         new (en) Engine<ClusterExec>(ex, a.pr, a.ws + (size_t)cid * a.ws_stride);
     }
     __syncthreads();
+    en->ex.bar_init(Engine<ClusterExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
     for (int b = cid; b < a.B; b += ncl) run_chain(*en, a, b);
     cl.sync();                                   // no CTA may exit while a peer can still address its shared memory
@@ -212,6 +225,7 @@ __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
         new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
     }
     __syncthreads();
+    en->ex.bar_init(Engine<CtaExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(*en, a, b);
 }

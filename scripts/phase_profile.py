@@ -7,7 +7,10 @@ import numpy as np, torch
 out = os.path.join(ROOT, "gpurun_out", "libfthmc_prof.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 import __graft_entry__ as G
-subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + G.NVCC_FLAGS + ["-DFT_PROFILE", "-o", out, os.path.join(ROOT, "fthmc_b200/csrc/fthmc_capi.cu")])
+if os.environ.get("FT_PROF_SO"):
+    out = os.path.abspath(os.environ["FT_PROF_SO"])      # a prebuilt -DFT_PROFILE library (A/B comparisons)
+else:
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc"] + G.NVCC_FLAGS + ["-DFT_PROFILE", "-o", out, os.path.join(ROOT, "fthmc_b200/csrc/fthmc_capi.cu")])
 import fthmc_b200._lib as L
 L.LIB_PATH = out
 import fthmc_b200 as ft

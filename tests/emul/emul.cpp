@@ -18,11 +18,10 @@ struct SerialExec {
     double* peer(double* p, int) const { return p; }
     double* arena;
     double* smem() const { return arena; }
-    void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
-    void async_copy8(double* dst, const double* src) const { *dst = *src; }
-    void async_copy16(double* dst, const double* src) const { dst[0] = src[0]; dst[1] = src[1]; }
-    void async_commit() const {}
-    template <int N> void async_wait() const {}
+    void bar_init(int) const {}
+    void bulk_load(int, double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
+    void bar_wait(int, int) const {}
+    void proxy_fence() const {}
     int tid() const { return 0; }
     int nt() const { return 1; }
     void sync() const {}
@@ -80,11 +79,10 @@ struct ThreadExec {
     int nranks() const { return sh->nr; }
     double* smem() const { return sh->arenas[rk]; }
     double* peer(double* p, int r) const { return sh->arenas[r] + (p - sh->arenas[rk]); }
-    void async_copy(double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
-    void async_copy8(double* dst, const double* src) const { *dst = *src; }
-    void async_copy16(double* dst, const double* src) const { dst[0] = src[0]; dst[1] = src[1]; }
-    void async_commit() const {}
-    template <int N> void async_wait() const {}
+    void bar_init(int) const {}
+    void bulk_load(int, double* dst, const double* src, int n) const { memcpy(dst, src, sizeof(double) * n); }
+    void bar_wait(int, int) const {}
+    void proxy_fence() const {}
     int tid() const { return 0; }
     int nt() const { return 1; }
     void sync() const { sh->bar.arrive_and_wait(); }
