@@ -99,31 +99,45 @@ FT_HD double regularize1(double f) {
 // e^x for |x| <= 708 with ~1 ulp error: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on
 // |r| <= 0.347 (remainder 4e-18), scaling through the exponent bits.  About half the instructions of
 // the library exp(): the SiLU evaluations are a quarter of the trajectory's run time.
+// On the device the constants sit in constant memory: a DFMA takes a constant-bank operand directly, whereas
+// 64-bit literals cost two uniform-register moves each and made the activation loops issue-bound.
+#define FT_EXP_COEFS { 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
+                       2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, \
+                       8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0, \
+                       1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10 }
+#ifdef __CUDACC__
+__constant__ double c_exp[18] = FT_EXP_COEFS;
+#endif
 FT_HD double exp_fast(double x) {
+#ifdef __CUDA_ARCH__
+    const double* K = c_exp;
+#else
+    const double K[18] = FT_EXP_COEFS;
+#endif
+    // clamp to [-708, 708] (a NaN maps to +-708).  On the device: integer compare/select on the high word (708.0 ==
+    // 0x40862000'00000000) instead of DSETP/FSEL pairs on the fp64 pipe
+#ifdef __CUDA_ARCH__
+    {
+        const int hi = __double2hiint(x);
+        if ((hi & 0x7fffffff) >= 0x40862000) x = __hiloint2double((hi & 0x80000000) | 0x40862000, 0);
+    }
+#else
     x = fmin(fmax(x, -708.0), 708.0);
-    const double t = x * 1.4426950408889634074;
-    const double n = (t + 6755399441055744.0) - 6755399441055744.0;          // rint(t)
-    double r = fma(n, -6.93147180369123816490e-01, x);
-    r = fma(n, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;                                       // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 1.984126984126984e-04);
-    p = fma(p, r, 1.388888888888889e-03);
-    p = fma(p, r, 8.333333333333333e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const long long bits = ((long long)n + 1023LL) << 52;                      // 2^n, n in [-1022, 1022]
+#endif
+    const double t = x * K[14];                                              // x / ln2
+    const double nm = t + K[15];                                             // rint(t) in the low mantissa bits
+    const double n = nm - K[15];
+    double r = fma(n, K[16], x);
+    r = fma(n, K[17], r);
+    double p = K[0];                                                         // 1/13!
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = fma(p, r, K[i]);
+    // 2^n, n in [-1022, 1022]: n is the low word of nm (two's complement), shifted into the exponent field
     double sc;
 #ifdef __CUDA_ARCH__
-    sc = __longlong_as_double(bits);
+    sc = __hiloint2double((__double2loint(nm) + 1023) << 20, 0);
 #else
+    long long bits = ((long long)n + 1023LL) << 52;
     memcpy(&sc, &bits, sizeof(sc));
 #endif
     return p * sc;
@@ -233,6 +247,7 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 // ------------------------------------------------------------------------------------------------
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
+//   E::fine(tasks)                    true when the block has more threads than `tasks` (phases then split tasks finer)
 //   E::smem()                         base of the chain's shared-memory arena (address space known to nvcc)
 //   E::bar_init(n)                    n transaction barriers (mbarrier) for the bulk copies below
 //   E::bulk_load(bar, dst_smem, src_global, ndoubles)   ONE thread: TMA bulk copy (cp.async.bulk) completing on `bar`
@@ -304,7 +319,7 @@ struct Engine {
     int* iters_out;                                    // optional global: bisection iterations per layer
     // transaction barriers of the bulk (TMA) copies.  barcnt[b] counts completed uses: the k-th use of a barrier is
     // waited with parity k & 1.  Thread 0 advances a counter only after a block barrier that follows every thread's wait.
-    enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, NBAR };
+    enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, BAR_SO, NBAR };
     int barcnt[NBAR];
 
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
@@ -575,22 +590,27 @@ struct Engine {
     // A thread owns rows {2rp, 2rp+1} and 4 of the 8 channels: every weight it loads (128-bit) feeds both
     // rows, every input feeds up to 9 taps x 4 channels, and the two halves of a warp read the same inputs
     // (broadcast).  This keeps the shared-memory pipe under the fp64 pipe.
-    FT_HD void task2(const LayerGeom& g, int t, int& gi, int& h, int& r0) const {
-        const int R = g.R, hr = R >> 1;
-        gi = t / R;
-        const int rem = t - gi * R;
+    // CH = channels per thread: 4 (V/4 tasks per layer) or 2 (V/2 tasks, when the block has more threads than V/4)
+    template <int CH> FT_HD void task2(const LayerGeom& g, int t, int& gi, int& h, int& r0) const {
+        const int hr = g.R >> 1, per = (NH / CH) * hr;
+        gi = t / per;
+        const int rem = t - gi * per;
         h = rem / hr;
         r0 = 2 * (rem - h * hr);
     }
+    FT_HD bool fine_tasks() const { return ex.fine(VQ); }
 
     // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
-    FT_PHASE void ph_conv2(const LayerGeom g, double* d2_save) {
+    FT_HD void ph_conv2(const LayerGeom g, double* d2_save) {
+        if (fine_tasks()) ph_conv2_t<2>(g, d2_save); else ph_conv2_t<4>(g, d2_save);
+    }
+    template <int CH> FT_PHASE void ph_conv2_t(const LayerGeom g, double* d2_save) {
         const double* A = sm(oA); const double* W = sm(oW);
         double* B = sm(oB);
-        const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
+        const int T = g.G * g.R * (4 / CH), R = g.R, Cn = g.Cn, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi, h, r0;
-            task2(g, t, gi, h, r0);
+            task2<CH>(g, t, gi, h, r0);
             const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
             // input columns 4g-2 .. 4g+2: offset of channel 0 from A, and the channel stride.  In cluster mode the
             // two columns left of the rank's first group sit in the halo buffer AH[ci][j][r] (arena C)
@@ -601,10 +621,10 @@ struct Engine {
                 if (CL && c < 0) { cc[j] = (oC - oA) + (c + 2) * R; cst[j] = 2 * R; }
                 else { cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; cst[j] = Cn * R; }
             }
-            double acc[2][3][4];
+            double acc[2][3][CH];
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const double bv = W[OFF_B2 + 4 * h + o];
+            for (int o = 0; o < CH; ++o) {
+                const double bv = W[OFF_B2 + CH * h + o];
 #pragma unroll
                 for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
@@ -625,31 +645,32 @@ struct Engine {
                     in[1][j] = m.x; in[2][j] = m.y;
                     in[3][j] = col[rp];
                 }
-                const double* wc = W + OFF_W2F + ci * 9 * NH + 4 * h;
+                const double* wc = W + OFF_W2F + ci * 9 * NH + CH * h;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
-                        const dbl2 w01 = ld2(wc + (a * 3 + b) * NH), w23 = ld2(wc + (a * 3 + b) * NH + 2);
-                        const double w[4] = { w01.x, w01.y, w23.x, w23.y };
+                        double w[CH];
+#pragma unroll
+                        for (int o = 0; o < CH; o += 2) { const dbl2 wv = ld2(wc + (a * 3 + b) * NH + o); w[o] = wv.x; w[o + 1] = wv.y; }
 #pragma unroll
                         for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
                             for (int k = 0; k < 3; ++k)
 #pragma unroll
-                                for (int o = 0; o < 4; ++o) acc[dr][k][o] = fma(w[o], in[dr + a][k + b], acc[dr][k][o]);
+                                for (int o = 0; o < CH; ++o) acc[dr][k][o] = fma(w[o], in[dr + a][k + b], acc[dr][k][o]);
                     }
             }
 #ifdef FT_PROFILE
             ex.prof_add(PF_C2_MAC, ex.clock() - tp0); tp0 = ex.clock();
 #endif
-            const int cs = 3 * g.G * R, i0 = (4 * h * 3 * g.G + 3 * gi) * R + r0;
+            const int cs = 3 * g.G * R, i0 = (CH * h * 3 * g.G + 3 * gi) * R + r0;
 #pragma unroll
-            for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < CH; ++o)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) st2(B + i0 + o * cs + k * R, acc[0][k][o], acc[1][k][o]);
             // element e -> (channel e/6, column (e/2)%3, row e%2)
-            act_pass_any<24>(act, B, d2_save, [=](int e) { return i0 + (e / 6) * cs + ((e >> 1) % 3) * R + (e & 1); });
+            act_pass_any<6 * CH>(act, B, d2_save, [=](int e) { return i0 + (e / 6) * cs + ((e >> 1) % 3) * R + (e & 1); });
 #ifdef FT_PROFILE
             ex.prof_add(PF_C2_ACT, ex.clock() - tp0);
 #endif
@@ -660,7 +681,11 @@ struct Engine {
     FT_HD void conv3_out(const double* B, const double* W, const LayerGeom& g, int gi, int r, double out[NOUT]) const {
         const int R = g.R;
         int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
-        double o0 = W[OFF_B3 + 0], o1 = W[OFF_B3 + 1], o2 = W[OFF_B3 + 2];
+        // one accumulator per (output, kernel row): nine independent chains instead of three (this phase runs on
+        // a quarter of the sites and is latency bound)
+        double o[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { o[a][0] = 0.0; o[a][1] = 0.0; o[a][2] = 0.0; }
 #pragma unroll 2
         for (int ci = 0; ci < NH; ++ci) {
             const double* Bp = B + (ci * 3 * g.G + 3 * gi) * R;
@@ -669,11 +694,14 @@ struct Engine {
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
                     double v = Bp[b * R + rr[a]];
-                    const double* w = W + OFF_W3F + ((ci * 3 + a) * 3 + b) * 4;
-                    o0 = fma(w[0], v, o0); o1 = fma(w[1], v, o1); o2 = fma(w[2], v, o2);
+                    const dbl2 w01 = ld2(W + OFF_W3F + ((ci * 3 + a) * 3 + b) * 4);
+                    const double w2 = W[OFF_W3F + ((ci * 3 + a) * 3 + b) * 4 + 2];
+                    o[a][0] = fma(w01.x, v, o[a][0]); o[a][1] = fma(w01.y, v, o[a][1]); o[a][2] = fma(w2, v, o[a][2]);
                 }
         }
-        out[0] = o0; out[1] = o1; out[2] = o2;
+        out[0] = ((W[OFF_B3 + 0] + o[0][0]) + o[1][0]) + o[2][0];
+        out[1] = ((W[OFF_B3 + 1] + o[0][1]) + o[1][1]) + o[2][1];
+        out[2] = ((W[OFF_B3 + 2] + o[0][2]) + o[1][2]) + o[2][2];
     }
 
     // forward transform of the active plaquettes + link update; returns this thread's logJ partial.
@@ -809,23 +837,26 @@ struct Engine {
     // =============================================================================================
     // put the pre-update active links back, then the adjoint of the mixture transform and of -logJ at
     // the active sites:  OUT <- (s1bar, s2bar, tbar),  UA <- Pbar(active)
-    FT_PHASE void ph_outgrad(const LayerGeom g, const double* sv, const double* so) {
+    // On entry OUT holds (s_1, s_2, pre-update active links) of this layer, prefetched from the layer block; every
+    // task reads its own three entries before overwriting them.
+    FT_PHASE void ph_outgrad(const LayerGeom g) {
         double* OUT = sm(oOUT); double* UA = sm(oUA);
         const int T = g.G * g.R, R = g.R, order = pr.conv;
+        wait_bar(BAR_SO);
         // the active plaquette only involves its own active link, so restore + plaquette fuse per task
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
-            *xat(oX, g.mu, n0, n1) = sv[t];
+            *xat(oX, g.mu, n0, n1) = OUT[2 * T + t];
             double gl = *xat(oGR, g.mu, n0, n1);
             double db = g.mu == 0 ? gl : -gl;                 // delta-bar
             double u = plaq(oX, n0, n1, order);
-            double s0 = so[t], s1 = so[T + t];
+            double s0 = OUT[t], s1 = OUT[T + t];
             double c, s;
             sincos(u / 2, &s, &c);
             double su = sin(u);
             double c2 = c * c, s2 = s * s;
-            double ep0 = exp(s0), em0 = exp(-s0), ep1 = exp(s1), em1 = exp(-s1);
+            double ep0 = exp_fast(s0), em0 = exp_fast(-s0), ep1 = exp_fast(s1), em1 = exp_fast(-s1);
             double e0 = 1.0 / (em0 * c2 + ep0 * s2), e1 = 1.0 / (em1 * c2 + ep1 * s2);   // e^{l_k}
             double sg0 = e0 / (e0 + e1), sg1 = e1 / (e0 + e1);                             // softmax_k l_k
             // w = -1 multiplies the logJ terms (ft_action = S - sum logJ)
@@ -875,13 +906,16 @@ struct Engine {
     }
 
     // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1)); same task shape as ph_conv2
-    FT_PHASE void ph_conv2T(const LayerGeom g, int oZ) {
+    FT_HD void ph_conv2T(const LayerGeom g, int oZ) {
+        if (fine_tasks()) ph_conv2T_t<2>(g, oZ); else ph_conv2T_t<4>(g, oZ);
+    }
+    template <int CH> FT_PHASE void ph_conv2T_t(const LayerGeom g, int oZ) {
         const double* C = sm(oZ); const double* W = sm(oW);
         double* A = sm(oA);
-        const int T = g.G * g.R, R = g.R, G = g.G;
+        const int T = g.G * g.R * (4 / CH), R = g.R, G = g.G;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi, h, r0;
-            task2(g, t, gi, h, r0);
+            task2<CH>(g, t, gi, h, r0);
             const int gn = gi + 1 == G ? 0 : gi + 1;
             const int rm = r0 == 0 ? R - 1 : r0 - 1, rp = r0 + 2 == R ? 0 : r0 + 2;
             // source column slots j=0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1,4g,4g+1,4g+3,4g+4
@@ -895,13 +929,13 @@ struct Engine {
 #ifdef FT_PROFILE
             long long tp0 = ex.clock();
 #endif
-            double acc[2][4][4];                                                 // [row][column q][channel]
+            double acc[2][4][CH];                                                // [row][column q][channel]
 #pragma unroll
             for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = 0.0;
+                    for (int ci = 0; ci < CH; ++ci) acc[dr][q][ci] = 0.0;
 #pragma unroll 1
             for (int o = 0; o < NH; ++o) {
                 const double* Cp = C + o * 3 * G * R;
@@ -914,7 +948,7 @@ struct Engine {
                     zb[1][j] = m.x; zb[2][j] = m.y;
                     zb[3][j] = col[rp];
                 }
-                const double* wo = W + OFF_W2T + o * 9 * NH + 4 * h;
+                const double* wo = W + OFF_W2T + o * 9 * NH + CH * h;
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -923,13 +957,14 @@ struct Engine {
                         for (int q = 0; q < 4; ++q) {
                             const int b = q - CO[j] + 1;           // source column = column - b + 1
                             if (b >= 0 && b <= 2) {
-                                const dbl2 w01 = ld2(wo + (a * 3 + b) * NH), w23 = ld2(wo + (a * 3 + b) * NH + 2);
-                                const double w[4] = { w01.x, w01.y, w23.x, w23.y };
+                                double w[CH];
+#pragma unroll
+                                for (int ci = 0; ci < CH; ci += 2) { const dbl2 wv = ld2(wo + (a * 3 + b) * NH + ci); w[ci] = wv.x; w[ci + 1] = wv.y; }
                                 // output row r0+dr reads source row r0+dr-a+1 == zb[dr - a + 2]
 #pragma unroll
                                 for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
-                                    for (int ci = 0; ci < 4; ++ci) acc[dr][q][ci] = fma(w[ci], zb[dr - a + 2][j], acc[dr][q][ci]);
+                                    for (int ci = 0; ci < CH; ++ci) acc[dr][q][ci] = fma(w[ci], zb[dr - a + 2][j], acc[dr][q][ci]);
                             }
                         }
             }
@@ -940,8 +975,8 @@ struct Engine {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
-                    double* p = A + ((4 * h + ci) * g.Cn + 4 * gi + q) * R + r0;
+                for (int ci = 0; ci < CH; ++ci) {
+                    double* p = A + ((CH * h + ci) * g.Cn + 4 * gi + q) * R + r0;
                     const dbl2 d = ld2(p);
                     st2(p, acc[0][q][ci] * d.x, acc[1][q][ci] * d.y);
                 }
@@ -1019,15 +1054,18 @@ struct Engine {
     FT_HD void issue_d2(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(zbar(l), sm(zbuf(l)), wsD2(l), 6 * V); }
     FT_HD void issue_d1(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_D1, sm(oA), wsD1(l), 8 * V); }
     FT_HD void issue_cs(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_CS, sm(oCS), wsCS(l), V); }
+    // (s_1, s_2) and the pre-update active links: contiguous in the layer block, same order as OUT
+    FT_HD void issue_so(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_SO, sm(oOUT), wsSO(l), 3 * VQ); }
 
     // in flight on entry: d2(l) [, d2(l-1)], Wt(l), d1(l), cs(l)
     FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
-        FT_T(PF_OUTGRAD, ph_outgrad(g, wsSV(l), wsSO(l));
+        FT_T(PF_OUTGRAD, ph_outgrad(g);            // waits for so/sv(l)
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
              ex.sync();
-             advance_bar(zbar(l)); advance_bar(BAR_W));
+             advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
+        FT_T(PF_ISSUE, issue_so(l - 1));           // OUT is free again
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.sync();
@@ -1083,6 +1121,7 @@ struct Engine {
              issue_d1(last);
              issue_cs(last));
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
+        FT_T(PF_ISSUE, issue_so(last));
         for (int l = last; l >= 0; --l) layer_adjoint(l);
     }
 

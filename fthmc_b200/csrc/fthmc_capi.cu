@@ -46,6 +46,10 @@ extern "C" unsigned long long fthmc_launch_count(void) { return g_launches.load(
 __device__ unsigned long long g_prof[32];
 #endif
 
+#ifndef FT_THREADS
+#define FT_THREADS 256          // threads per CTA of the resident-chain kernels
+#endif
+
 struct CtaExec {
     static constexpr bool kCluster = false;
     __host__ __device__ int rank() const { return 0; }
@@ -122,6 +126,7 @@ struct CtaExec {
         return 1;
 #endif
     }
+    __host__ __device__ bool fine(int tasks) const { return nt() > tasks; }
     __host__ __device__ void sync() const {
 #ifdef __CUDA_ARCH__
         __syncthreads();
@@ -198,7 +203,7 @@ struct ClusterExec : CtaExec {
 #endif
 };
 
-__global__ void __launch_bounds__(256, 1) k_chain_cluster(const ChainArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
     __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<ClusterExec>)];
     Engine<ClusterExec>* en = reinterpret_cast<Engine<ClusterExec>*>(en_buf);
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_cluster(const ChainArgs a) {
     cl.sync();                                   // no CTA may exit while a peer can still address its shared memory
 }
 
-__global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
     // the engine object lives in (static) shared memory: its members are read by every noinline phase
     __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<CtaExec>)];
@@ -398,8 +403,9 @@ static DevInfo& devinfo() {
 
 static int chain_threads(int L0, int L1, bool flow, int nr) {
     int tasks = (flow ? (L0 * L1) / 4 : L0 * L1) / nr;
+    if (flow && FT_THREADS > 256) tasks *= 2;           // the two big convolutions split their tasks by channel pairs
     int nt = ((tasks + 31) / 32) * 32;
-    return nt < 32 ? 32 : (nt > 256 ? 256 : nt);
+    return nt < 32 ? 32 : (nt > FT_THREADS ? FT_THREADS : nt);
 }
 static size_t chain_smem_bytes(int L0, int L1, bool flow, int nr) { return (engine_smem_doubles(L0, L1, flow, nr) + 64) * sizeof(double); }
 

@@ -24,6 +24,7 @@ struct SerialExec {
     void proxy_fence() const {}
     int tid() const { return 0; }
     int nt() const { return 1; }
+    bool fine(int) const { return getenv("FT_EMUL_FINE") != nullptr; }     // exercise the finer task split of wide blocks
     void sync() const {}
     double sum(double v) const { return v; }
     double maxv(double v) const { return v; }
@@ -85,6 +86,7 @@ struct ThreadExec {
     void proxy_fence() const {}
     int tid() const { return 0; }
     int nt() const { return 1; }
+    bool fine(int) const { return getenv("FT_EMUL_FINE") != nullptr; }
     void sync() const { sh->bar.arrive_and_wait(); }
     double sum(double v) const {
         sh->slots[rk] = v; sh->bar.arrive_and_wait();
