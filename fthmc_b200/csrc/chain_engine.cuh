@@ -40,6 +40,9 @@
 #define FT_T(id, ...) do { __VA_ARGS__; } while (0)
 #endif
 
+// loop over the lanes a "thread" carries: exactly one iteration (its own lane) on the device, 32 in the serial emulation
+#define FT_LANES(ln, ls) for (int ls = 0, ln = ex.lane0(); ls < E::kLanes; ++ls, ++ln)
+
 namespace fthmc {
 
 enum ProfId { PF_PLANES = 0, PF_CONV1, PF_CONV2, PF_CONV3F, PF_CONV3R, PF_OUTGRAD, PF_CONV3T, PF_CONV2T, PF_CONV1T,
@@ -62,6 +65,13 @@ constexpr int OFF_W3T = 1052;   // [o=3][a][k=3][ci=8] conv3 transposed (input g
 constexpr int OFF_W2T = 1268;   // [o=8][a][b][ci=8]   conv2 transposed
 constexpr int OFF_W1T = 1844;   // [o=8][a][b][ci=2]   conv1 transposed
 constexpr int PACK_DOUBLES = 1988;
+
+// The activation planes are [channel][column][row]; a channel stride of V (resp. 3V/4) doubles is a multiple of the 32
+// shared-memory banks, which makes the 4-channel tensor-core fragments of ph_conv2_mma / ph_conv2T_mma 4-way bank
+// conflicted.  PLANE_PAD extra doubles per channel shift consecutive channels by 8 banks: conflict-free.
+constexpr int PLANE_PAD = 4;
+FT_HD size_t plane_a_doubles(size_t V) { return NH * (V + PLANE_PAD); }            // A: 8 channels x (V + pad)
+FT_HD size_t plane_b_doubles(size_t V) { return NH * (3 * V / 4 + PLANE_PAD); }    // B, C: 8 channels x (3V/4 + pad)
 
 constexpr double PI_D = 3.141592653589793;       // == math.pi == np.pi
 constexpr double TWO_PI_D = 6.283185307179586;   // == 2*math.pi (exact doubling)
@@ -247,6 +257,10 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 // ------------------------------------------------------------------------------------------------
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
+//   E::kLanes, E::warp(), E::nwarps(), E::lane0(), E::use_mma(), E::mma884(d0, d1, a, b)
+//                                     warp-level fp64 tensor-core tile D(8x8) += A(8x4) B(4x8) with the PTX m8n8k4 fragment
+//                                     layout.  Device: kLanes == 1, every thread holds its own lane's fragment elements;
+//                                     serial emulation: kLanes == 32, one "thread" carries all 32 lanes in arrays
 //   E::fine(tasks)                    true when the block has more threads than `tasks` (phases then split tasks finer)
 //   E::smem()                         base of the chain's shared-memory arena (address space known to nvcc)
 //   E::bar_init(n)                    n transaction barriers (mbarrier) for the bulk copies below
@@ -289,15 +303,15 @@ struct EngineParams {
 FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true, int nr = 1) {
     size_t V = (size_t)L0 * L1 / nr, LP = L1 + 1, H = L0 / nr;
     if (!flow) return 2 * H * LP * 2 + V + 4;
-    return 2 * H * LP * 2 + V + V / 4 + 3 * (V / 4) + 8 * V + 6 * V + 6 * V + PACK_DOUBLES + 32 + 4;
+    return 2 * H * LP * 2 + V + V / 4 + 3 * (V / 4) + plane_a_doubles(V) + 2 * plane_b_doubles(V) + PACK_DOUBLES + 32 + 4;
 }
 
 // Per-layer block of the per-CTA global workspace written by the forward sweep of ft_force and read
-// back (cp.async) by the reverse sweep: act'(z1) [8V], act'(z2) [6V], cos/sin of the frozen
+// back (bulk copies) by the reverse sweep: act'(z1) [plane A], act'(z2) [plane B], cos/sin of the frozen
 // plaquettes [V], (s_1,s_2) of the active sites [2 V/4], pre-update active links [V/4].
 FT_HD size_t engine_layer_ws_doubles(int L0, int L1, int nr = 1) {
     size_t V = (size_t)L0 * L1 / nr;
-    return 15 * V + 3 * (V / 4);
+    return plane_a_doubles(V) + plane_b_doubles(V) + V + 3 * (V / 4);
 }
 // per-chain global workspace (doubles): momenta, x0, y0 (whole lattice), then for every rank nlayers layer blocks
 FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers, int nr = 1) {
@@ -313,6 +327,7 @@ struct Engine {
     static constexpr bool CL = E::kCluster;
     int L0, L1, LP, V, VQ;          // V, VQ: sites per rank (the whole lattice without a cluster)
     int Vg, nr, rk, H;              // whole-lattice volume, ranks in the cluster, own rank, lattice rows per rank
+    int sA, sB;                     // channel strides of plane A and of planes B, C (padded, see PLANE_PAD)
     int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
     double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
     size_t layStride;
@@ -325,6 +340,7 @@ struct Engine {
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
         L0 = p.L0; L1 = p.L1; LP = L1 + 1; Vg = L0 * L1;
         nr = ex.nranks(); rk = ex.rank(); H = L0 / nr; V = Vg / nr; VQ = V / 4;
+        sA = V + PLANE_PAD; sB = 3 * VQ + PLANE_PAD;
         int o = 0;
         oX = o;  o += 2 * H * LP;
         oGR = o; o += 2 * H * LP;
@@ -339,9 +355,9 @@ struct Engine {
         oUA = o;  o += VQ;
         oOUT = o; o += 3 * VQ;
         o += (o & 1);                                  // 16-byte alignment of the big planes / weights
-        oA = o;   o += 8 * V;
-        oB = o;   o += 6 * V;
-        oC = o;   o += 6 * V;
+        oA = o;   o += NH * sA;
+        oB = o;   o += NH * sB;
+        oC = o;   o += NH * sB;
         oW = o;   o += PACK_DOUBLES;
         oTab = o; o += 32;                             // per-layer (mu, off) bytes, MAX_LAYERS = 128
         oS = oUA;                                      // Wilson-force scratch plane = UA+OUT (V doubles, contiguous)
@@ -355,8 +371,8 @@ struct Engine {
     FT_HD double* sm(int off) const { return ex.smem() + off; }
     // layer block pieces in the global workspace
     FT_HD double* wsD1(int l) const { return wsLay + (size_t)l * layStride; }
-    FT_HD double* wsD2(int l) const { return wsD1(l) + 8 * (size_t)V; }
-    FT_HD double* wsCS(int l) const { return wsD2(l) + 6 * (size_t)V; }
+    FT_HD double* wsD2(int l) const { return wsD1(l) + NH * (size_t)sA; }
+    FT_HD double* wsCS(int l) const { return wsD2(l) + NH * (size_t)sB; }
     FT_HD double* wsSO(int l) const { return wsCS(l) + V; }
     FT_HD double* wsSV(int l) const { return wsSO(l) + 2 * VQ; }
 
@@ -513,22 +529,27 @@ struct Engine {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int o = 0; o < NH; ++o) z[q][o] = W[OFF_B1 + q * NH + o];
-        // (q, b, k): output column class q sees frozen column k through kernel column b
-        const int QB[6][3] = { {0, 2, 0}, {1, 1, 0}, {1, 2, 1}, {2, 0, 0}, {2, 1, 1}, {3, 0, 1} };
+            for (int o = 0; o < NH; o += 2) { const dbl2 bv = ld2(W + OFF_B1 + q * NH + o); z[q][o] = bv.x; z[q][o + 1] = bv.y; }
+        // output column class q sees frozen column k through kernel column b = k + 2 - q: every weight vector
+        // (b, a, ci) is loaded once (128-bit) and feeds the two (q, k) pairs of its kernel column.  Per output the
+        // accumulation order is (b ascending, a, ci).
 #pragma unroll
-        for (int e = 0; e < 6; ++e) {
-            const int q = QB[e][0], b = QB[e][1], k = QB[e][2];
+        for (int b = 0; b < 3; ++b)
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int ci = 0; ci < 2; ++ci) {
-                    const double* w = W + OFF_W1F + ((b * 3 + a) * 2 + ci) * NH;
-                    double v = in[k][a][ci];
+                    double w[NH];
 #pragma unroll
-                    for (int o = 0; o < NH; ++o) z[q][o] = fma(w[o], v, z[q][o]);
+                    for (int o = 0; o < NH; o += 2) { const dbl2 wv = ld2(W + OFF_W1F + ((b * 3 + a) * 2 + ci) * NH + o); w[o] = wv.x; w[o + 1] = wv.y; }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int q = k + 2 - b;
+                        const double v = in[k][a][ci];
+#pragma unroll
+                        for (int o = 0; o < NH; ++o) z[q][o] = fma(w[o], v, z[q][o]);
+                    }
                 }
-        }
     }
 
     // h1 = act(conv1) on all columns -> A[o][c][r];  d1_save: act'(z1) to the global layer block
@@ -546,13 +567,13 @@ struct Engine {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int o = 0; o < NH; ++o) A[(o * Cn + 4 * gi + q) * R + r] = z[q][o];
+                for (int o = 0; o < NH; ++o) A[o * sA + (4 * gi + q) * R + r] = z[q][o];
 #ifdef FT_PROFILE
             ex.prof_add(PF_C1_MAC, ex.clock() - tp0); tp0 = ex.clock();
 #endif
             // activation pass as a partially unrolled loop over this thread's own 32 values (a fully
             // unrolled exp() per element overflows the instruction cache); element e -> channel e/4, column e%4
-            const int i0 = 4 * gi * R + r, so = Cn * R;
+            const int i0 = 4 * gi * R + r, so = sA;
             act_pass_any<4 * NH>(act, A, d1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
 #ifdef FT_PROFILE
             ex.prof_add(PF_C1_ACT, ex.clock() - tp0);
@@ -569,7 +590,7 @@ struct Engine {
             const int R = g.R, n = NH * 2 * R;
             for (int i = ex.tid(); i < n; i += ex.nt()) {
                 const int ci = i / (2 * R), rem = i - ci * 2 * R, j = rem / R, r = rem - j * R;
-                dst[i] = A[(ci * g.Cn + g.Cn - 2 + j) * R + r];
+                dst[i] = A[ci * sA + (g.Cn - 2 + j) * R + r];
             }
         }
     }
@@ -581,7 +602,7 @@ struct Engine {
             const int R = g.R, n = NH * 2 * R;
             for (int i = ex.tid(); i < n; i += ex.nt()) {
                 const int o = i / (2 * R), rem = i - o * 2 * R, j = rem / R, r = rem - j * R;
-                dst[i] = Z[(o * 3 * g.G + j) * R + r];
+                dst[i] = Z[o * sB + j * R + r];
             }
         }
     }
@@ -601,8 +622,78 @@ struct Engine {
     FT_HD bool fine_tasks() const { return ex.fine(VQ); }
 
     // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
+    // tensor-core (DMMA) form of the two big convolutions: single-CTA chains whose stripe length is a multiple of 8
+    FT_HD bool mma_ok() const { return !CL && (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
     FT_HD void ph_conv2(const LayerGeom g, double* d2_save) {
-        if (fine_tasks()) ph_conv2_t<2>(g, d2_save); else ph_conv2_t<4>(g, d2_save);
+        if (mma_ok()) {
+            if (pr.act == ACT_SILU) ph_conv2_mma<ACT_SILU>(g, d2_save);
+            else if (pr.act == ACT_LEAKY) ph_conv2_mma<ACT_LEAKY>(g, d2_save);
+            else ph_conv2_mma<ACT_RELU>(g, d2_save);
+        } else if (fine_tasks()) ph_conv2_t<2>(g, d2_save);
+        else ph_conv2_t<4>(g, d2_save);
+    }
+
+    // conv2 as warp-level GEMM tiles on the fp64 tensor path: D[8 rows of one column][8 output channels] +=
+    // A[8 rows][4 input channels of one tap] * B[those 4 channels][8 output channels]; 18 k-chunks = 9 taps x 2 channel
+    // halves.  One warp task = 8 rows of one stripe group, all three output columns (three accumulator tiles in flight).
+    // The weight fragments stay in registers for the whole phase; A fragments are one 64-bit shared-memory load per
+    // lane per DMMA (conflict-free thanks to PLANE_PAD).  Same output layout as ph_conv2_t.
+    template <int ACT> FT_PHASE void ph_conv2_mma(const LayerGeom g, double* d2_save) {
+        constexpr int NL = E::kLanes;
+        const double* A = sm(oA); const double* W = sm(oW);
+        double* B = sm(oB);
+        const int R = g.R, Cn = g.Cn, RB = R >> 3;
+        double bf[18][NL];                                   // chunk c = tap * 2 + half, tap = a * 3 + b
+        FT_LANES(ln, ls) {
+            const int j = ln & 3, n = ln >> 2;               // B fragment: row j (input channel 4*half + j), column n (output channel)
+#pragma unroll
+            for (int c = 0; c < 18; ++c) bf[c][ls] = W[OFF_W2F + ((4 * (c & 1) + j) * 9 + (c >> 1)) * NH + n];
+        }
+        for (int st = ex.warp(); st < g.G * RB; st += ex.nwarps()) {
+            const int gi = st / RB, rb = 8 * (st - gi * RB);
+            int cc[5];                                       // columns 4g-2 .. 4g+2 (offsets in doubles)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) { const int c = 4 * gi - 2 + m; cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            double acc0[3][NL], acc1[3][NL];
+            int rowa[3][NL];                                 // A fragment: row i = lane / 4 (site rb + i), column j = lane % 4 (channel)
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3, r = rb + i;
+                rowa[0][ls] = j * sA + (r == 0 ? R - 1 : r - 1);
+                rowa[1][ls] = j * sA + r;
+                rowa[2][ls] = j * sA + (r + 1 == R ? 0 : r + 1);
+                const double b0 = W[OFF_B2 + 2 * j], b1 = W[OFF_B2 + 2 * j + 1];     // C fragment: channels 2j, 2j+1 of site i
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { acc0[k][ls] = b0; acc1[k][ls] = b1; }
+            }
+#pragma unroll
+            for (int c = 0; c < 18; ++c) {
+                const int tap = c >> 1, a = tap / 3, b = tap - 3 * a, hoff = 4 * (c & 1) * sA;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double av[NL];
+                    FT_LANES(ln, ls) av[ls] = A[rowa[a][ls] + cc[k + b] + hoff];
+                    ex.mma884(acc0[k], acc1[k], av, bf[c]);
+                }
+            }
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3;
+                const int i0 = 2 * j * sB + 3 * gi * R + rb + i;
+                double z[6], h[6], d[6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { z[2 * k] = acc0[k][ls]; z[2 * k + 1] = acc1[k][ls]; }
+                if (d2_save) {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) act_fwd_der_t<ACT>(z[e], h[e], d[e]);
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) { const int idx = i0 + (e & 1) * sB + (e >> 1) * R; B[idx] = h[e]; d2_save[idx] = d[e]; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) act_fwd_t<ACT>(z[e], h[e]);
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) B[i0 + (e & 1) * sB + (e >> 1) * R] = h[e];
+                }
+            }
+        }
     }
     template <int CH> FT_PHASE void ph_conv2_t(const LayerGeom g, double* d2_save) {
         const double* A = sm(oA); const double* W = sm(oW);
@@ -619,7 +710,7 @@ struct Engine {
             for (int j = 0; j < 5; ++j) {
                 int c = 4 * gi - 2 + j;
                 if (CL && c < 0) { cc[j] = (oC - oA) + (c + 2) * R; cst[j] = 2 * R; }
-                else { cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; cst[j] = Cn * R; }
+                else { cc[j] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; cst[j] = sA; }
             }
             double acc[2][3][CH];
 #pragma unroll
@@ -636,7 +727,7 @@ struct Engine {
 #pragma unroll 1
             for (int ci = 0; ci < NH; ++ci) {
                 double in[4][5];
-                const double* Ap = A + ci * Cn * R;
+                const double* Ap = A + ci * sA;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
                     const double* col = CL ? A + cc[j] + ci * cst[j] : Ap + cc[j];
@@ -664,7 +755,7 @@ struct Engine {
 #ifdef FT_PROFILE
             ex.prof_add(PF_C2_MAC, ex.clock() - tp0); tp0 = ex.clock();
 #endif
-            const int cs = 3 * g.G * R, i0 = (CH * h * 3 * g.G + 3 * gi) * R + r0;
+            const int cs = sB, i0 = CH * h * sB + 3 * gi * R + r0;
 #pragma unroll
             for (int o = 0; o < CH; ++o)
 #pragma unroll
@@ -688,7 +779,7 @@ struct Engine {
         for (int a = 0; a < 3; ++a) { o[a][0] = 0.0; o[a][1] = 0.0; o[a][2] = 0.0; }
 #pragma unroll 2
         for (int ci = 0; ci < NH; ++ci) {
-            const double* Bp = B + (ci * 3 * g.G + 3 * gi) * R;
+            const double* Bp = B + ci * sB + 3 * gi * R;
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -883,7 +974,7 @@ struct Engine {
             for (int o = 0; o < NOUT; ++o)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) ob[o][a] = OUT[o * T + gi * R + rs[a]];
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < 3; ++k) {
                 double acc[NH];
 #pragma unroll
@@ -892,13 +983,15 @@ struct Engine {
                 for (int o = 0; o < NOUT; ++o)
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const double* w = W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH;
+                        double w[NH];
+#pragma unroll
+                        for (int ci = 0; ci < NH; ci += 2) { const dbl2 wv = ld2(W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH + ci); w[ci] = wv.x; w[ci + 1] = wv.y; }
 #pragma unroll
                         for (int ci = 0; ci < NH; ++ci) acc[ci] = fma(w[ci], ob[o][a], acc[ci]);
                     }
 #pragma unroll
                 for (int ci = 0; ci < NH; ++ci) {
-                    int idx = (ci * 3 * g.G + 3 * gi + k) * R + r;
+                    int idx = ci * sB + (3 * gi + k) * R + r;
                     C[idx] = acc[ci] * C[idx];
                 }
             }
@@ -907,7 +1000,65 @@ struct Engine {
 
     // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1)); same task shape as ph_conv2
     FT_HD void ph_conv2T(const LayerGeom g, int oZ) {
-        if (fine_tasks()) ph_conv2T_t<2>(g, oZ); else ph_conv2T_t<4>(g, oZ);
+        if (mma_ok()) ph_conv2T_mma(g, oZ);
+        else if (fine_tasks()) ph_conv2T_t<2>(g, oZ);
+        else ph_conv2T_t<4>(g, oZ);
+    }
+
+    // conv2^T on the fp64 tensor path: D[8 rows of output column 4g+q][8 input channels ci] += A[8 rows][4 channels o of
+    // zbar2 at one tap] * B[o][ci].  One warp task = 8 rows of one stripe group, the four output columns (four accumulator
+    // tiles); per (a, b) only the output columns whose source column 4g + q - b + 1 carries zbar2 take part (9 of 12).
+    FT_PHASE void ph_conv2T_mma(const LayerGeom g, int oZ) {
+        constexpr int NL = E::kLanes;
+        const double* C = sm(oZ); const double* W = sm(oW);
+        double* A = sm(oA);
+        const int R = g.R, G = g.G, RB = R >> 3;
+        double bf[18][NL];                                   // chunk c = tap * 2 + half: rows o = 4*half + j, columns ci = n
+        FT_LANES(ln, ls) {
+            const int j = ln & 3, n = ln >> 2;
+#pragma unroll
+            for (int c = 0; c < 18; ++c) bf[c][ls] = W[OFF_W2T + ((4 * (c & 1) + j) * 9 + (c >> 1)) * NH + n];
+        }
+        for (int st = ex.warp(); st < G * RB; st += ex.nwarps()) {
+            const int gi = st / RB, rb = 8 * (st - gi * RB);
+            const int gn = gi + 1 == G ? 0 : gi + 1;
+            // source column slots m = 0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1, 4g, 4g+1, 4g+3, 4g+4
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
+            double acc0[4][NL], acc1[4][NL];
+            int rowa[3][NL];                                 // output row r reads source row r - a + 1
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3, r = rb + i;
+                rowa[0][ls] = j * sB + (r + 1 == R ? 0 : r + 1);
+                rowa[1][ls] = j * sB + r;
+                rowa[2][ls] = j * sB + (r == 0 ? R - 1 : r - 1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { acc0[q][ls] = 0.0; acc1[q][ls] = 0.0; }
+            }
+#pragma unroll
+            for (int c = 0; c < 18; ++c) {
+                const int tap = c >> 1, a = tap / 3, b = tap - 3 * a, hoff = 4 * (c & 1) * sB;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int co = q - b + 1;                // source column relative to 4g: must be one of -1, 0, 1, 3, 4
+                    const int m = co == -1 ? 0 : co == 0 ? 1 : co == 1 ? 2 : co == 3 ? 3 : co == 4 ? 4 : -1;
+                    if (m >= 0) {
+                        double av[NL];
+                        FT_LANES(ln, ls) av[ls] = C[rowa[a][ls] + sc[m] + hoff];
+                        ex.mma884(acc0[q], acc1[q], av, bf[c]);
+                    }
+                }
+            }
+            wait_bar(BAR_D1);                                // act'(z1) has landed in A
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double* p = A + 2 * j * sA + (4 * gi + q) * R + rb + i;
+                    p[0] = acc0[q][ls] * p[0];
+                    p[sA] = acc1[q][ls] * p[sA];
+                }
+            }
+        }
     }
     template <int CH> FT_PHASE void ph_conv2T_t(const LayerGeom g, int oZ) {
         const double* C = sm(oZ); const double* W = sm(oW);
@@ -924,7 +1075,7 @@ struct Engine {
             const bool hal = CL && gi + 1 == G;
             const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R,
                                 hal ? (oC - oZ) : 3 * gn * R, hal ? (oC - oZ) + R : (3 * gn + 1) * R };
-            const int sst = hal ? 2 * R : 3 * G * R;           // channel stride of slots 3, 4
+            const int sst = hal ? 2 * R : sB;                  // channel stride of slots 3, 4
             const int CO[5] = { -1, 0, 1, 3, 4 };                                // column offsets from 4g
 #ifdef FT_PROFILE
             long long tp0 = ex.clock();
@@ -938,7 +1089,7 @@ struct Engine {
                     for (int ci = 0; ci < CH; ++ci) acc[dr][q][ci] = 0.0;
 #pragma unroll 1
             for (int o = 0; o < NH; ++o) {
-                const double* Cp = C + o * 3 * G * R;
+                const double* Cp = C + o * sB;
                 double zb[4][5];                                                 // rows r0-1 .. r0+2
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
@@ -976,7 +1127,7 @@ struct Engine {
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int ci = 0; ci < CH; ++ci) {
-                    double* p = A + ((CH * h + ci) * g.Cn + 4 * gi + q) * R + r0;
+                    double* p = A + (CH * h + ci) * sA + (4 * gi + q) * R + r0;
                     const dbl2 d = ld2(p);
                     st2(p, acc[0][q][ci] * d.x, acc[1][q][ci] * d.y);
                 }
@@ -995,14 +1146,16 @@ struct Engine {
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
-            double gc[2] = { 0.0, 0.0 }, gs[2] = { 0.0, 0.0 };
+            double gca[3][2], gsa[3][2];                                          // per kernel row: 12 independent chains
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { gca[a][0] = gca[a][1] = 0.0; gsa[a][0] = gsa[a][1] = 0.0; }
 #pragma unroll 2
             for (int o = 0; o < NH; ++o) {
                 double v[3][4];                                                   // rows r-a+1, columns 4g..4g+3
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[a][q] = A[(o * Cn + 4 * gi + q) * R + rs[a]];
+                    for (int q = 0; q < 4; ++q) v[a][q] = A[o * sA + (4 * gi + q) * R + rs[a]];
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -1010,11 +1163,13 @@ struct Engine {
                         const dbl2 w = ld2(W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {                             // frozen column 4g+1+k reads column 4g+1+k-b+1
-                            gc[k] = fma(w.x, v[a][k + 2 - b], gc[k]);
-                            gs[k] = fma(w.y, v[a][k + 2 - b], gs[k]);
+                            gca[a][k] = fma(w.x, v[a][k + 2 - b], gca[a][k]);
+                            gsa[a][k] = fma(w.y, v[a][k + 2 - b], gsa[a][k]);
                         }
                     }
             }
+            const double gc[2] = { (gca[0][0] + gca[1][0]) + gca[2][0], (gca[0][1] + gca[1][1]) + gca[2][1] };
+            const double gs[2] = { (gsa[0][0] + gsa[1][0]) + gsa[2][0], (gsa[0][1] + gsa[1][1]) + gsa[2][1] };
             PB[(4 * gi) * R + r] = UA[t];
             PB[(4 * gi + 3) * R + r] = 0.0;
             wait_bar(BAR_CS);                     // the frozen cos/sin have landed in CS
@@ -1051,8 +1206,8 @@ struct Engine {
     // cluster mode: act'(z2) is single-buffered in B, one layer ahead; arena C holds the halos
     FT_HD int zbuf(int l) const { return CL ? oB : ((l & 1) ? oB : oC); }
     FT_HD int zbar(int l) const { return zbuf(l) == oB ? BAR_D2B : BAR_D2C; }
-    FT_HD void issue_d2(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(zbar(l), sm(zbuf(l)), wsD2(l), 6 * V); }
-    FT_HD void issue_d1(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_D1, sm(oA), wsD1(l), 8 * V); }
+    FT_HD void issue_d2(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(zbar(l), sm(zbuf(l)), wsD2(l), NH * sB); }
+    FT_HD void issue_d1(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_D1, sm(oA), wsD1(l), NH * sA); }
     FT_HD void issue_cs(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_CS, sm(oCS), wsCS(l), V); }
     // (s_1, s_2) and the pre-update active links: contiguous in the layer block, same order as OUT
     FT_HD void issue_so(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_SO, sm(oOUT), wsSO(l), 3 * VQ); }

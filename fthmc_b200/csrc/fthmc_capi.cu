@@ -127,6 +127,36 @@ struct CtaExec {
 #endif
     }
     __host__ __device__ bool fine(int tasks) const { return nt() > tasks; }
+    // warp-level fp64 tensor-core tile (DMMA.8x8x4): every thread holds its own lane's fragment elements
+    static constexpr int kLanes = 1;
+    __host__ __device__ bool use_mma() const { return true; }
+    __host__ __device__ int warp() const {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x >> 5;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ int nwarps() const {
+#ifdef __CUDA_ARCH__
+        return blockDim.x >> 5;
+#else
+        return 1;
+#endif
+    }
+    __host__ __device__ int lane0() const {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x & 31;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ void mma884(double (&d0)[1], double (&d1)[1], const double (&a)[1], const double (&b)[1]) const {
+#ifdef __CUDA_ARCH__
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+            : "+d"(d0[0]), "+d"(d1[0]) : "d"(a[0]), "d"(b[0]));
+#endif
+    }
     __host__ __device__ void sync() const {
 #ifdef __CUDA_ARCH__
         __syncthreads();

@@ -3,6 +3,7 @@
 // indexing, the weight packing and the hand-derived adjoint can be checked against the oracle
 // without a GPU.  Nothing in the product package loads this library.
 #include <barrier>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -25,6 +26,19 @@ struct SerialExec {
     int tid() const { return 0; }
     int nt() const { return 1; }
     bool fine(int) const { return getenv("FT_EMUL_FINE") != nullptr; }     // exercise the finer task split of wide blocks
+    // warp-level tile D(8x8) += A(8x4) B(4x8) in the PTX m8n8k4 fragment layout; this "thread" carries all 32 lanes
+    static constexpr int kLanes = 32;
+    bool use_mma() const { return getenv("FT_EMUL_MMA") != nullptr; }
+    int warp() const { return 0; }
+    int nwarps() const { return 1; }
+    int lane0() const { return 0; }
+    void mma884(double (&d0)[32], double (&d1)[32], const double (&a)[32], const double (&b)[32]) const {
+        for (int i = 0; i < 8; ++i)
+            for (int n = 0; n < 8; ++n) {
+                double& d = (n & 1) ? d1[4 * i + (n >> 1)] : d0[4 * i + (n >> 1)];
+                for (int j = 0; j < 4; ++j) d = fma(a[4 * i + j], b[4 * n + j], d);
+            }
+    }
     void sync() const {}
     double sum(double v) const { return v; }
     double maxv(double v) const { return v; }
@@ -87,6 +101,19 @@ struct ThreadExec {
     int tid() const { return 0; }
     int nt() const { return 1; }
     bool fine(int) const { return getenv("FT_EMUL_FINE") != nullptr; }
+    // warp-level tile D(8x8) += A(8x4) B(4x8) in the PTX m8n8k4 fragment layout; this "thread" carries all 32 lanes
+    static constexpr int kLanes = 32;
+    bool use_mma() const { return getenv("FT_EMUL_MMA") != nullptr; }
+    int warp() const { return 0; }
+    int nwarps() const { return 1; }
+    int lane0() const { return 0; }
+    void mma884(double (&d0)[32], double (&d1)[32], const double (&a)[32], const double (&b)[32]) const {
+        for (int i = 0; i < 8; ++i)
+            for (int n = 0; n < 8; ++n) {
+                double& d = (n & 1) ? d1[4 * i + (n >> 1)] : d0[4 * i + (n >> 1)];
+                for (int j = 0; j < 4; ++j) d = fma(a[4 * i + j], b[4 * n + j], d);
+            }
+    }
     void sync() const { sh->bar.arrive_and_wait(); }
     double sum(double v) const {
         sh->slots[rk] = v; sh->bar.arrive_and_wait();
