@@ -497,6 +497,24 @@ struct Engine {
     FT_PHASE void ph_planes(const LayerGeom g, double* cs_save) {
         double* CS = sm(oCS); double* UA = sm(oUA);
         const int T = g.G * g.R, order = pr.conv;
+        if (fine_tasks()) {                                  // one plaquette per task: T active, then 2T frozen
+            for (int t = ex.tid(); t < 3 * T; t += ex.nt()) {
+                const int kind = t / T, tt = t - kind * T;
+                const int gi = tt / g.R, r = tt - gi * g.R;
+                int n0, n1;
+                site(g, r, 4 * gi + kind, n0, n1);
+                const double p = plaq(oX, n0, n1, order);
+                if (kind == 0) UA[tt] = p;
+                else {
+                    double sp, cp;
+                    sincos(p, &sp, &cp);
+                    const int i = (2 * gi + kind - 1) * g.R + r;
+                    CS[i] = cp; CS[V / 2 + i] = sp;
+                    if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
+                }
+            }
+            return;
+        }
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / g.R, r = t - gi * g.R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
@@ -514,8 +532,14 @@ struct Engine {
         }
     }
 
+    // task t of a phase split NS ways per (group, row): lanes stay consecutive in the row r
+    template <int NS> FT_HD void task_split(const LayerGeom& g, int t, int& gi, int& h, int& r) const {
+        if (NS == 1) { gi = t / g.R; h = 0; r = t - gi * g.R; }
+        else { gi = t / (NS * g.R); const int rem = t - gi * NS * g.R; h = rem / g.R; r = rem - h * g.R; }
+    }
+
     // conv1 pre-activations for the 4 columns of group gi at row r.  z[q][o]
-    FT_HD void conv1_z(const double* CS, const double* W, const LayerGeom& g, int gi, int r, double z[4][NH]) const {
+    template <int CH> FT_HD void conv1_z(const double* CS, const double* W, const LayerGeom& g, int gi, int r, int h, double z[4][CH]) const {
         const int R = g.R;
         int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
         double in[2][3][2];                                  // [k][a][ci]
@@ -529,7 +553,7 @@ struct Engine {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int o = 0; o < NH; o += 2) { const dbl2 bv = ld2(W + OFF_B1 + q * NH + o); z[q][o] = bv.x; z[q][o + 1] = bv.y; }
+            for (int o = 0; o < CH; o += 2) { const dbl2 bv = ld2(W + OFF_B1 + q * NH + CH * h + o); z[q][o] = bv.x; z[q][o + 1] = bv.y; }
         // output column class q sees frozen column k through kernel column b = k + 2 - q: every weight vector
         // (b, a, ci) is loaded once (128-bit) and feeds the two (q, k) pairs of its kernel column.  Per output the
         // accumulation order is (b ascending, a, ci).
@@ -539,42 +563,46 @@ struct Engine {
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int ci = 0; ci < 2; ++ci) {
-                    double w[NH];
+                    double w[CH];
 #pragma unroll
-                    for (int o = 0; o < NH; o += 2) { const dbl2 wv = ld2(W + OFF_W1F + ((b * 3 + a) * 2 + ci) * NH + o); w[o] = wv.x; w[o + 1] = wv.y; }
+                    for (int o = 0; o < CH; o += 2) { const dbl2 wv = ld2(W + OFF_W1F + ((b * 3 + a) * 2 + ci) * NH + CH * h + o); w[o] = wv.x; w[o + 1] = wv.y; }
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const int q = k + 2 - b;
                         const double v = in[k][a][ci];
 #pragma unroll
-                        for (int o = 0; o < NH; ++o) z[q][o] = fma(w[o], v, z[q][o]);
+                        for (int o = 0; o < CH; ++o) z[q][o] = fma(w[o], v, z[q][o]);
                     }
                 }
     }
 
     // h1 = act(conv1) on all columns -> A[o][c][r];  d1_save: act'(z1) to the global layer block
-    FT_PHASE void ph_conv1(const LayerGeom g, double* d1_save) {
+    FT_HD void ph_conv1(const LayerGeom g, double* d1_save) {
+        if (fine_tasks()) ph_conv1_t<4>(g, d1_save); else ph_conv1_t<8>(g, d1_save);
+    }
+    template <int CH> FT_PHASE void ph_conv1_t(const LayerGeom g, double* d1_save) {
         const double* CS = sm(oCS); const double* W = sm(oW);
         double* A = sm(oA);
-        const int T = g.G * g.R, R = g.R, Cn = g.Cn, act = pr.act;
+        const int T = g.G * g.R * (NH / CH), R = g.R, act = pr.act;
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
+            int gi, h, r;
+            task_split<NH / CH>(g, t, gi, h, r);
 #ifdef FT_PROFILE
             long long tp0 = ex.clock();
 #endif
-            double z[4][NH];
-            conv1_z(CS, W, g, gi, r, z);
+            double z[4][CH];
+            conv1_z<CH>(CS, W, g, gi, r, h, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int o = 0; o < NH; ++o) A[o * sA + (4 * gi + q) * R + r] = z[q][o];
+                for (int o = 0; o < CH; ++o) A[(CH * h + o) * sA + (4 * gi + q) * R + r] = z[q][o];
 #ifdef FT_PROFILE
             ex.prof_add(PF_C1_MAC, ex.clock() - tp0); tp0 = ex.clock();
 #endif
             // activation pass as a partially unrolled loop over this thread's own 32 values (a fully
             // unrolled exp() per element overflows the instruction cache); element e -> channel e/4, column e%4
-            const int i0 = 4 * gi * R + r, so = sA;
-            act_pass_any<4 * NH>(act, A, d1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
+            const int i0 = CH * h * sA + 4 * gi * R + r, so = sA;
+            act_pass_any<4 * CH>(act, A, d1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
 #ifdef FT_PROFILE
             ex.prof_add(PF_C1_ACT, ex.clock() - tp0);
 #endif
@@ -961,12 +989,16 @@ struct Engine {
     }
 
     // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C, which holds act'(z2))
-    FT_PHASE void ph_conv3T(const LayerGeom g, int oZ) {
+    FT_HD void ph_conv3T(const LayerGeom g, int oZ) {
+        if (fine_tasks()) ph_conv3T_t<4>(g, oZ); else ph_conv3T_t<8>(g, oZ);
+    }
+    template <int CH> FT_PHASE void ph_conv3T_t(const LayerGeom g, int oZ) {
         const double* OUT = sm(oOUT); const double* W = sm(oW);
         double* C = sm(oZ);
         const int T = g.G * g.R, R = g.R;
-        for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
+        for (int t2 = ex.tid(); t2 < T * (NH / CH); t2 += ex.nt()) {
+            int gi, h, r;
+            task_split<NH / CH>(g, t2, gi, h, r);
             // out-gradient rows r-a+1 for a=0,1,2 -> r+1, r, r-1
             int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };
             double ob[NOUT][3];
@@ -976,22 +1008,22 @@ struct Engine {
                 for (int a = 0; a < 3; ++a) ob[o][a] = OUT[o * T + gi * R + rs[a]];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                double acc[NH];
+                double acc[CH];
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci) acc[ci] = 0.0;
+                for (int ci = 0; ci < CH; ++ci) acc[ci] = 0.0;
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o)
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        double w[NH];
+                        double w[CH];
 #pragma unroll
-                        for (int ci = 0; ci < NH; ci += 2) { const dbl2 wv = ld2(W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH + ci); w[ci] = wv.x; w[ci + 1] = wv.y; }
+                        for (int ci = 0; ci < CH; ci += 2) { const dbl2 wv = ld2(W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH + CH * h + ci); w[ci] = wv.x; w[ci + 1] = wv.y; }
 #pragma unroll
-                        for (int ci = 0; ci < NH; ++ci) acc[ci] = fma(w[ci], ob[o][a], acc[ci]);
+                        for (int ci = 0; ci < CH; ++ci) acc[ci] = fma(w[ci], ob[o][a], acc[ci]);
                     }
 #pragma unroll
-                for (int ci = 0; ci < NH; ++ci) {
-                    int idx = ci * sB + (3 * gi + k) * R + r;
+                for (int ci = 0; ci < CH; ++ci) {
+                    int idx = (CH * h + ci) * sB + (3 * gi + k) * R + r;
                     C[idx] = acc[ci] * C[idx];
                 }
             }
@@ -1139,44 +1171,52 @@ struct Engine {
 
     // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar in the canonical layout
     // PB[c][r] (the unused forward-weight slots of W: V <= OFF_W3T doubles)
-    FT_PHASE void ph_conv1T(const LayerGeom g) {
+    FT_HD void ph_conv1T(const LayerGeom g) {
+        if (fine_tasks()) ph_conv1T_t<1>(g); else ph_conv1T_t<2>(g);
+    }
+    // KN = frozen columns per task: 2 (one task per (group, row)) or 1 (two tasks, wide blocks)
+    template <int KN> FT_PHASE void ph_conv1T_t(const LayerGeom g) {
         const double* A = sm(oA); const double* W = sm(oW); const double* CS = sm(oCS); const double* UA = sm(oUA);
         double* PB = sm(oW);
-        const int T = g.G * g.R, R = g.R, Cn = g.Cn;
-        for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
+        const int T = g.G * g.R, R = g.R;
+        for (int t2 = ex.tid(); t2 < T * (2 / KN); t2 += ex.nt()) {
+            int gi, k0, r;
+            task_split<2 / KN>(g, t2, gi, k0, r);
             int rs[3] = { r + 1 == R ? 0 : r + 1, r, r == 0 ? R - 1 : r - 1 };   // r-a+1
-            double gca[3][2], gsa[3][2];                                          // per kernel row: 12 independent chains
+            double gca[3][KN], gsa[3][KN];                                        // per kernel row: independent chains
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { gca[a][0] = gca[a][1] = 0.0; gsa[a][0] = gsa[a][1] = 0.0; }
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int k = 0; k < KN; ++k) { gca[a][k] = 0.0; gsa[a][k] = 0.0; }
 #pragma unroll 2
             for (int o = 0; o < NH; ++o) {
-                double v[3][4];                                                   // rows r-a+1, columns 4g..4g+3
+                double v[3][KN + 2];                                              // rows r-a+1, columns 4g+k0 .. 4g+k0+KN+1
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[a][q] = A[o * sA + (4 * gi + q) * R + rs[a]];
+                    for (int q = 0; q < KN + 2; ++q) v[a][q] = A[o * sA + (4 * gi + k0 + q) * R + rs[a]];
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
                         const dbl2 w = ld2(W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2);
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {                             // frozen column 4g+1+k reads column 4g+1+k-b+1
+                        for (int k = 0; k < KN; ++k) {                            // frozen column 4g+1+k reads column 4g+1+k-b+1
                             gca[a][k] = fma(w.x, v[a][k + 2 - b], gca[a][k]);
                             gsa[a][k] = fma(w.y, v[a][k + 2 - b], gsa[a][k]);
                         }
                     }
             }
-            const double gc[2] = { (gca[0][0] + gca[1][0]) + gca[2][0], (gca[0][1] + gca[1][1]) + gca[2][1] };
-            const double gs[2] = { (gsa[0][0] + gsa[1][0]) + gsa[2][0], (gsa[0][1] + gsa[1][1]) + gsa[2][1] };
-            PB[(4 * gi) * R + r] = UA[t];
-            PB[(4 * gi + 3) * R + r] = 0.0;
+            if (k0 == 0) {
+                PB[(4 * gi) * R + r] = UA[gi * R + r];
+                PB[(4 * gi + 3) * R + r] = 0.0;
+            }
             wait_bar(BAR_CS);                     // the frozen cos/sin have landed in CS
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                double cp = CS[(2 * gi + k) * R + r], sp = CS[V / 2 + (2 * gi + k) * R + r];
-                PB[(4 * gi + 1 + k) * R + r] = -sp * gc[k] + cp * gs[k];
+            for (int k = 0; k < KN; ++k) {
+                const double gc = (gca[0][k] + gca[1][k]) + gca[2][k], gs = (gsa[0][k] + gsa[1][k]) + gsa[2][k];
+                const double cp = CS[(2 * gi + k0 + k) * R + r], sp = CS[V / 2 + (2 * gi + k0 + k) * R + r];
+                PB[(4 * gi + 1 + k0 + k) * R + r] = -sp * gc + cp * gs;
             }
         }
     }

@@ -126,7 +126,8 @@ struct CtaExec {
         return 1;
 #endif
     }
-    __host__ __device__ bool fine(int tasks) const { return nt() > tasks; }
+    // finer task split of the phases: only in builds with wide blocks (-DFT_THREADS=512), compiled out otherwise
+    __host__ __device__ bool fine(int tasks) const { return FT_THREADS > 256 && nt() > tasks; }
     // warp-level fp64 tensor-core tile (DMMA.8x8x4): every thread holds its own lane's fragment elements
     static constexpr int kLanes = 1;
     __host__ __device__ bool use_mma() const { return true; }
