@@ -66,6 +66,7 @@ def alg_flop_per_chain_traj(a):
 # ------------------------------------------------------------------------------------------------
 def cpu_port_setup(a):
     from oracle import fthmc_oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))      # all host threads (torchrun exports OMP_NUM_THREADS=1)
     from fthmc_b200.flow import default_init_raw
     torch.set_default_dtype(torch.float64)
     raw = default_init_raw(a.layers, 3647)

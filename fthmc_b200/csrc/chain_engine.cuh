@@ -256,7 +256,7 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 
 // ------------------------------------------------------------------------------------------------
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
-//   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v)
+//   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v), E::all(pred) (block/cluster-wide AND, a barrier)
 //   E::kLanes, E::warp(), E::nwarps(), E::lane0(), E::use_mma(), E::mma884(d0, d1, a, b)
 //                                     warp-level fp64 tensor-core tile D(8x8) += A(8x4) B(4x8) with the PTX m8n8k4 fragment
 //                                     layout.  Device: kLanes == 1, every thread holds its own lane's fragment elements;
@@ -907,8 +907,9 @@ struct Engine {
                 MID[t] = mid;
                 if (y > f) LO[t] = mid; else HI[t] = mid;
             }
-            err = ex.maxv(err);
-            if (err < pr.inv_tol) { ++it; break; }
+            // stop test max_t err_t < tol == AND_t (err_t < tol): one hardware barrier-reduction instead of a shuffle tree,
+            // a shared-memory exchange and two barriers per iteration
+            if (ex.all(err < pr.inv_tol)) { ++it; break; }
         }
         if (iters) *iters = it;
         double lj = 0.0;

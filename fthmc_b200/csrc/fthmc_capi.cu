@@ -178,6 +178,13 @@ struct CtaExec {
         return v;
 #endif
     }
+    __host__ __device__ bool all(bool pred) const {
+#ifdef __CUDA_ARCH__
+        return __syncthreads_and(pred) != 0;
+#else
+        return pred;
+#endif
+    }
     __host__ __device__ double maxv(double v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -224,7 +231,9 @@ struct ClusterExec : CtaExec {
     }
     __device__ double sum(double v) const { return reduce<false>(v); }
     __device__ double maxv(double v) const { return reduce<true>(v); }
+    __device__ bool all(bool pred) const { return reduce<true>(pred ? 0.0 : 1.0) == 0.0; }
 #else
+    bool all(bool pred) const { return pred; }
     int rank() const { return 0; }
     int nranks() const { return 1; }
     double* peer(double* p, int) const { return p; }

@@ -42,6 +42,7 @@ struct SerialExec {
     void sync() const {}
     double sum(double v) const { return v; }
     double maxv(double v) const { return v; }
+    bool all(bool pred) const { return pred; }
 };
 }
 
@@ -121,6 +122,7 @@ struct ThreadExec {
         sh->bar.arrive_and_wait();
         return t;
     }
+    bool all(bool pred) const { return maxv(pred ? 0.0 : 1.0) == 0.0; }
     double maxv(double v) const {
         sh->slots[rk] = v; sh->bar.arrive_and_wait();
         double t = sh->slots[0]; for (int i = 1; i < sh->nr; ++i) t = t > sh->slots[i] ? t : sh->slots[i];
