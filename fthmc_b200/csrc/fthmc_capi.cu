@@ -315,47 +315,88 @@ __device__ __forceinline__ T wrap_t(T x) {
     return r - PI;
 }
 
-// what: 0 = sum cos P (action), 1 = sum regularize(P) (floored charge), 2 = sum wrap(P) (batched charge)
-// grid (nchunk, B); each block reduces rows [c*rows, (c+1)*rows) of one chain in fp64.
+// 16-byte vectors of link angles: the streaming stencils move VEC consecutive sites of a lattice row per thread
+template <typename T> struct Vec;
+template <> struct Vec<double> { static constexpr int N = 2; using type = double2; };
+template <> struct Vec<float> { static constexpr int N = 4; using type = float4; };
+
+// plaquettes of the N sites (n0, n1 .. n1+N-1): three 16-byte loads and one scalar instead of 4N scalar loads
 template <typename T>
+__device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1, int n0, int n1, int order, T (&p)[Vec<T>::N]) {
+    constexpr int N = Vec<T>::N;
+    using VT = typename Vec<T>::type;
+    const int n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1n = n1 + N == L1 ? 0 : n1 + N;
+    __align__(16) T t0[N + 1], t1[N], t1p[N];
+    *reinterpret_cast<VT*>(t0) = *reinterpret_cast<const VT*>(f + (size_t)n0 * L1 + n1);
+    t0[N] = f[(size_t)n0 * L1 + n1n];
+    *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0) * L1 + n1);
+    *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0p) * L1 + n1);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+}
+
+// what: 0 = sum cos P (action), 1 = sum regularize(P) (floored charge), 2 = sum wrap(P) (batched charge)
+// grid (nc, B), thread-block cluster (nc, 1, 1): the nc CTAs of a cluster split the rows of ONE chain, reduce in fp64,
+// hand their partial sums to rank 0 through distributed shared memory, and rank 0 writes the finished per-chain value.
+// One launch, no global scratch, deterministic summation order.  nc == 1 (large batches): a plain one-CTA-per-chain scan.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links, int L0, int L1, int rows, int what, int order,
-                                                   double* __restrict__ partial) {
+                                                   double beta, int rounded, T* __restrict__ out) {
     __shared__ double red[8];
-    const int b = blockIdx.y, c = blockIdx.x;
+    __shared__ double part[16];                              // rank 0: one slot per rank of the cluster
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int b = blockIdx.y, c = blockIdx.x, nc = gridDim.x;
     const T* f = links + (size_t)b * 2 * L0 * L1;
     const int r0 = c * rows, r1 = min(L0, r0 + rows);
     double acc = 0.0;
-    for (int i = threadIdx.x; i < (r1 - r0) * L1; i += blockDim.x) {
-        const int n0 = r0 + i / L1, n1 = i % L1;
-        const T p = plaq_g(f, L0, L1, n0, n1, order);
-        acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+    if (VEC) {
+        // one 16-byte vector of sites per thread and step; (row, column) advance without divisions
+        constexpr int N = Vec<T>::N;
+        const int W = L1 / N, dr = (int)blockDim.x / W, dc = (int)blockDim.x - dr * W, nr = r1 - r0;
+        int row = (int)threadIdx.x / W, col = (int)threadIdx.x - row * W;
+        while (row < nr) {
+            T p[N];
+            plaq_vec<T>(f, L0, L1, r0 + row, col * N, order, p);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < (r1 - r0) * L1; i += blockDim.x) {
+            const int n0 = r0 + i / L1, n1 = i % L1;
+            const T p = plaq_g(f, L0, L1, n0, n1, order);
+            acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
+    double t = 0.0;
     if (threadIdx.x == 0) {
-        double t = 0.0;
         for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
-        partial[(size_t)b * gridDim.x + c] = t;
+        if (nc > 1) cl.map_shared_rank(part, 0)[c] = t;
+    }
+    if (nc > 1) {
+        cl.sync();
+        if (c != 0) return;
+        if (threadIdx.x == 0) { t = 0.0; for (int i = 0; i < nc; ++i) t += part[i]; }
+    }
+    if (threadIdx.x == 0) {
+        double r;
+        if (what == 0) r = -beta * t;
+        else if (rounded) r = floor(0.1 + t / TWO_PI_D);
+        else r = t / TWO_PI_D;
+        out[b] = (T)r;
     }
 }
 
-template <typename T>
-__global__ void k_finalize(const double* __restrict__ partial, int nchunk, int B, int what, double beta, int rounded, T* __restrict__ out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double t = 0.0;
-    for (int c = 0; c < nchunk; ++c) t += partial[(size_t)b * nchunk + c];
-    double r;
-    if (what == 0) r = -beta * t;
-    else if (rounded) r = floor(0.1 + t / TWO_PI_D);
-    else r = t / TWO_PI_D;
-    out[b] = (T)r;
-}
-
-// grid (nchunk, B): rows [r0,r1) of one chain; sin P of rows r0-1..r1-1 staged in shared memory.
-template <typename T>
+// grid (nchunk, B): rows [r0,r1) of one chain; sin P of rows r0-1..r1-1 staged in shared memory (one sine per site).
+// VEC: 16-byte loads / stores of consecutive sites and division-free (row, column) stepping; needs L1 % Vec<T>::N == 0.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int L0, int L1, int rows, T beta, int order, T* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);                  // (rows+1) x L1, row 0 is r0-1
@@ -363,6 +404,37 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
     const T* f = links + (size_t)b * 2 * L0 * L1;
     T* o = out + (size_t)b * 2 * L0 * L1;
     const int r0 = c * rows, r1 = min(L0, r0 + rows), nr = r1 - r0;
+    if (VEC) {
+        constexpr int N = Vec<T>::N;
+        using VT = typename Vec<T>::type;
+        const int W = L1 / N, dr = (int)blockDim.x / W, dc = (int)blockDim.x - dr * W;
+        const int row0 = (int)threadIdx.x / W, col0 = (int)threadIdx.x - row0 * W;
+        for (int row = row0, col = col0; row < nr + 1;) {
+            int n0 = r0 - 1 + row; if (n0 < 0) n0 += L0;
+            __align__(16) T p[N];
+            plaq_vec<T>(f, L0, L1, n0, col * N, order, p);
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[j] = M<T>::sinv(p[j]);
+            *reinterpret_cast<VT*>(S + row * L1 + col * N) = *reinterpret_cast<const VT*>(p);
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+        __syncthreads();
+        for (int row = row0, col = col0; row < nr;) {
+            const int n1 = col * N;
+            __align__(16) T s[N], su[N], f0[N], f1[N];
+            *reinterpret_cast<VT*>(s) = *reinterpret_cast<const VT*>(S + (row + 1) * L1 + n1);
+            *reinterpret_cast<VT*>(su) = *reinterpret_cast<const VT*>(S + row * L1 + n1);
+            T sl = S[(row + 1) * L1 + (n1 == 0 ? L1 - 1 : n1 - 1)];
+#pragma unroll
+            for (int j = 0; j < N; ++j) { f0[j] = beta * (s[j] - sl); f1[j] = beta * (su[j] - s[j]); sl = s[j]; }
+            *reinterpret_cast<VT*>(o + (size_t)(r0 + row) * L1 + n1) = *reinterpret_cast<const VT*>(f0);
+            *reinterpret_cast<VT*>(o + (size_t)(L0 + r0 + row) * L1 + n1) = *reinterpret_cast<const VT*>(f1);
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < (nr + 1) * L1; i += blockDim.x) {
         int n0 = r0 - 1 + i / L1; if (n0 < 0) n0 += L0;
         S[i] = M<T>::sinv(plaq_g(f, L0, L1, n0, i % L1, order));
@@ -376,10 +448,21 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
     }
 }
 
+// elementwise wrap; nv 16-byte vectors, then the scalar tail
 template <typename T>
-__global__ void k_regularize(const T* __restrict__ in, T* __restrict__ out, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = regularize_t(in[i]);
+__global__ void __launch_bounds__(256) k_regularize(const T* __restrict__ in, T* __restrict__ out, long long n, int vec) {
+    constexpr int N = Vec<T>::N;
+    using VT = typename Vec<T>::type;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nv = vec ? n / N : 0;
+    for (long long i = i0; i < nv; i += stride) {
+        __align__(16) T v[N];
+        *reinterpret_cast<VT*>(v) = reinterpret_cast<const VT*>(in)[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = regularize_t(v[j]);
+        reinterpret_cast<VT*>(out)[i] = *reinterpret_cast<const VT*>(v);
+    }
+    for (long long i = nv * N + i0; i < n; i += stride) out[i] = regularize_t(in[i]);
 }
 
 // fp64 FMA-pipe peak probe (roofline denominator for the resident-chain kernel; MEASURED_PEAKS.json has no
@@ -562,21 +645,24 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
 // ------------------------------------------------------------------------------------------------
 // C ABI: stencils
 // ------------------------------------------------------------------------------------------------
-static int stencil_rows(int L0, int L1) {
-    int rows = 8192 / L1; if (rows < 1) rows = 1; if (rows > L0) rows = L0;
-    return rows;
-}
-
+// CTAs per chain of the reduction stencils: 1 when the batch alone fills the device, otherwise a cluster of up to 16
 template <typename T>
 static int reduce_launch(const void* links, int B, int L0, int L1, int what, int order, double beta, int rounded, void* out, cudaStream_t st) {
-    const int rows = stencil_rows(L0, L1), nchunk = (L0 + rows - 1) / rows;
-    double* partial = nullptr;
-    CK(cudaMallocAsync(&partial, sizeof(double) * (size_t)B * nchunk, st));
-    k_action_topo<T><<<dim3(nchunk, B), 256, 0, st>>>((const T*)links, L0, L1, rows, what, order, partial);
-    k_finalize<T><<<(B + 127) / 128, 128, 0, st>>>(partial, nchunk, B, what, beta, rounded, (T*)out);
-    g_launches += 2;
+    int nc = 1;
+    while (nc < 16 && (long long)B * nc < 4 * 148 && 2 * nc <= L0 && (long long)(L0 / (2 * nc)) * L1 >= 1024) nc *= 2;
+    const int rows = (L0 + nc - 1) / nc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nc, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // 16-byte vector path: whole vectors per row, 16-byte aligned rows
+    const bool vec = L1 % Vec<T>::N == 0 && ((uintptr_t)links & 15) == 0;
+    auto kern = vec ? k_action_topo<T, true> : k_action_topo<T, false>;
+    if (nc > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, what, order, beta, rounded, (T*)out));
+    g_launches += 1;
     CK(cudaGetLastError());
-    CK(cudaFreeAsync(partial, st));
     return 0;
 }
 
@@ -607,15 +693,24 @@ extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta
     int rc = check_stencil(links, force_out, B, L0, L1, dtype); if (rc) return rc;
     if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
     const size_t es = dtype == FTHMC_F64 ? 8 : 4;
-    int rows = (int)((40 * 1024) / (es * L1)) - 1;
+    int rows = (int)((64 * 1024) / (es * L1)) - 1;
     if (rows < 1) return fail(FTHMC_E_LATTICE, "L1 too large for the force tile");
     if (rows > L0) rows = L0;
+    // small batches of large lattices: shorter tiles until the grid fills the device
+    while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) < 4 * 148) rows = (rows + 1) / 2;
     const int nchunk = (L0 + rows - 1) / rows;
     const size_t smem = (size_t)(rows + 1) * L1 * es;
-    if (dtype == FTHMC_F64)
-        k_force<double><<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const double*)links, L0, L1, rows, beta, order, (double*)force_out);
-    else
-        k_force<float><<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const float*)links, L0, L1, rows, (float)beta, order, (float*)force_out);
+    const int vw = dtype == FTHMC_F64 ? Vec<double>::N : Vec<float>::N;
+    const bool vec = L1 % vw == 0 && ((uintptr_t)links & 15) == 0 && ((uintptr_t)force_out & 15) == 0;
+    if (dtype == FTHMC_F64) {
+        auto kern = vec ? k_force<double, true> : k_force<double, false>;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        kern<<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const double*)links, L0, L1, rows, beta, order, (double*)force_out);
+    } else {
+        auto kern = vec ? k_force<float, true> : k_force<float, false>;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        kern<<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const float*)links, L0, L1, rows, (float)beta, order, (float*)force_out);
+    }
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -623,9 +718,10 @@ extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta
 
 extern "C" int fthmc_regularize(const void* in, void* out, long long n, int dtype, void* stream) {
     if (!in || !out || n <= 0) return fail(FTHMC_E_ARG, "null pointer or n <= 0");
-    long long blocks = (n + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
-    if (dtype == FTHMC_F64) k_regularize<double><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, n);
-    else if (dtype == FTHMC_F32) k_regularize<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)in, (float*)out, n);
+    const int vec = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    long long blocks = (n / 2 + 255) / 256; if (blocks < 1) blocks = 1; if (blocks > 148 * 32) blocks = 148 * 32;
+    if (dtype == FTHMC_F64) k_regularize<double><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, n, vec);
+    else if (dtype == FTHMC_F32) k_regularize<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)in, (float*)out, n, vec);
     else return fail(FTHMC_E_DTYPE, "dtype must be FTHMC_F64 or FTHMC_F32");
     g_launches++;
     CK(cudaGetLastError());
