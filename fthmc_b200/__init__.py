@@ -6,8 +6,10 @@ calling any entry point does, and raises if the library or the device is missing
 from ._lib import FthmcError, LIB_PATH, lib  # noqa: F401
 from .flow import PackedFlow, pack, raw_weights_of, default_init_raw  # noqa: F401
 from .api import (Param, action, u1_action, force, regularize, topocharge, topo_charge, leapfrog, hmc, hmc_batch,  # noqa: F401
-                  ft_flow, ft_flow_inv, ft_action, ft_force, ft_leapfrog, ft_hmc, ft_hmc_batch)
+                  ft_flow, ft_flow_inv, ft_action, ft_force, ft_leapfrog, ft_hmc, ft_hmc_batch,
+                  hmc_run_batch, ft_hmc_run_batch, run, ft_run, topo_history)
+from . import stats, shard  # noqa: F401
 
 __all__ = ["Param", "action", "u1_action", "force", "regularize", "topocharge", "topo_charge", "leapfrog", "hmc",
-           "hmc_batch", "ft_flow", "ft_flow_inv", "ft_action", "ft_force", "ft_leapfrog", "ft_hmc", "ft_hmc_batch",
+           "hmc_batch", "hmc_run_batch", "ft_hmc_run_batch", "run", "ft_run", "stats", "shard", "ft_flow", "ft_flow_inv", "ft_action", "ft_force", "ft_leapfrog", "ft_hmc", "ft_hmc_batch",
            "PackedFlow", "pack", "raw_weights_of", "FthmcError", "lib", "LIB_PATH"]

@@ -36,6 +36,10 @@ SIGNATURES = {
     "fthmc_ft_leapfrog": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_dp, c_sz, c_dp]),
     "fthmc_ft_hmc_traj": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_ull, c_ull, c_ull, c_int, c_int, c_int, c_dbl, c_dbl,
                                   c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
+    "fthmc_hmc_run": (c_int, [c_dp, c_dp, c_dp, c_dp, c_ull, c_ull, c_ull, c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_int,
+                              c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
+    "fthmc_ft_hmc_run": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_ull, c_ull, c_ull, c_int, c_int, c_int, c_dbl, c_dbl,
+                                 c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
 }
 
 

@@ -332,3 +332,117 @@ def ft_hmc(param, flow, field):
     u = torch.rand([], dtype=torch.float64)
     r = ft_hmc_batch(param, flow, field, p, u.reshape(1))
     return float(r["dH"][0]), float(r["exp_mdH"][0]), r["acc"][0], r["field"]
+
+
+# ------------------------------------------------------------------------------------------------
+# run loops: many trajectories per launch, the chains resident in shared memory
+# ------------------------------------------------------------------------------------------------
+def _run_call(flow_pf, beta, dt, nstep, ntraj, x, p, u, seed, traj0, chain0):
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        xd = _dev_in(x, dev, torch.float64)
+        if xd.dim() != 4:
+            raise _lib.FthmcError(-1, f"field must be (B,2,L0,L1), got {tuple(xd.shape)}")
+        B, _, L0, L1 = xd.shape
+        pd = None if p is None else _dev_in(p, dev, torch.float64)
+        ud = None if u is None else _dev_in(u, dev, torch.float64)
+        if pd is not None and tuple(pd.shape) != (ntraj,) + tuple(xd.shape):
+            raise _lib.FthmcError(-1, "p must be (ntraj,) + field.shape")
+        if ud is not None and tuple(ud.shape) != (ntraj, B):
+            raise _lib.FthmcError(-1, "u must be (ntraj, B)")
+        xo = torch.empty_like(xd)
+        sc = torch.empty((4, ntraj, B), dtype=torch.float64, device=dev)      # dH, exp(-dH), plaq, Q
+        acc = torch.empty((ntraj, B), dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        handle = None if flow_pf is None else flow_pf.handle
+        ws = _workspace(handle, B, L0, L1, dev)
+        if flow_pf is None:
+            _lib.check(L.fthmc_hmc_run(xd.data_ptr(), xo.data_ptr(), _ptr(pd), _ptr(ud), seed, traj0, chain0, B, L0, L1,
+                                       float(beta), float(dt), int(nstep), int(ntraj), sc[0].data_ptr(), sc[1].data_ptr(),
+                                       acc.data_ptr(), sc[2].data_ptr(), sc[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        else:
+            _lib.check(L.fthmc_ft_hmc_run(handle, xd.data_ptr(), xo.data_ptr(), _ptr(pd), _ptr(ud), seed, traj0, chain0,
+                                          B, L0, L1, float(beta), float(dt), int(nstep), int(ntraj), sc[0].data_ptr(),
+                                          sc[1].data_ptr(), acc.data_ptr(), sc[2].data_ptr(), sc[3].data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _stream()))
+    return dict(field=_back(xo, x), dH=_back(sc[0], x), exp_mdH=_back(sc[1], x), acc=_back(acc, x).bool(),
+                plaq=_back(sc[2], x), topo=_back(sc[3], x))
+
+
+def hmc_run_batch(param, x, ntraj, p=None, u=None, seed=0, traj0=0, chain0=0):
+    """`ntraj` consecutive plain-HMC trajectories of B chains in ONE launch (the loop of hmc_2dU1.py:697-707 with the
+    field resident on the SM).  Per-trajectory results are (ntraj, B); p (ntraj,B,2,L0,L1) / u (ntraj,B) optional."""
+    return _run_call(None, param.beta, param.dt, param.nstep, ntraj, x, p, u, seed, traj0, chain0)
+
+
+def ft_hmc_run_batch(param, flow, field, ntraj, p=None, u=None, seed=0, traj0=0, chain0=0):
+    """`ntraj` consecutive FT-HMC trajectories of B chains in ONE launch (the loop of ipynb/ft_hmc.py:454-467)."""
+    dev = _device(field)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+    return _run_call(pf, param.beta, param.dt, param.nstep, ntraj, field, p, u, seed, traj0, chain0)
+
+
+def _status_lines(first, r, b=0):
+    out = []
+    for i in range(r["dH"].shape[0]):
+        ifacc = "ACCEPT" if bool(r["acc"][i, b]) else "REJECT"
+        out.append(f"Traj: {first + i + 1:4}  {ifacc}  dH: {float(r['dH'][i, b]):< 12.8}  exp(-dH): {float(r['exp_mdH'][i, b]):< 12.8}  "
+                   f"plaq: {float(r['plaq'][i, b]):< 12.8}  topo: {float(r['topo'][i, b]):< 3.3}\n")
+    return out
+
+
+def _run_loop(param, flow, field, out, topo_history):
+    """shared body of run / ft_run: param.nrun blocks of param.ntraj trajectories, one launch per block.  Momenta and
+    Metropolis uniforms are drawn from the torch generator in the reference's order (randn_like, then rand([]), per
+    trajectory), so a seeded run follows the reference chain."""
+    import sys
+    from timeit import default_timer as timer
+    put = (lambda s: None) if out is None else out.write
+    plaq, topo = action(param, field) / (-param.beta * param.volume), topocharge(field)
+    put(f"Initial configuration:  plaq: {plaq}  topo: {topo} {field.shape}\n")
+    ts = []
+    for n in range(param.nrun):
+        t = -timer()
+        ps, us = [], []
+        for _ in range(param.ntraj):
+            ps.append(torch.randn_like(field))
+            us.append(torch.rand([], dtype=torch.float64))
+        p, u = torch.stack(ps).unsqueeze(1), torch.stack(us).reshape(-1, 1)
+        if flow is None:
+            r = hmc_run_batch(param, field.unsqueeze(0), param.ntraj, p, u)
+        else:
+            r = ft_hmc_run_batch(param, flow, field.unsqueeze(0), param.ntraj, p, u)
+        field = r["field"][0]
+        for line in _status_lines(n * param.ntraj, r):
+            put(line)
+        topo_history.extend(float(v) for v in r["topo"][:, 0])
+        t += timer()
+        ts.append(t)
+    put(f"Run times:  {ts}\n")
+    put(f"Per trajectory:  {[t / param.ntraj for t in ts]}\n")
+    if out is sys.stdout:
+        sys.stdout.flush()
+    return field
+
+
+topo_history = []
+
+
+def run(param, field=None, out=None):
+    """The trajectory loop of run(param, field) (ipynb/ft_hmc.py:180-216, hmc_2dU1.py:686-715): nrun x ntraj plain-HMC
+    trajectories of one chain (2,L0,L1), the status line of every trajectory written to `out` (a file-like object;
+    None = quiet), the charges appended to `topo_history`.  Returns the final field.  The reference's result-file
+    bookkeeping (uniquestr / skip-if-exists) stays with the caller."""
+    if field is None:
+        field = param.initializer()
+    topo_history.clear()
+    return _run_loop(param, None, field, out, topo_history)
+
+
+def ft_run(param, flow, field=None, out=None):
+    """The trajectory loop of ft_run(param, flow, field) (ipynb/ft_hmc.py:437-475) for one chain (2,L0,L1)."""
+    if field is None:
+        field = param.initializer()
+    topo_history.clear()
+    return _run_loop(param, flow, field, out, topo_history)

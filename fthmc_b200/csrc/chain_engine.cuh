@@ -1343,6 +1343,9 @@ struct TrajIO {
     double beta, dt; int nstep;
     double* out_dH; double* out_expmdH; int* out_acc; double* out_plaq; double* out_Q;
     double* out_h0; double* out_h1;
+    // multi-trajectory runs keep the chain resident: only the first trajectory of a launch loads the field from
+    // global memory and only the last one stores it
+    bool first, last;
 };
 
 // Box-Muller normals from Philox: element pair index j -> two normals
@@ -1399,7 +1402,7 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     const int V = en.Vg;
     double* P = en.wsP;
     double* X = en.sm(en.oX);
-    en.load_field(en.oX, io.field_in);
+    if (io.first) en.load_field(en.oX, io.field_in);
     ex.sync();
     en.flow_reverse(false);                                     // x = ft_flow_inv(field)
     en.for_links([&](int si, int gi) { en.wsX0[gi] = X[si]; });
@@ -1433,7 +1436,7 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     }
     ex.sync();
     double q = en.topo_floor();
-    en.store_field(io.field_out, en.oX);
+    if (io.last) en.store_field(io.field_out, en.oX);
     if (io.p_out) en.for_links([&](int, int gi) { io.p_out[gi] = P[gi]; });
     if (ex.tid() == 0 && en.rk == 0) {
         if (io.out_dH) *io.out_dH = dH;
@@ -1454,7 +1457,9 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     const int V = en.Vg;
     double* P = en.wsP;
     double* X = en.sm(en.oX);
-    en.load_field(en.oX, io.field_in);
+    if (io.first) en.load_field(en.oX, io.field_in);
+    ex.sync();
+    en.for_links([&](int si, int gi) { en.wsX0[gi] = X[si]; });   // the trajectory's start field, restored on reject
     if (io.p_in) en.for_links([&](int, int gi) { P[gi] = io.p_in[gi]; });
     else philox_momenta(en, io, P);
     ex.sync();
@@ -1477,11 +1482,11 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     bool acc = u < e;
     if (!acc) {
         ex.sync();
-        en.load_field(en.oX, io.field_in);                        // newx = x (bit-identical input)
+        en.for_links([&](int si, int gi) { X[si] = en.wsX0[gi]; });   // newx = x (bit-identical input)
     }
     ex.sync();
     double q = en.topo_floor();
-    en.store_field(io.field_out, en.oX);
+    if (io.last) en.store_field(io.field_out, en.oX);
     if (io.p_out) en.for_links([&](int, int gi) { io.p_out[gi] = P[gi]; });
     if (ex.tid() == 0 && en.rk == 0) {
         if (io.out_dH) *io.out_dH = dH;

@@ -22,9 +22,10 @@ struct ChainArgs {
     EngineParams pr;
     double beta, dt;
     int nstep;
+    int ntraj;                // trajectory modes: trajectories per launch (>= 1); per-trajectory arrays are (ntraj, B, ...)
     const double* field_in;   // (B,2,L0,L1)
-    const double* p_in;       // (B,2,L0,L1) or null
-    const double* u_in;       // (B) or null
+    const double* p_in;       // (B,2,L0,L1) or null; trajectory modes: (ntraj,B,2,L0,L1)
+    const double* u_in;       // (B) or null; trajectory modes: (ntraj,B)
     double* field_out;        // (B,2,L0,L1): flowed field / force / new field
     double* p_out;            // (B,2,L0,L1) or null
     double* s_out;            // (B): logJ / action / dH
@@ -90,21 +91,28 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
     } break;
     case MODE_FT_HMC:
     case MODE_HMC: {
-        TrajIO io;
-        io.field_in = fin; io.field_out = fout;
-        io.p_in = a.p_in ? a.p_in + (size_t)b * fs : nullptr;
-        io.u_in = a.u_in ? a.u_in + b : nullptr;
-        io.p_out = a.p_out ? a.p_out + (size_t)b * fs : nullptr;
-        io.seed = a.seed; io.chain = a.chain0 + (uint64_t)b; io.traj = a.traj;
-        io.beta = a.beta; io.dt = a.dt; io.nstep = a.nstep;
-        io.out_dH = a.s_out ? a.s_out + b : nullptr;
-        io.out_expmdH = a.expmdH ? a.expmdH + b : nullptr;
-        io.out_acc = a.acc ? a.acc + b : nullptr;
-        io.out_plaq = a.plaq ? a.plaq + b : nullptr;
-        io.out_Q = a.topo ? a.topo + b : nullptr;
-        io.out_h0 = a.h0 ? a.h0 + b : nullptr;
-        io.out_h1 = a.h1 ? a.h1 + b : nullptr;
-        if (a.mode == MODE_FT_HMC) ft_hmc_trajectory(en, io); else hmc_trajectory(en, io);
+        // run loops (ipynb/ft_hmc.py:180, 437; hmc_2dU1.py:697): ntraj trajectories of this chain in one launch, the
+        // field resident in shared memory throughout; row t of every per-trajectory array belongs to trajectory t
+        const int nt = a.ntraj < 1 ? 1 : a.ntraj;
+        for (int t = 0; t < nt; ++t) {
+            const size_t row = (size_t)t * a.B + b;
+            TrajIO io;
+            io.field_in = fin; io.field_out = fout;
+            io.p_in = a.p_in ? a.p_in + row * fs : nullptr;
+            io.u_in = a.u_in ? a.u_in + row : nullptr;
+            io.p_out = (a.p_out && t == nt - 1) ? a.p_out + (size_t)b * fs : nullptr;
+            io.seed = a.seed; io.chain = a.chain0 + (uint64_t)b; io.traj = a.traj + (uint64_t)t;
+            io.beta = a.beta; io.dt = a.dt; io.nstep = a.nstep;
+            io.out_dH = a.s_out ? a.s_out + row : nullptr;
+            io.out_expmdH = a.expmdH ? a.expmdH + row : nullptr;
+            io.out_acc = a.acc ? a.acc + row : nullptr;
+            io.out_plaq = a.plaq ? a.plaq + row : nullptr;
+            io.out_Q = a.topo ? a.topo + row : nullptr;
+            io.out_h0 = a.h0 ? a.h0 + row : nullptr;
+            io.out_h1 = a.h1 ? a.h1 + row : nullptr;
+            io.first = t == 0; io.last = t == nt - 1;
+            if (a.mode == MODE_FT_HMC) ft_hmc_trajectory(en, io); else hmc_trajectory(en, io);
+        }
     } break;
     default: break;
     }

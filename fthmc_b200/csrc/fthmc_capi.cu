@@ -828,10 +828,12 @@ static int traj_common(fthmc_flow_t flow, int mode, const double* field_in, doub
                        unsigned long long seed, unsigned long long traj, unsigned long long chain0,
                        int B, int L0, int L1, double beta, double dt, int nstep,
                        double* dH, double* exp_mdH, int* acc, double* plaq, double* topo, double* h0, double* h1,
-                       void* ws, size_t ws_bytes, void* stream) {
+                       void* ws, size_t ws_bytes, void* stream, int ntraj = 1) {
     if (!field_in || !field_out) return fail(FTHMC_E_ARG, "null pointer");
     if (nstep < 1) return fail(FTHMC_E_ARG, "nstep must be >= 1");
+    if (ntraj < 1) return fail(FTHMC_E_ARG, "ntraj must be >= 1");
     ChainArgs a{}; a.mode = mode; a.B = B; a.field_in = field_in; a.field_out = field_out; a.p_in = p_in; a.u_in = u_in;
+    a.ntraj = ntraj;
     a.seed = seed; a.traj = traj; a.chain0 = chain0; a.beta = beta; a.dt = dt; a.nstep = nstep;
     a.s_out = dH; a.expmdH = exp_mdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
     return launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
@@ -854,4 +856,26 @@ extern "C" int fthmc_ft_hmc_traj(fthmc_flow_t flow, const double* field_in, doub
     if (!flow) return fail(FTHMC_E_ARG, "null flow");
     return traj_common(flow, MODE_FT_HMC, field_in, field_out, p_in, u_in, seed, traj, chain0, B, L0, L1, beta, dt, nstep,
                        dH, exp_mdH, acc, plaq, topo, h0, h1, ws, ws_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: run loops -- ntraj consecutive trajectories per chain in ONE launch, the field resident in shared memory
+// ------------------------------------------------------------------------------------------------
+extern "C" int fthmc_hmc_run(const double* x_in, double* x_out, const double* p_in, const double* u_in,
+                             unsigned long long seed, unsigned long long traj0, unsigned long long chain0,
+                             int B, int L0, int L1, double beta, double dt, int nstep, int ntraj,
+                             double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
+                             void* ws, size_t ws_bytes, void* stream) {
+    return traj_common(nullptr, MODE_HMC, x_in, x_out, p_in, u_in, seed, traj0, chain0, B, L0, L1, beta, dt, nstep,
+                       dH, exp_mdH, acc, plaq, topo, nullptr, nullptr, ws, ws_bytes, stream, ntraj);
+}
+
+extern "C" int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, double* field_out, const double* p_in, const double* u_in,
+                                unsigned long long seed, unsigned long long traj0, unsigned long long chain0,
+                                int B, int L0, int L1, double beta, double dt, int nstep, int ntraj,
+                                double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
+                                void* ws, size_t ws_bytes, void* stream) {
+    if (!flow) return fail(FTHMC_E_ARG, "null flow");
+    return traj_common(flow, MODE_FT_HMC, field_in, field_out, p_in, u_in, seed, traj0, chain0, B, L0, L1, beta, dt, nstep,
+                       dH, exp_mdH, acc, plaq, topo, nullptr, nullptr, ws, ws_bytes, stream, ntraj);
 }

@@ -106,6 +106,23 @@ int fthmc_ft_hmc_traj(fthmc_flow_t flow, const double* field_in, double* field_o
                       double* dH, double* exp_mdH, int* acc, double* plaq, double* topo, double* h0, double* h1,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* ---- run loops -------------------------------------------------------------------------------------------- */
+/* The trajectory loops of run(param, field) hmc_2dU1.py:697-707 / ipynb/ft_hmc.py:199-208 and ft_run(param, flow, field)
+ * ipynb/ft_hmc.py:454-467: ntraj consecutive trajectories of every chain in ONE launch, the field resident in shared
+ * memory throughout.  Per-trajectory arrays are (ntraj, B) -- dH, exp(-dH), acc, and the two observables the
+ * reference recomputes after every trajectory (plaq = action/(-beta V), floored topological charge) -- and p_in / u_in,
+ * when given, are (ntraj, B, 2, L0, L1) / (ntraj, B) in trajectory order; NULL => Philox(seed, chain0+b, traj0+t). */
+int fthmc_hmc_run(const double* x_in, double* x_out, const double* p_in, const double* u_in,
+                  unsigned long long seed, unsigned long long traj0, unsigned long long chain0,
+                  int B, int L0, int L1, double beta, double dt, int nstep, int ntraj,
+                  double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
+                  void* ws, size_t ws_bytes, void* stream);
+int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, double* field_out, const double* p_in, const double* u_in,
+                     unsigned long long seed, unsigned long long traj0, unsigned long long chain0,
+                     int B, int L0, int L1, double beta, double dt, int nstep, int ntraj,
+                     double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* diagnostic: launch `blocks` x 256 threads of pure fp64 FMA chains (2*16*iters flop per thread); *flop_out (host)
  * receives the flop count.  Used by bench.py to measure the fp64 roofline denominator on the device. */
 int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);

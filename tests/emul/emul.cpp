@@ -11,6 +11,9 @@
 #include "../../fthmc_b200/csrc/chain_programs.cuh"
 #include "../../fthmc_b200/csrc/weight_pack.h"
 
+static int g_ntraj = 1;
+extern "C" void emul_set_ntraj(int n) { g_ntraj = n < 1 ? 1 : n; }   // trajectories per emul_run call (run-loop mode)
+
 namespace {
 struct SerialExec {
     static constexpr bool kCluster = false;
@@ -64,7 +67,7 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
     a.field_in = field_in; a.p_in = p_in; a.u_in = u_in; a.field_out = field_out; a.p_out = p_out;
     a.s_out = s_out; a.layer_logJ = layer_logJ; a.iters = iters;
     a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
-    a.seed = seed; a.traj = traj; a.chain0 = 0;
+    a.seed = seed; a.traj = traj; a.chain0 = 0; a.ntraj = g_ntraj;
     SerialExec ex{ smem.data() };
     Engine<SerialExec> en(ex, a.pr, ws.data());
     if (nlayers > 0) en.load_geom_table();
@@ -153,7 +156,7 @@ extern "C" int emul_run_cluster(int nr, int mode, int B, int L0, int L1, int nla
     a.field_in = field_in; a.p_in = p_in; a.u_in = u_in; a.field_out = field_out; a.p_out = p_out;
     a.s_out = s_out; a.layer_logJ = layer_logJ; a.iters = iters;
     a.expmdH = expmdH; a.acc = acc; a.plaq = plaq; a.topo = topo; a.h0 = h0; a.h1 = h1;
-    a.seed = seed; a.traj = traj; a.chain0 = 0;
+    a.seed = seed; a.traj = traj; a.chain0 = 0; a.ntraj = g_ntraj;
     ClusterShared sh(nr);
     for (int r = 0; r < nr; ++r) sh.arenas[r] = arenas[r].data();
     std::vector<std::thread> th;

@@ -41,18 +41,20 @@ def _p(a, ct=ctypes.c_double):
 
 
 def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, act="silu", conv=0,
-        tol=1e-6, max_iter=1000, mu=None, off=None, seed=0, traj=0, nranks=0):
+        tol=1e-6, max_iter=1000, mu=None, off=None, seed=0, traj=0, nranks=0, ntraj=1):
     """field: (B,2,L0,L1) float64.  Returns a dict of outputs.  nranks >= 1: the cluster code path of the
     engine with that many ranks (host threads standing in for the CTAs of a thread-block cluster)."""
     field = np.ascontiguousarray(field, dtype=np.float64)
     B, _, L0, L1 = field.shape
+    lib().emul_set_ntraj(int(ntraj))     # run-loop mode: per-trajectory outputs are (ntraj, B), p/u (ntraj, B, ...)
     raw = np.ascontiguousarray(raw_weights, dtype=np.float64) if raw_weights is not None else np.zeros((0, 955))
     n = raw.shape[0]
     mu = np.array([i % 2 for i in range(n)] if mu is None else mu, dtype=np.int32)
     off = np.array([(i // 2) % 4 for i in range(n)] if off is None else off, dtype=np.int32)
-    out = dict(field=np.zeros_like(field), p=np.zeros_like(field), s=np.zeros(B), layer_logJ=np.zeros((B, max(n, 1))),
-               iters=np.zeros((B, max(n, 1)), dtype=np.int32), expmdH=np.zeros(B), acc=np.zeros(B, dtype=np.int32),
-               plaq=np.zeros(B), topo=np.zeros(B), h0=np.zeros(B), h1=np.zeros(B))
+    nb = B * int(ntraj)
+    out = dict(field=np.zeros_like(field), p=np.zeros_like(field), s=np.zeros(nb), layer_logJ=np.zeros((B, max(n, 1))),
+               iters=np.zeros((B, max(n, 1)), dtype=np.int32), expmdH=np.zeros(nb), acc=np.zeros(nb, dtype=np.int32),
+               plaq=np.zeros(nb), topo=np.zeros(nb), h0=np.zeros(nb), h1=np.zeros(nb))
     p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
     fn = lib().emul_run if nranks == 0 else (lambda *args: lib().emul_run_cluster(nranks, *args))
@@ -62,5 +64,6 @@ def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, 
                         _p(out["layer_logJ"]), _p(out["iters"], ctypes.c_int), _p(out["expmdH"]),
                         _p(out["acc"], ctypes.c_int), _p(out["plaq"]), _p(out["topo"]), _p(out["h0"]), _p(out["h1"]),
                         ctypes.c_ulonglong(seed), ctypes.c_ulonglong(traj))
+    lib().emul_set_ntraj(1)
     assert rc == 0, rc
     return out

@@ -295,12 +295,69 @@ def gen_thousand(plain, ftlib, ref, out):
     print("ft 1000: acc rate", np.mean(acc), "dH range", np.min(dH), np.max(dH))
 
 
+def gen_run(plain, ftlib, ref, out):
+    """The trajectory loops of run / ft_run (ipynb/ft_hmc.py:199-208, 454-467) seeded ONCE: a free-running chain whose
+    momenta and uniforms come from consecutive draws of the torch generator, plus the block statistics of a synthetic
+    charge history (ipynb/ft_hmc.py:14-56).  The loops are replayed here without the reference's result-file handling."""
+    L, ntraj, seed = 8, 12, 781          # seed picked so that both chains contain rejected trajectories
+    rec = dict(L=L, ntraj=ntraj, seed=seed)
+    # plain
+    P = ref.Param(beta=2.0, lat=(L, L), tau=1.6, nstep=6)
+    torch.manual_seed(1331)
+    x0 = torch.empty((2, L, L)).uniform_(-np.pi, np.pi)
+    rec.update(x0=x0.numpy().copy(), plain_beta=2.0, plain_tau=1.6, plain_nstep=6)
+    torch.manual_seed(seed)
+    field = x0.clone()
+    dHs, accs, plaqs, topos = [], [], [], []
+    for i in range(ntraj):
+        dH, e, acc, field = ref.hmc(P, field)
+        dHs.append(float(dH)); accs.append(bool(acc))
+        plaqs.append(float(ref.action(P, field) / (-P.beta * P.volume))); topos.append(float(ref.topocharge(field)))
+    rec.update(plain_dH=np.array(dHs), plain_acc=np.array(accs), plain_plaq=np.array(plaqs), plain_topo=np.array(topos),
+               plain_final=field.numpy().copy())
+    # field transformed (8 layers, weights x2 so that the flow is far from the identity)
+    torch.manual_seed(3647)
+    flow = ftlib.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=8, n_mixture_comps=2, hidden_sizes=[8, 8], kernel_size=3)
+    flow.eval()
+    with torch.no_grad():
+        for prm in flow.parameters():
+            prm.mul_(2.0)
+    for prm in flow.parameters():
+        prm.requires_grad_(False)
+    Pf = ref.Param(beta=2.0, lat=(L, L), tau=0.9, nstep=6)
+    rec.update(weights=flat_weights(flow), ft_beta=2.0, ft_tau=0.9, ft_nstep=6)
+    torch.manual_seed(seed)
+    field = x0.clone()
+    dHs, accs, plaqs, topos = [], [], [], []
+    for i in range(ntraj):
+        fr = torch.reshape(field, (1,) + field.shape)
+        dH, e, acc, fr = quiet(ref.ft_hmc, Pf, flow, fr)
+        field = fr[0]
+        dHs.append(float(dH)); accs.append(bool(acc))
+        plaqs.append(float(ref.action(Pf, field) / (-Pf.beta * Pf.volume))); topos.append(float(ref.topocharge(field)))
+    rec.update(ft_dH=np.array(dHs), ft_acc=np.array(accs), ft_plaq=np.array(plaqs), ft_topo=np.array(topos),
+               ft_final=field.numpy().copy())
+    # statistics
+    rng = np.random.default_rng(5)
+    hist = np.cumsum(rng.integers(-1, 2, size=300)).astype(np.float64)
+    rec["stat_hist"] = hist
+    rec["stat_change_sqr_vs_dt"] = np.array(ref.change_sqr_vs_dt(list(hist[100:]), 10), dtype=np.float64)
+    rec["stat_block_sizes"] = np.array([len(b) for b in ref.block_list(list(range(37)))])
+    np.savez_compressed(os.path.join(out, "run_L8.npz"), **rec)
+    print("run_L8: plain acc", np.mean(rec["plain_acc"]), "ft acc", np.mean(rec["ft_acc"]), "ft dH", rec["ft_dH"][:4])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=HERE)
+    ap.add_argument("--only", default="", help="generate only this fixture (e.g. run)")
     a = ap.parse_args()
     plain, ftlib, ref = load_reference(a.ref)
+    if a.only == "run":
+        gen_run(plain, ftlib, ref, a.out)
+        return
+    gen_run(plain, ftlib, ref, a.out)
     gen_plain(plain, a.out)
     gen_flow_case(ftlib, ref, "ft_L8_n8", a.out, L=8, beta=2.0, n_layers=8, B=3, nstep=6, ntraj=6, scale=2.0)
     gen_flow_case(ftlib, ref, "ft_L16_b6", a.out, L=16, beta=6.0, n_layers=24, B=2, nstep=10, ntraj=3)

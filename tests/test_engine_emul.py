@@ -154,3 +154,41 @@ def test_cluster_decomposition_is_invisible():
         assert np.array_equal(o["topo"], ref["topo"]) and np.array_equal(o["acc"], ref["acc"])
         o = E.run("hmc", None, x, beta=3.0, dt=0.05, nstep=4, seed=5, traj=1, nranks=nr)
         assert np.array_equal(o["field"], refp["field"]) and np.max(np.abs(o["s"] - refp["s"])) < 1e-10
+
+
+def replay_draws(seed, shape, n):
+    """the momenta and uniforms a run loop seeded once would draw: randn_like(field), rand([]) per trajectory"""
+    import torch
+    st = torch.get_rng_state()
+    torch.manual_seed(seed)
+    ps, us = [], []
+    for _ in range(n):
+        ps.append(torch.randn(shape, dtype=torch.float64).numpy())
+        us.append(float(torch.rand([], dtype=torch.float64)))
+    torch.set_rng_state(st)
+    return np.stack(ps), np.array(us)
+
+
+@pytest.mark.parametrize("nranks", [0, 2])
+def test_run_loops_resident_chain(golden, nranks):
+    """ntraj trajectories in ONE call with the field resident (run / ft_run): the reference's free-running chain,
+    accepts and rejects included; and identical to calling trajectory by trajectory."""
+    g = golden("run_L8")
+    n, seed = int(g["ntraj"]), int(g["seed"])
+    p, u = replay_draws(seed, (2, 8, 8), n)
+    x0 = g["x0"][None]
+    kw = dict(beta=float(g["plain_beta"]), dt=float(g["plain_tau"]) / int(g["plain_nstep"]), nstep=int(g["plain_nstep"]))
+    o = E.run("hmc", None, x0, p=p[:, None], u=u[:, None], ntraj=n, nranks=nranks, **kw)
+    assert np.max(np.abs(o["s"] - g["plain_dH"])) < 1e-9 and np.array_equal(o["acc"].astype(bool), g["plain_acc"])
+    assert np.array_equal(o["topo"], g["plain_topo"]) and np.max(np.abs(o["plaq"] - g["plain_plaq"])) < 1e-12
+    assert np.max(np.abs(o["field"][0] - g["plain_final"])) < 1e-10
+    kw = dict(beta=float(g["ft_beta"]), dt=float(g["ft_tau"]) / int(g["ft_nstep"]), nstep=int(g["ft_nstep"]))
+    o = E.run("ft_hmc", g["weights"], x0, p=p[:, None], u=u[:, None], ntraj=n, nranks=nranks, **kw)
+    assert np.max(np.abs(o["s"] - g["ft_dH"])) < 1e-8 and np.array_equal(o["acc"].astype(bool), g["ft_acc"])
+    assert np.array_equal(o["topo"], g["ft_topo"]) and np.max(np.abs(o["plaq"] - g["ft_plaq"])) < 1e-10
+    assert np.max(np.abs(o["field"][0] - g["ft_final"])) < 1e-8
+    cur = x0
+    for t in range(3):
+        r = E.run("ft_hmc", g["weights"], cur, p=p[t][None], u=u[t:t + 1], nranks=nranks, **kw)
+        assert r["s"][0] == o["s"][t] and r["acc"][0] == o["acc"][t]
+        cur = r["field"]

@@ -331,6 +331,59 @@ def test_cluster_path_vs_oracle(L, layers, B):
     assert np.max(np.abs(xg.numpy() - xo.numpy())) < 1e-11 and np.max(np.abs(pg.numpy() - po.numpy())) < 1e-11
 
 
+# ---------------------------------------------------------------- run loops (many trajectories per launch)
+def test_run_loops_reproduce_reference_chain(golden):
+    """run / ft_run seeded once: the reference's free-running chain (12 trajectories, accepts and rejects), every
+    printed observable, from ONE kernel launch per nrun block with the chain resident in shared memory."""
+    import io
+    g = golden("run_L8")
+    n, x0 = int(g["ntraj"]), T(g["x0"])
+    P = ft.Param(beta=float(g["plain_beta"]), lat=(8, 8), tau=float(g["plain_tau"]), nstep=int(g["plain_nstep"]), ntraj=n // 2, nrun=2)
+    torch.manual_seed(int(g["seed"]))
+    buf = io.StringIO()
+    f = ft.run(P, x0.clone(), out=buf)
+    assert np.max(np.abs(f.numpy() - g["plain_final"])) < 1e-10
+    assert np.array_equal(np.array(ft.topo_history), g["plain_topo"])
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("Traj:")]
+    assert len(lines) == n and [("ACCEPT" in l) for l in lines] == list(g["plain_acc"])
+    flow = module_like(g)
+    Pf = ft.Param(beta=float(g["ft_beta"]), lat=(8, 8), tau=float(g["ft_tau"]), nstep=int(g["ft_nstep"]), ntraj=n, nrun=1)
+    torch.manual_seed(int(g["seed"]))
+    f = ft.ft_run(Pf, flow, x0.clone())
+    assert np.max(np.abs(f.numpy() - g["ft_final"])) < 1e-8
+    assert np.array_equal(np.array(ft.topo_history), g["ft_topo"])
+
+
+def test_run_batch_equals_trajectory_by_trajectory():
+    """ft_hmc_run_batch(ntraj) == ntraj calls of ft_hmc_batch (bit for bit), explicit momenta and device-RNG mode,
+    single-CTA (L=16) and cluster (L=64) paths; same for plain HMC."""
+    flow = O.random_flow(n_layers=6, seed=4, scale=2.0)
+    pf = ft.PackedFlow(_raw_of(flow))
+    for L, B in ((16, 5), (64, 2)):
+        gen = torch.Generator().manual_seed(L)
+        x = ((torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+        P = ft.Param(beta=3.0, lat=(L, L), tau=0.4, nstep=3)
+        n = 3
+        r = ft.ft_hmc_run_batch(P, pf, x, n, seed=9, traj0=5, chain0=2)
+        cur = x
+        for t in range(n):
+            s1 = ft.ft_hmc_batch(P, pf, cur, seed=9, traj=5 + t, chain0=2)
+            assert torch.equal(s1["dH"], r["dH"][t]) and torch.equal(s1["acc"], r["acc"][t])
+            assert torch.equal(s1["topo"], r["topo"][t]) and torch.equal(s1["plaq"], r["plaq"][t])
+            cur = s1["field"]
+        assert torch.equal(cur, r["field"])
+        p = torch.randn(n, B, 2, L, L, generator=gen, dtype=torch.float64).cuda()
+        u = torch.rand(n, B, generator=gen, dtype=torch.float64).cuda()
+        r = ft.hmc_run_batch(P, x, n, p, u)
+        cur = x
+        for t in range(n):
+            s1 = ft.hmc_batch(P, cur, p[t], u[t])
+            assert torch.equal(s1["dH"], r["dH"][t]) and torch.equal(s1["acc"], r["acc"][t])
+            cur = s1["field"]
+        assert torch.equal(cur, r["field"])
+        assert r["dH"].shape == (n, B) and r["acc"].dtype == torch.bool
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:

@@ -31,3 +31,17 @@ def test_mask_parameters_from_active_mask():
             got_mu = 0 if bool(m[0].any()) else 1
             line = m[0][0, :] if got_mu == 0 else m[1][:, 0]
             assert (got_mu, int(torch.nonzero(line)[0])) == (mu, off)
+
+
+def test_block_statistics_match_reference(golden):
+    """fthmc_b200.stats against the reference's own functions (ipynb/ft_hmc.py:14-56) on a synthetic charge history."""
+    from fthmc_b200 import stats
+    g = golden("run_L8")
+    hist = list(g["stat_hist"][100:])
+    got = np.array(stats.change_sqr_vs_dt(hist, 10), dtype=np.float64)
+    assert np.array_equal(got, g["stat_change_sqr_vs_dt"])
+    assert [len(b) for b in stats.block_list(list(range(37)))] == list(g["stat_block_sizes"])
+    assert np.array_equal(np.array(stats.topo_change_sqr(list(g["stat_hist"]), 10)), g["stat_change_sqr_vs_dt"])
+    q = np.stack([g["stat_hist"], g["stat_hist"][::-1]], axis=1)
+    m, e = stats.batched_topo_change_sqr(q, dt=1)
+    assert m > 0 and e >= 0

@@ -137,3 +137,26 @@ def test_known_answers():
     assert abs(float(O.topo_charge(x) - O.topo_charge(xg))) < 1e-10
     _, logJg = O.ft_flow_logJ(flow, xg)
     assert abs(float(logJ - logJg)) < 1e-9
+
+
+def test_run_loops_follow_reference_chain(golden):
+    """A chain seeded once (momenta / uniforms from consecutive generator draws, the order of run / ft_run):
+    the oracle reproduces the reference's free-running chain, accepts and rejects included."""
+    g = golden("run_L8")
+    x0 = torch.from_numpy(g["x0"])
+    torch.manual_seed(int(g["seed"]))
+    f = x0.clone()
+    for i in range(int(g["ntraj"])):
+        dH, e, acc, f = O.hmc(float(g["plain_beta"]), float(g["plain_tau"]) / int(g["plain_nstep"]), int(g["plain_nstep"]), f)
+        assert abs(float(dH) - g["plain_dH"][i]) < 1e-9 and bool(acc) == bool(g["plain_acc"][i])
+        assert float(O.topocharge(f)) == g["plain_topo"][i]
+    assert np.max(np.abs(f.numpy() - g["plain_final"])) < 1e-10
+    flow = oracle_flow_from_golden(dict(weights=g["weights"], activation="silu", convention=0))
+    torch.manual_seed(int(g["seed"]))
+    f = x0.clone()
+    for i in range(int(g["ntraj"])):
+        dH, e, acc, fr = O.ft_hmc(float(g["ft_beta"]), float(g["ft_tau"]) / int(g["ft_nstep"]), int(g["ft_nstep"]), flow, f[None])
+        f = fr[0]
+        assert abs(float(dH) - g["ft_dH"][i]) < 1e-8 and bool(acc) == bool(g["ft_acc"][i])
+        assert float(O.topocharge(f)) == g["ft_topo"][i]
+    assert np.max(np.abs(f.numpy() - g["ft_final"])) < 1e-8
