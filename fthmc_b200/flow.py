@@ -120,3 +120,60 @@ def default_init_raw(n_layers=24, seed=3647):
         torch.set_default_dtype(old)
         torch.set_rng_state(st)
     return np.stack(rows)
+
+
+# ------------------------------------------------------------------------------------------------
+# on-disk formats and lattice transfer
+# ------------------------------------------------------------------------------------------------
+def raw_from_state_dict(sd):
+    """(n_layers,955) raw weights from the `state_dict()` of a reference flow (`ModuleList` of `GaugeEquivCouplingLayer`):
+    keys `"{i}.plaq_coupling.net.{k}.weight|bias"` with k the positions of the three convolutions in the `Sequential`
+    (0, 2, 4 for make_conv_net, ipynb/field_transformation.py:84-99).  Also accepts a whole checkpoint dict as written by
+    `save_checkpoint` (fthmc/utils/io.py:148-170: the flow is under 'model_state_dict').  Mask tensors and other
+    entries are ignored: masks are regenerated from (mu, off) for whatever lattice the flow is applied to."""
+    import re
+    if "model_state_dict" in sd:
+        sd = sd["model_state_dict"]
+    pat = re.compile(r"^(?:layers\.)?(\d+)\.plaq_coupling\.net\.(\d+)\.(weight|bias)$")
+    layers = {}
+    for key, val in sd.items():
+        m = pat.match(key)
+        if m:
+            layers.setdefault(int(m.group(1)), {}).setdefault(int(m.group(2)), {})[m.group(3)] = val
+    if not layers:
+        raise _lib.FthmcError(-5, "no '<i>.plaq_coupling.net.<k>.weight' entries: not a flow state_dict")
+    rows = []
+    for i in range(len(layers)):
+        if i not in layers:
+            raise _lib.FthmcError(-5, f"layer {i} missing from the state_dict")
+        convs = [layers[i][k] for k in sorted(layers[i])]
+        shapes = [tuple(c["weight"].shape) for c in convs]
+        if shapes != [(8, 2, 3, 3), (8, 8, 3, 3), (3, 8, 3, 3)]:
+            raise _lib.FthmcError(-5, f"unsupported CNN shape {shapes} in layer {i}")
+        rows.append(np.concatenate([np.concatenate([torch.as_tensor(c["weight"]).detach().double().cpu().numpy().ravel(),
+                                                    torch.as_tensor(c["bias"]).detach().double().cpu().numpy().ravel()]) for c in convs]))
+    return np.stack(rows)
+
+
+def pack_state_dict(sd, activation="silu", convention=0, inv_prec=1e-6, inv_max_iter=1000, device=None):
+    """PackedFlow from a flow `state_dict` / checkpoint dict (see raw_from_state_dict)."""
+    return PackedFlow(raw_from_state_dict(sd), activation=activation, convention=convention, inv_prec=inv_prec,
+                      inv_max_iter=inv_max_iter, device=device)
+
+
+def load_flow(path, activation="silu", convention=0, device=None):
+    """Flow weights from disk: a `ckpt-era*-epoch*.tar` checkpoint or a bare `state_dict` file (fthmc/utils/io.py:114-197),
+    or a pickled `ModuleList` as written by `torch.save(flow, 'flow_b{beta}_l{L}x{L}.dat')` (ipynb/ft_hmc.py:356-373;
+    unpickling that one needs the reference's classes importable)."""
+    obj = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(obj, dict):
+        return pack_state_dict(obj, activation=activation, convention=convention, device=device)
+    return pack(obj, convention=convention, device=device)
+
+
+def flow_resize(flow, lat_new=None):
+    """flow_resize(flow, lat_new) (ipynb/ft_hmc.py:511-513) / transfer_to_new_lattice (fthmc/train.py:434-455): the
+    reference rebuilds the layers around the same CNNs with masks for the new lattice.  The packed flow holds only
+    the translation-equivariant CNN weights and the (mu, off) of each mask, so the SAME handle already applies to every
+    lattice size (multiples of 4): this returns the packed flow unchanged."""
+    return pack(flow)

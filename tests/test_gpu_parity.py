@@ -384,6 +384,25 @@ def test_run_batch_equals_trajectory_by_trajectory():
         assert r["dH"].shape == (n, B) and r["acc"].dtype == torch.bool
 
 
+def test_checkpoint_load_and_lattice_transfer(golden, tmp_path):
+    """A checkpoint written in the reference's format drives the kernels; the packed flow of an L=16 run applies
+    unchanged to L=32 and L=128 (flow_resize / transfer_to_new_lattice: same CNN weights, masks for the new lattice)."""
+    g16, g32 = golden("ft_L16_b6"), golden("ft_L32_b4")
+    flow16 = module_like(g16)
+    fn = tmp_path / "ckpt-era0-epoch0.tar"
+    torch.save({"era": 0, "epoch": 0, "model_state_dict": flow16.state_dict(), "optimizer_state_dict": {}}, fn)
+    pf = ft.load_flow(str(fn))
+    assert np.max(np.abs(ft.ft_flow(pf, T(g16["x"])).numpy() - g16["flow_fwd"])) < 1e-12
+    big = ft.flow_resize(flow16, (32, 32))                      # the reference's flow at L=32 has the same weights
+    assert np.array_equal(g16["weights"], g32["weights"])
+    assert np.max(np.abs(ft.ft_flow(big, T(g32["x"])).numpy() - g32["flow_fwd"])) < 1e-12
+    assert relerr(ft.ft_force(ft.Param(beta=float(g32["beta"]), lat=(32, 32)), big, T(g32["x"])).numpy(), g32["ft_force"]) < REL
+    x = (torch.rand(1, 2, 128, 128, dtype=torch.float64) * 2 - 1) * np.pi
+    y, lj = ft.ft_flow(pf, x, with_logJ=True)
+    xi, lji = ft.ft_flow_inv(pf, y, with_logJ=True)
+    assert float(torch.max(torch.abs(torch.remainder(xi - x + np.pi, 2 * np.pi) - np.pi))) < 5e-5 and abs(float(lj + lji)) < 1e-2
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:

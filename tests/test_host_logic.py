@@ -45,3 +45,31 @@ def test_block_statistics_match_reference(golden):
     q = np.stack([g["stat_hist"], g["stat_hist"][::-1]], axis=1)
     m, e = stats.batched_topo_change_sqr(q, dt=1)
     assert m > 0 and e >= 0
+
+
+def test_state_dict_and_checkpoint_formats(golden, tmp_path):
+    """weights from a flow state_dict / a save_checkpoint-style dict (fthmc/utils/io.py:148-170) come out in the raw
+    order the packer expects; mask tensors in the state_dict are ignored; malformed inputs are refused."""
+    import torch.nn as nn
+    import pytest
+    g = golden("ft_L8_n8")
+    shapes = [(8, 2, 3, 3), (8,), (8, 8, 3, 3), (8,), (3, 8, 3, 3), (3,)]
+    sd = {}
+    for i, row in enumerate(g["weights"]):
+        pos = 0
+        for k, (ws, bs) in zip((0, 2, 4), zip(shapes[0::2], shapes[1::2])):
+            n = int(np.prod(ws)); sd[f"{i}.plaq_coupling.net.{k}.weight"] = torch.from_numpy(row[pos:pos + n].reshape(ws).copy()); pos += n
+            n = int(np.prod(bs)); sd[f"{i}.plaq_coupling.net.{k}.bias"] = torch.from_numpy(row[pos:pos + n].reshape(bs).copy()); pos += n
+        sd[f"{i}.active_mask"] = torch.zeros(2, 8, 8)
+        sd[f"{i}.plaq_coupling.active_mask"] = torch.zeros(8, 8)
+    assert np.array_equal(F.raw_from_state_dict(sd), g["weights"])
+    ck = {"era": 1, "epoch": 2, "model_state_dict": sd, "optimizer_state_dict": {}}
+    assert np.array_equal(F.raw_from_state_dict(ck), g["weights"])
+    fn = tmp_path / "ckpt-era1-epoch2.tar"
+    torch.save(ck, fn)
+    assert np.array_equal(F.raw_from_state_dict(torch.load(fn, weights_only=False)), g["weights"])
+    with pytest.raises(ft.FthmcError):
+        F.raw_from_state_dict({"foo": torch.zeros(1)})
+    bad = dict(sd); bad["0.plaq_coupling.net.0.weight"] = torch.zeros(4, 2, 3, 3)
+    with pytest.raises(ft.FthmcError):
+        F.raw_from_state_dict(bad)
