@@ -106,23 +106,30 @@ FT_HD double regularize1(double f) {
     return TWO_PI_D * (g - floor(g) - 0.5);
 }
 
-// e^x for |x| <= 708 with ~1 ulp error: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on
-// |r| <= 0.347 (remainder 4e-18), scaling through the exponent bits.  About half the instructions of
-// the library exp(): the SiLU evaluations are a quarter of the trajectory's run time.
-// On the device the constants sit in constant memory: a DFMA takes a constant-bank operand directly, whereas
-// 64-bit literals cost two uniform-register moves each and made the activation loops issue-bound.
-#define FT_EXP_COEFS { 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
-                       2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, \
-                       8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0, \
-                       1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10 }
+// e^x for |x| <= 708 with ~1 ulp error: x = (16 k + j) ln2/16 + r with |r| <= ln2/32, e^x = 2^k * 2^(j/16) * e^r.
+// 2^(j/16) comes from a 16-entry table (on the device: 128 bytes of shared memory, one bank each -- conflict free
+// for any index pattern), the power of two goes into its exponent bits with an integer add, and e^r - 1 needs a
+// degree-7 Taylor polynomial only (remainder r^8/8! < 1.3e-18).  8 fp64 operations after the range reduction instead of
+// the 14 of a degree-13 polynomial on |r| <= ln2/2: the SiLU evaluations are a fifth of the trajectory's run time.
+// The scalar constants sit in constant memory on the device (a DFMA takes a constant-bank operand directly).
+//
+// CONTRACT with the kernels: doubles [16, 32) of the dynamic shared memory hold FT_EXP_TABLE (chain kernels copy it
+// there before any phase runs, see fthmc_capi.cu).
+#define FT_EXP_TABLE { 1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474 }
+#define FT_EXP_COEFS { 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, \
+                       23.083120654223414517, 6755399441055744.0, -0.04332169877307024, -1.1926343307941173e-11 }
 #ifdef __CUDACC__
-__constant__ double c_exp[18] = FT_EXP_COEFS;
+__constant__ double c_exp[10] = FT_EXP_COEFS;
+__constant__ double c_exp_tab[16] = FT_EXP_TABLE;
 #endif
 FT_HD double exp_fast(double x) {
 #ifdef __CUDA_ARCH__
     const double* K = c_exp;
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    const double* TAB = fthmc_dyn_smem + 16;
 #else
-    const double K[18] = FT_EXP_COEFS;
+    const double K[10] = FT_EXP_COEFS;
+    static const double TAB[16] = FT_EXP_TABLE;
 #endif
     // clamp to [-708, 708] (a NaN maps to +-708).  On the device: integer compare/select on the high word (708.0 ==
     // 0x40862000'00000000) instead of DSETP/FSEL pairs on the fp64 pipe
@@ -134,34 +141,39 @@ FT_HD double exp_fast(double x) {
 #else
     x = fmin(fmax(x, -708.0), 708.0);
 #endif
-    const double t = x * K[14];                                              // x / ln2
-    const double nm = t + K[15];                                             // rint(t) in the low mantissa bits
-    const double n = nm - K[15];
-    double r = fma(n, K[16], x);
-    r = fma(n, K[17], r);
-    double p = K[0];                                                         // 1/13!
+    const double t = x * K[6];                                               // 16 x / ln2
+    const double nm = t + K[7];                                              // rint(t) in the low mantissa bits
+    const double n = nm - K[7];
+    double r = fma(n, K[8], x);                                              // Cody-Waite: ln2/16 in two pieces
+    r = fma(n, K[9], r);
+    double w = K[0];                                                         // e^r = 1 + r (1 + r w),  w = 1/2 + r/6 + ... + r^5/5040
 #pragma unroll
-    for (int i = 1; i < 14; ++i) p = fma(p, r, K[i]);
-    // 2^n, n in [-1022, 1022]: n is the low word of nm (two's complement), shifted into the exponent field
-    double sc;
+    for (int i = 1; i < 6; ++i) w = fma(w, r, K[i]);
+    const double q = r * fma(r, w, 1.0);                                     // e^r - 1
+    int ni;
 #ifdef __CUDA_ARCH__
-    sc = __hiloint2double((__double2loint(nm) + 1023) << 20, 0);
+    ni = __double2loint(nm);                                                 // n as a two's complement integer
+    const double tj = TAB[ni & 15];
+    const double sc = __hiloint2double(__double2hiint(tj) + ((ni >> 4) << 20), __double2loint(tj));   // 2^k * 2^(j/16)
 #else
-    long long bits = ((long long)n + 1023LL) << 52;
+    ni = (int)n;
+    const double tj = TAB[ni & 15];
+    long long bits;
+    memcpy(&bits, &tj, sizeof(bits));
+    bits += (long long)(ni >> 4) << 52;
+    double sc;
     memcpy(&sc, &bits, sizeof(sc));
 #endif
-    return p * sc;
+    return fma(sc, q, sc);
 }
 
-// 1/d for d >= 1 (two Newton steps on the hardware seed); host: plain division
+// 1/d for d >= 1 (one cubic Newton step on the hardware seed: three DFMA); host: plain division
 FT_HD double rcp_ge1(double d) {
 #ifdef __CUDA_ARCH__
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
+    const double e = fma(-d, y, 1.0);             // seed error e ~ 2^-20; y (1 + e + e^2) leaves e^3
+    y = fma(y, fma(e, e, e), y);
     return y;
 #else
     return 1.0 / d;

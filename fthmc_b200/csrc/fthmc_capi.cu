@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
         ClusterExec ex; ex.red = fthmc_dyn_smem;
         new (en) Engine<ClusterExec>(ex, a.pr, a.ws + (size_t)cid * a.ws_stride);
     }
+    if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
     __syncthreads();
     en->ex.bar_init(Engine<ClusterExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
         CtaExec ex{ fthmc_dyn_smem };
         new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
     }
+    if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
     __syncthreads();
     en->ex.bar_init(Engine<CtaExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
