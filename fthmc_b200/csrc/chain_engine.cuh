@@ -1238,8 +1238,11 @@ struct Engine {
     FT_PHASE void ph_scatter(const LayerGeom g) {
         const double* PB = sm(oW);
         const int R = g.R, Cn = g.Cn;
-        for (int i = ex.tid(); i < V; i += ex.nt()) {
-            const int c = i / R, r = i - c * R;
+        // (column, row) of the sites this thread visits advance without divisions: i += nt  <=>  c += nt / R, r += nt % R
+        const int dcol = ex.nt() / R, drow = ex.nt() - dcol * R;
+        int c = ex.tid() / R, r = ex.tid() - c * R;
+        for (int i = ex.tid(); i < V; i += ex.nt(), c += dcol, r += drow) {
+            if (r >= R) { r -= R; ++c; }
             // the column left of a rank's first column is the passive column of the previous group: Pbar == 0 there
             const int cm = c == 0 ? Cn - 1 : c - 1, rm = r == 0 ? R - 1 : r - 1;
             const double pb = PB[i], pmc = (CL && c == 0) ? 0.0 : PB[cm * R + r], pmr = PB[c * R + rm];
