@@ -14,7 +14,9 @@
  *   - return value: 0 ok, >0 a cudaError_t, <0 an argument error (FTHMC_E_*); the message is kept in
  *     fthmc_last_error_string() (thread-local).  There is NO CPU fallback and no silent dispatch.
  *   - L0 and L1 must be multiples of 4 (the 4-periodic stripe masks, ipynb/field_transformation.py:175-248);
- *     the flow entry points keep one chain resident in one SM's shared memory (L0*L1 <= 1024 in fp64).
+ *     the resident-chain entry points keep one chain in one SM's shared memory (L0*L1 <= 1024 sites in fp64) or, for
+ *     larger lattices (L = 48 .. 128), in the distributed shared memory of one thread-block cluster of up to 16 CTAs;
+ *     beyond that they return FTHMC_E_LATTICE.
  */
 #ifndef FTHMC_B200_H
 #define FTHMC_B200_H
