@@ -40,6 +40,10 @@ SIGNATURES = {
                               c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
     "fthmc_ft_hmc_run": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_ull, c_ull, c_ull, c_int, c_int, c_int, c_dbl, c_dbl,
                                  c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
+    "fthmc_grad_workspace_bytes": (c_sz, [c_dp, c_int, c_int, c_int]),
+    "fthmc_ft_action_grad": (c_int, [c_dp, c_dp, c_dbl, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_sz, c_dp]),
+    "fthmc_grad_doubles": (c_int, []),
+    "fthmc_grad_unpack": (c_int, [c_dp, c_int, c_dp, c_dp]),
 }
 
 

@@ -446,3 +446,38 @@ def ft_run(param, flow, field=None, out=None):
         field = param.initializer()
     topo_history.clear()
     return _run_loop(param, flow, field, out, topo_history)
+
+
+# ------------------------------------------------------------------------------------------------
+# flow training: the gradient of the reverse-KL loss with respect to the CNN weights
+# ------------------------------------------------------------------------------------------------
+def ft_action_grad(param, flow, x, want_force=False):
+    """ft_action(x_b) for every chain and d/d(weights) of sum_b ft_action(x_b), the quantity the reference's reverse-KL
+    train_step back-propagates (ipynb/ft_hmc.py:253-295), in ONE launch: (action (B,), grad (n_layers, 955) float64 CPU
+    tensor in the parameter order of layer.plaq_coupling.net [, force (B,2,L0,L1)])."""
+    import numpy as np
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+        xd = _dev_in(x, dev, torch.float64)
+        if xd.dim() != 4:
+            raise _lib.FthmcError(-1, f"field must be (B,2,L0,L1), got {tuple(xd.shape)}")
+        B, _, L0, L1 = xd.shape
+        L = _lib.lib()
+        need = L.fthmc_grad_workspace_bytes(pf.handle, B, L0, L1)
+        key = ("grad", dev)
+        ws = _ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _ws[key] = ws
+        act = torch.empty(B, dtype=torch.float64, device=dev)
+        gd = L.fthmc_grad_doubles()
+        gc = torch.empty((pf.n_layers, gd), dtype=torch.float64, device=dev)
+        frc = torch.empty_like(xd) if want_force else None
+        _lib.check(L.fthmc_ft_action_grad(pf.handle, xd.data_ptr(), float(param.beta), act.data_ptr(), gc.data_ptr(), _ptr(frc),
+                                          B, L0, L1, ws.data_ptr(), ws.numel(), _stream()))
+        gch = np.ascontiguousarray(gc.cpu().numpy())
+    raw = np.zeros((pf.n_layers, 955), dtype=np.float64)
+    _lib.check(L.fthmc_grad_unpack(gch.ctypes.data, pf.n_layers, pf.mu.ctypes.data, raw.ctypes.data))
+    out = (_back(act, x), torch.from_numpy(raw))
+    return out + (_back(frc, x),) if want_force else out

@@ -203,7 +203,7 @@ template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
 // in-place activation of N of this thread's own values buf[index(e)], e = 0..N-1; dsave != nullptr: the
 // derivative goes to the same index of the global layer block.  Blocks of U elements: all loads, then U
 // independent chains, then all stores (a load after a store to the same array would serialise them).
-template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double* dsave, IndexFn index) {
+template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double* dsave, double* hsave, IndexFn index) {
     constexpr int U = 4;
     static_assert(N % U == 0, "element count must be a multiple of the block");
 #pragma unroll 1
@@ -216,6 +216,10 @@ template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double
             for (int j = 0; j < U; ++j) act_fwd_der_t<ACT>(z[j], h[j], d[j]);
 #pragma unroll
             for (int j = 0; j < U; ++j) { buf[idx[j]] = h[j]; dsave[idx[j]] = d[j]; }
+            if (hsave) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) hsave[idx[j]] = h[j];
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < U; ++j) act_fwd_t<ACT>(z[j], h[j]);
@@ -224,10 +228,10 @@ template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double
         }
     }
 }
-template <int N, class IndexFn> FT_HD void act_pass_any(int act, double* buf, double* dsave, IndexFn index) {
-    if (act == ACT_SILU) act_pass<ACT_SILU, N>(buf, dsave, index);
-    else if (act == ACT_LEAKY) act_pass<ACT_LEAKY, N>(buf, dsave, index);
-    else act_pass<ACT_RELU, N>(buf, dsave, index);
+template <int N, class IndexFn> FT_HD void act_pass_any(int act, double* buf, double* dsave, double* hsave, IndexFn index) {
+    if (act == ACT_SILU) act_pass<ACT_SILU, N>(buf, dsave, hsave, index);
+    else if (act == ACT_LEAKY) act_pass<ACT_LEAKY, N>(buf, dsave, hsave, index);
+    else act_pass<ACT_RELU, N>(buf, dsave, hsave, index);
 }
 
 struct alignas(16) dbl2 { double x, y; };
@@ -308,6 +312,7 @@ struct EngineParams {
     const double* wpack;   // global: nlayers * PACK_DOUBLES
     const int* lmu;        // global: per layer mu
     const int* loff;       // global: per layer off
+    int train;             // 1: the forward sweep also saves the activations h1, h2 and the adjoint accumulates weight gradients
 };
 
 // Shared-memory arena (doubles) of one rank; V = sites per rank.  Flow: X GR | CS UA OUT | A(8V) B(6V) C(6V) | W.
@@ -321,15 +326,19 @@ FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true, int nr = 1) {
 // Per-layer block of the per-CTA global workspace written by the forward sweep of ft_force and read
 // back (bulk copies) by the reverse sweep: act'(z1) [plane A], act'(z2) [plane B], cos/sin of the frozen
 // plaquettes [V], (s_1,s_2) of the active sites [2 V/4], pre-update active links [V/4].
-FT_HD size_t engine_layer_ws_doubles(int L0, int L1, int nr = 1) {
+// Training mode (weight gradients) appends the activations themselves: h1 [plane A], h2 [plane B].
+FT_HD size_t engine_layer_ws_doubles(int L0, int L1, int nr = 1, bool train = false) {
     size_t V = (size_t)L0 * L1 / nr;
-    return plane_a_doubles(V) + plane_b_doubles(V) + V + 3 * (V / 4);
+    return (train ? 2 : 1) * (plane_a_doubles(V) + plane_b_doubles(V)) + V + 3 * (V / 4);
 }
 // per-chain global workspace (doubles): momenta, x0, y0 (whole lattice), then for every rank nlayers layer blocks
-FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers, int nr = 1) {
+FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers, int nr = 1, bool train = false) {
     size_t V = (size_t)L0 * L1;
-    return 3 * 2 * V + (size_t)nr * nlayers * engine_layer_ws_doubles(L0, L1, nr);
+    return 3 * 2 * V + (size_t)nr * nlayers * engine_layer_ws_doubles(L0, L1, nr, train);
 }
+// weight-gradient accumulators of one warp for one layer, in the layout of the forward half of the packed weights
+// (conv1 [b][a][ci][o], S_q[o] in the conv1-bias slots, conv2 [ci][a][b][o], bias2, conv3 [ci][a][b][4], bias3)
+constexpr int GRAD_DOUBLES = OFF_W3T;
 
 template <class E>
 struct Engine {
@@ -343,6 +352,7 @@ struct Engine {
     int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
     double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
     size_t layStride;
+    double* gW;                                        // training: this CTA's gradient accumulators [warp][layer][GRAD_DOUBLES]
     int* iters_out;                                    // optional global: bisection iterations per layer
     // transaction barriers of the bulk (TMA) copies.  barcnt[b] counts completed uses: the k-th use of a barrier is
     // waited with parity k & 1.  Thread 0 advances a counter only after a block barrier that follows every thread's wait.
@@ -356,7 +366,8 @@ struct Engine {
         int o = 0;
         oX = o;  o += 2 * H * LP;
         oGR = o; o += 2 * H * LP;
-        layStride = engine_layer_ws_doubles(L0, L1, nr);
+        layStride = engine_layer_ws_doubles(L0, L1, nr, p.train != 0);
+        gW = nullptr;
         for (int b = 0; b < NBAR; ++b) barcnt[b] = 0;
         wsP = ws; wsX0 = ws + 2 * Vg; wsY0 = ws + 4 * Vg;
         wsLay = ws + 6 * (size_t)Vg + (size_t)rk * p.nlayers * layStride;
@@ -387,6 +398,8 @@ struct Engine {
     FT_HD double* wsCS(int l) const { return wsD2(l) + NH * (size_t)sB; }
     FT_HD double* wsSO(int l) const { return wsCS(l) + V; }
     FT_HD double* wsSV(int l) const { return wsSO(l) + 2 * VQ; }
+    FT_HD double* wsH1(int l) const { return wsSV(l) + VQ; }                 // training mode only
+    FT_HD double* wsH2(int l) const { return wsH1(l) + NH * (size_t)sA; }
 
     // ---- geometry ----
     FT_HD LayerGeom geom(int l) const {
@@ -589,10 +602,10 @@ struct Engine {
     }
 
     // h1 = act(conv1) on all columns -> A[o][c][r];  d1_save: act'(z1) to the global layer block
-    FT_HD void ph_conv1(const LayerGeom g, double* d1_save) {
-        if (fine_tasks()) ph_conv1_t<4>(g, d1_save); else ph_conv1_t<8>(g, d1_save);
+    FT_HD void ph_conv1(const LayerGeom g, double* d1_save, double* h1_save = nullptr) {
+        if (fine_tasks()) ph_conv1_t<4>(g, d1_save, h1_save); else ph_conv1_t<8>(g, d1_save, h1_save);
     }
-    template <int CH> FT_PHASE void ph_conv1_t(const LayerGeom g, double* d1_save) {
+    template <int CH> FT_PHASE void ph_conv1_t(const LayerGeom g, double* d1_save, double* h1_save) {
         const double* CS = sm(oCS); const double* W = sm(oW);
         double* A = sm(oA);
         const int T = g.G * g.R * (NH / CH), R = g.R, act = pr.act;
@@ -614,7 +627,7 @@ struct Engine {
             // activation pass as a partially unrolled loop over this thread's own 32 values (a fully
             // unrolled exp() per element overflows the instruction cache); element e -> channel e/4, column e%4
             const int i0 = CH * h * sA + 4 * gi * R + r, so = sA;
-            act_pass_any<4 * CH>(act, A, d1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
+            act_pass_any<4 * CH>(act, A, d1_save, h1_save, [=](int e) { return i0 + (e >> 2) * so + (e & 3) * R; });
 #ifdef FT_PROFILE
             ex.prof_add(PF_C1_ACT, ex.clock() - tp0);
 #endif
@@ -664,12 +677,12 @@ struct Engine {
     // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
     // tensor-core (DMMA) form of the two big convolutions: single-CTA chains whose stripe length is a multiple of 8
     FT_HD bool mma_ok() const { return !CL && (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
-    FT_HD void ph_conv2(const LayerGeom g, double* d2_save) {
+    FT_HD void ph_conv2(const LayerGeom g, double* d2_save, double* h2_save = nullptr) {
         if (mma_ok()) {
-            if (pr.act == ACT_SILU) ph_conv2_mma<ACT_SILU>(g, d2_save);
-            else if (pr.act == ACT_LEAKY) ph_conv2_mma<ACT_LEAKY>(g, d2_save);
-            else ph_conv2_mma<ACT_RELU>(g, d2_save);
-        } else if (fine_tasks()) ph_conv2_t<2>(g, d2_save);
+            if (pr.act == ACT_SILU) ph_conv2_mma<ACT_SILU>(g, d2_save, h2_save);
+            else if (pr.act == ACT_LEAKY) ph_conv2_mma<ACT_LEAKY>(g, d2_save, h2_save);
+            else ph_conv2_mma<ACT_RELU>(g, d2_save, h2_save);
+        } else if (fine_tasks()) ph_conv2_t<2>(g, d2_save);      // (the training mode requires the tensor-core path)
         else ph_conv2_t<4>(g, d2_save);
     }
 
@@ -678,7 +691,7 @@ struct Engine {
     // halves.  One warp task = 8 rows of one stripe group, all three output columns (three accumulator tiles in flight).
     // The weight fragments stay in registers for the whole phase; A fragments are one 64-bit shared-memory load per
     // lane per DMMA (conflict-free thanks to PLANE_PAD).  Same output layout as ph_conv2_t.
-    template <int ACT> FT_PHASE void ph_conv2_mma(const LayerGeom g, double* d2_save) {
+    template <int ACT> FT_PHASE void ph_conv2_mma(const LayerGeom g, double* d2_save, double* h2_save) {
         constexpr int NL = E::kLanes;
         const double* A = sm(oA); const double* W = sm(oW);
         double* B = sm(oB);
@@ -726,6 +739,10 @@ struct Engine {
                     for (int e = 0; e < 6; ++e) act_fwd_der_t<ACT>(z[e], h[e], d[e]);
 #pragma unroll
                     for (int e = 0; e < 6; ++e) { const int idx = i0 + (e & 1) * sB + (e >> 1) * R; B[idx] = h[e]; d2_save[idx] = d[e]; }
+                    if (h2_save) {
+#pragma unroll
+                        for (int e = 0; e < 6; ++e) h2_save[i0 + (e & 1) * sB + (e >> 1) * R] = h[e];
+                    }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 6; ++e) act_fwd_t<ACT>(z[e], h[e]);
@@ -801,7 +818,7 @@ struct Engine {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) st2(B + i0 + o * cs + k * R, acc[0][k][o], acc[1][k][o]);
             // element e -> (channel e/6, column (e/2)%3, row e%2)
-            act_pass_any<6 * CH>(act, B, d2_save, [=](int e) { return i0 + (e / 6) * cs + ((e >> 1) % 3) * R + (e & 1); });
+            act_pass_any<6 * CH>(act, B, d2_save, nullptr, [=](int e) { return i0 + (e / 6) * cs + ((e >> 1) % 3) * R + (e & 1); });
 #ifdef FT_PROFILE
             ex.prof_add(PF_C2_ACT, ex.clock() - tp0);
 #endif
@@ -876,9 +893,10 @@ struct Engine {
              wait_bar(BAR_W);
              ex.sync();
              advance_bar(BAR_W));
-        FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr); ex.sync());
+        const bool tr = save && pr.train;
+        FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr, tr ? wsH1(l) : nullptr); ex.sync());
         if constexpr (CL) { push_halo_h1(g); ex.sync(); }
-        FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr); ex.sync());
+        FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr, tr ? wsH2(l) : nullptr); ex.sync());
         FT_T(PF_CONV3F, lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
              tot = want_logJ ? ex.sum(lj) : 0.0;
              ex.sync());
@@ -1275,13 +1293,16 @@ struct Engine {
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
              ex.sync();
              advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
+        if (pr.train) ph_wgrad3(g, wsH2(l), gslice(l));                 // OUT = (s1bar, s2bar, tbar) is complete and intact
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
+        if (pr.train) ph_wgrad2(g, zbuf(l), wsH1(l), gslice(l));        // zbar2 complete; reads it only
         FT_T(PF_ISSUE, issue_so(l - 1));           // OUT is free again
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.sync();
              advance_bar(BAR_D1));
         FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
+        if (pr.train) ph_wgrad1(g, gslice(l));                          // zbar1 complete in A; reads A and CS only
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
              ex.sync();
              advance_bar(BAR_CS));
@@ -1321,8 +1342,10 @@ struct Engine {
         return s - lj;
     }
     // ft_force (ipynb/ft_hmc.py:240-249): GR <- d/dx [S(F(x)) - sum logJ]; X is preserved.
-    FT_HD void ft_force(double beta) {
-        flow_forward(false, true);
+    // want_logJ (training): the forward sweep also accumulates sum logJ and ft_action(x) = S(F(x)) - sum logJ is returned
+    FT_HD double ft_force(double beta, bool want_logJ = false) {
+        double lj = flow_forward(want_logJ, true);
+        if (want_logJ) lj = wilson_action(beta, pr.conv) - lj;          // ft_action(x) = S(F(x)) - sum logJ
         ex.proxy_fence();                 // the layer blocks just written are read back by bulk copies (async proxy)
         ex.sync();
         const int last = pr.nlayers - 1;
@@ -1334,6 +1357,137 @@ struct Engine {
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         FT_T(PF_ISSUE, issue_so(last));
         for (int l = last; l >= 0; --l) layer_adjoint(l);
+        return lj;
+    }
+
+    // =============================================================================================
+    // weight gradients (flow training, ipynb/ft_hmc.py:253-295: d/dweights of sum_b [S(F(x_b)) - sum logJ]), accumulated
+    // next to the input-gradient sweep.  Each is a GEMM with K = sites on the fp64 tensor path:
+    //     D[8 output channels o][8 columns] += A[o][4 consecutive rows of one plane column] * B[those 4 sites][columns]
+    // with the adjoint signal (OUT, zbar2, zbar1; shared memory) as A and the saved activations (h2, h1 from the layer
+    // block in L2 -- no shared memory is left for them; cos/sin planes) as B.  One accumulator tile per kernel tap.
+    // Every warp sums its share of the K chunks in registers and adds the result to ITS OWN slice of the CTA's gradient
+    // buffer (no atomics; the host-side reduction over (CTA, warp) slices is in a fixed order).
+    // =============================================================================================
+    FT_HD double* gslice(int l) const { return gW + ((size_t)ex.warp() * pr.nlayers + l) * GRAD_DOUBLES; }
+    FT_HD int wrapr(int r, int R) const { return r < 0 ? r + R : (r >= R ? r - R : r); }
+
+    // conv3: dW3[o][ci][a][b] = sum_t OUT[o][t] h2[ci][3g+b][r+a-1], db3[o] = sum_t OUT[o][t]   (t = active sites)
+    FT_PHASE void ph_wgrad3(const LayerGeom g, const double* h2g, double* gl) {
+        constexpr int NL = E::kLanes;
+        const double* OUT = sm(oOUT);
+        const int T = g.G * g.R, R = g.R, RQ = R >> 2;
+        double acc0[10][NL], acc1[10][NL];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) FT_LANES(ln, ls) { acc0[i][ls] = 0.0; acc1[i][ls] = 0.0; }
+        for (int ch = ex.warp(); ch < g.G * RQ; ch += ex.nwarps()) {
+            const int gi = ch / RQ, r0 = 4 * (ch - gi * RQ);
+            double av[NL], one[NL];
+            FT_LANES(ln, ls) {
+                const int o = ln >> 2, sI = ln & 3;
+                av[ls] = o < NOUT ? OUT[o * T + gi * R + r0 + sI] : 0.0;
+                one[ls] = (ln >> 2) == 0 ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int a = tap / 3, b = tap - 3 * a;
+                double bv[NL];
+                FT_LANES(ln, ls) { const int sI = ln & 3, ci = ln >> 2; bv[ls] = h2g[ci * sB + (3 * gi + b) * R + wrapr(r0 + sI + a - 1, R)]; }
+                ex.mma884(acc0[tap], acc1[tap], av, bv);
+            }
+            ex.mma884(acc0[9], acc1[9], av, one);
+        }
+        FT_LANES(ln, ls) {
+            const int o = ln >> 2, j = ln & 3;
+            if (o < NOUT) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    gl[OFF_W3F + ((2 * j) * 9 + tap) * 4 + o] += acc0[tap][ls];
+                    gl[OFF_W3F + ((2 * j + 1) * 9 + tap) * 4 + o] += acc1[tap][ls];
+                }
+                if (j == 0) gl[OFF_B3 + o] += acc0[9][ls];
+            }
+        }
+    }
+
+    // conv2: dW2[o][ci][a][b] = sum z2bar[o][3g+k][r] h1[ci][4g-1+k+b-1][r+a-1], db2[o] = sum z2bar[o]
+    FT_PHASE void ph_wgrad2(const LayerGeom g, int oZ, const double* h1g, double* gl) {
+        constexpr int NL = E::kLanes;
+        const double* Z = sm(oZ);
+        const int R = g.R, Cn = g.Cn, RQ = R >> 2;
+        double acc0[10][NL], acc1[10][NL];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) FT_LANES(ln, ls) { acc0[i][ls] = 0.0; acc1[i][ls] = 0.0; }
+        for (int ch = ex.warp(); ch < g.G * 3 * RQ; ch += ex.nwarps()) {
+            const int gi = ch / (3 * RQ), rem = ch - gi * 3 * RQ, k = rem / RQ, r0 = 4 * (rem - k * RQ);
+            double av[NL], one[NL];
+            FT_LANES(ln, ls) {
+                const int o = ln >> 2, sI = ln & 3;
+                av[ls] = Z[o * sB + (3 * gi + k) * R + r0 + sI];
+                one[ls] = (ln >> 2) == 0 ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int a = tap / 3, b = tap - 3 * a;
+                int c = 4 * gi + k + b - 2; c = c < 0 ? c + Cn : (c >= Cn ? c - Cn : c);
+                double bv[NL];
+                FT_LANES(ln, ls) { const int sI = ln & 3, ci = ln >> 2; bv[ls] = h1g[ci * sA + c * R + wrapr(r0 + sI + a - 1, R)]; }
+                ex.mma884(acc0[tap], acc1[tap], av, bv);
+            }
+            ex.mma884(acc0[9], acc1[9], av, one);
+        }
+        FT_LANES(ln, ls) {
+            const int o = ln >> 2, j = ln & 3;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                gl[OFF_W2F + ((2 * j) * 9 + tap) * NH + o] += acc0[tap][ls];
+                gl[OFF_W2F + ((2 * j + 1) * 9 + tap) * NH + o] += acc1[tap][ls];
+            }
+            if (j == 0) gl[OFF_B2 + o] += acc0[9][ls];
+        }
+    }
+
+    // conv1: output column class q sees the frozen column k through kernel column b = k + 2 - q:
+    //   dW1[o][ci][a][b] += sum_{g,r} z1bar[o][4g+q][r] (cos,sin)[ci][2g+k][r+a-1]      (one tile per b, columns n = 2a + ci)
+    // and the column-class sums S_q[o] = sum z1bar[o][class q] (tile columns 6, 7: ones for k = 0, 1), from which the
+    // host derives db1 and the gradient through the constant (cos 0, sin 0) = (1, 0) inputs of the non-frozen sites.
+    FT_PHASE void ph_wgrad1(const LayerGeom g, double* gl) {
+        constexpr int NL = E::kLanes;
+        const double* A = sm(oA); const double* CS = sm(oCS);
+        const int R = g.R, RQ = R >> 2;
+        wait_bar(BAR_CS);                                    // the frozen cos/sin of this layer have landed
+        double acc0[3][NL], acc1[3][NL];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) FT_LANES(ln, ls) { acc0[i][ls] = 0.0; acc1[i][ls] = 0.0; }
+        for (int ch = ex.warp(); ch < 2 * g.G * RQ; ch += ex.nwarps()) {
+            const int k = ch / (g.G * RQ), rem = ch - k * g.G * RQ, gi = rem / RQ, r0 = 4 * (rem - gi * RQ);
+            double bv[NL];
+            FT_LANES(ln, ls) {
+                const int sI = ln & 3, n = ln >> 2;
+                if (n < 6) bv[ls] = CS[(n & 1) * (V / 2) + (2 * gi + k) * R + wrapr(r0 + sI + (n >> 1) - 1, R)];
+                else bv[ls] = (n - 6) == k ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int q = k + 2 - b;
+                double av[NL];
+                FT_LANES(ln, ls) { const int o = ln >> 2, sI = ln & 3; av[ls] = A[o * sA + (4 * gi + q) * R + r0 + sI]; }
+                ex.mma884(acc0[b], acc1[b], av, bv);
+            }
+        }
+        FT_LANES(ln, ls) {
+            const int o = ln >> 2, j = ln & 3;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                if (j < 3) {                                 // columns n = 2j, 2j+1  ->  kernel row a = j, ci = 0, 1
+                    gl[OFF_W1F + ((b * 3 + j) * 2 + 0) * NH + o] += acc0[b][ls];
+                    gl[OFF_W1F + ((b * 3 + j) * 2 + 1) * NH + o] += acc1[b][ls];
+                } else if (b != 1) {                         // columns 6, 7: class sums; b = 0 -> S_2, S_3;  b = 2 -> S_0, S_1
+                    gl[OFF_B1 + (2 - b) * NH + o] += acc0[b][ls];
+                    gl[OFF_B1 + (3 - b) * NH + o] += acc1[b][ls];
+                }
+            }
+        }
     }
 
     // elementwise helpers on the link field (skip the pitch padding)

@@ -14,6 +14,7 @@ enum ChainMode {
     MODE_FT_HMC = 5,       // ft_hmc          ipynb/ft_hmc.py:420
     MODE_HMC = 6,          // hmc             hmc_2dU1.py:144
     MODE_LEAPFROG = 7,     // leapfrog        hmc_2dU1.py:132
+    MODE_FT_GRAD = 8,      // d/dweights of sum_b ft_action(x_b): the reverse-KL training gradient, ipynb/ft_hmc.py:253-295
 };
 
 struct ChainArgs {
@@ -33,6 +34,8 @@ struct ChainArgs {
     int* iters;               // (B,nlayers) or null (bisection iteration counts)
     double* expmdH; int* acc; double* plaq; double* topo; double* h0; double* h1;   // (B) each, trajectory modes
     uint64_t seed, traj, chain0;
+    double* gbuf;             // MODE_FT_GRAD: gradient accumulators, one slice of gbuf_stride doubles per CTA
+    size_t gbuf_stride;
     double* ws;               // per-CTA workspace base
     size_t ws_stride;         // doubles per CTA
 };
@@ -74,6 +77,13 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
         en.load_field(en.oX, fin); ex.sync();
         en.ft_force(a.beta);
         en.store_field(fout, en.oGR);
+        ex.sync();
+    } break;
+    case MODE_FT_GRAD: {
+        en.load_field(en.oX, fin); ex.sync();
+        double s = en.ft_force(a.beta, true);                // weight gradients accumulate into en.gW along the adjoint sweep
+        if (a.s_out && ex.tid() == 0) a.s_out[b] = s;
+        if (fout) en.store_field(fout, en.oGR);              // optional: the force on the input field
         ex.sync();
     } break;
     case MODE_FT_LEAPFROG:

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
     if (threadIdx.x == 0) {
         ClusterExec ex; ex.red = fthmc_dyn_smem;
         new (en) Engine<ClusterExec>(ex, a.pr, a.ws + (size_t)cid * a.ws_stride);
+        en->gW = nullptr;                                    // (the training mode runs on the single-CTA path)
     }
     if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
     __syncthreads();
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
     if (threadIdx.x == 0) {
         CtaExec ex{ fthmc_dyn_smem };
         new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
+        en->gW = a.gbuf ? a.gbuf + (size_t)blockIdx.x * a.gbuf_stride : nullptr;
     }
     if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
     __syncthreads();
@@ -467,6 +469,15 @@ __global__ void __launch_bounds__(256) k_regularize(const T* __restrict__ in, T*
     for (long long i = nv * N + i0; i < n; i += stride) out[i] = regularize_t(in[i]);
 }
 
+// sum of the per-(CTA, warp) gradient slices in a fixed order: out[i] = sum_s gbuf[s * n + i]
+__global__ void __launch_bounds__(256) k_grad_reduce(const double* __restrict__ gbuf, int nslices, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    for (int sI = 0; sI < nslices; ++sI) t += gbuf[(size_t)sI * n + i];
+    out[i] = t;
+}
+
 // fp64 FMA-pipe peak probe (roofline denominator for the resident-chain kernel; MEASURED_PEAKS.json has no
 // fp64 entry).  16 independent DFMA chains per thread; 2*16*iters flop per thread.
 __global__ void __launch_bounds__(256) k_dfma_probe(double* __restrict__ out, int iters) {
@@ -619,15 +630,25 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
         a.pr.nlayers = 0; a.pr.act = 0; a.pr.conv = 0; a.pr.inv_tol = 0; a.pr.inv_max_iter = 0;
         a.pr.wpack = nullptr; a.pr.lmu = nullptr; a.pr.loff = nullptr;
     }
+    const bool train = a.mode == MODE_FT_GRAD;
+    a.pr.train = train ? 1 : 0;
+    if (train && (nr != 1 || (L0 & 7) || (L1 & 7)))
+        return fail(FTHMC_E_LATTICE, "the weight-gradient path needs L0, L1 multiples of 8 and a lattice that fits one SM (L0*L1 <= 1024)");
     int res = chain_resident(L0, L1, has_flow, nr);
     if (res < 1) return fail(FTHMC_E_LATTICE, "the device cannot co-schedule a thread-block cluster of the size this lattice needs");
     const int chains = a.B < res ? a.B : res;
-    a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers, nr);
-    const size_t need = (size_t)chains * a.ws_stride * sizeof(double);
-    if (!ws || ws_bytes < need) return fail(FTHMC_E_WORKSPACE, "workspace null or smaller than fthmc_workspace_bytes()");
+    a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers, nr, train);
+    const int nt = chain_threads(L0, L1, has_flow, nr);
+    size_t need = (size_t)chains * a.ws_stride * sizeof(double);
+    if (train) {            // gradient accumulators behind the chain workspaces: [CTA][warp][layer][GRAD_DOUBLES]
+        a.gbuf_stride = (size_t)(nt / 32) * a.pr.nlayers * GRAD_DOUBLES;
+        a.gbuf = (double*)ws + (size_t)chains * a.ws_stride;
+        need += (size_t)chains * a.gbuf_stride * sizeof(double);
+    }
+    if (!ws || ws_bytes < need) return fail(FTHMC_E_WORKSPACE, "workspace null or smaller than fthmc_workspace_bytes() / fthmc_grad_workspace_bytes()");
     if (((uintptr_t)ws) & 15) return fail(FTHMC_E_WORKSPACE, "workspace must be 16-byte aligned");
     a.ws = (double*)ws;
-    const int nt = chain_threads(L0, L1, has_flow, nr);
+    if (train) CK(cudaMemsetAsync(a.gbuf, 0, (size_t)chains * a.gbuf_stride * sizeof(double), (cudaStream_t)stream));
     const size_t smem = chain_smem_bytes(L0, L1, has_flow, nr);
     if (nr == 1) {
         k_chain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
@@ -880,4 +901,40 @@ extern "C" int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, doubl
     if (!flow) return fail(FTHMC_E_ARG, "null flow");
     return traj_common(flow, MODE_FT_HMC, field_in, field_out, p_in, u_in, seed, traj0, chain0, B, L0, L1, beta, dt, nstep,
                        dH, exp_mdH, acc, plaq, topo, nullptr, nullptr, ws, ws_bytes, stream, ntraj);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: flow-training gradient
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t fthmc_grad_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
+    if (!flow || B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
+    DevInfo& d = devinfo();
+    long long g = (long long)(d.sm > 0 ? d.sm : 148) * 32;
+    if (B < g) g = B;
+    return (size_t)g * (engine_ws_doubles(L0, L1, flow->n_layers, 1, true) + (size_t)(FT_THREADS / 32) * flow->n_layers * GRAD_DOUBLES)
+               * sizeof(double) + 256;
+}
+
+extern "C" int fthmc_ft_action_grad(fthmc_flow_t flow, const double* x, double beta, double* action_out, double* grad_canon, double* force_out,
+                                    int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x || !grad_canon) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FT_GRAD; a.B = B; a.field_in = x; a.field_out = force_out; a.s_out = action_out; a.beta = beta;
+    int rc = launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+    if (rc) return rc;
+    const int n = flow->n_layers * GRAD_DOUBLES;
+    const int chains = (int)(((char*)a.gbuf - (char*)a.ws) / (a.ws_stride * sizeof(double)));
+    const int nslices = chains * (int)(a.gbuf_stride / ((size_t)flow->n_layers * GRAD_DOUBLES));
+    k_grad_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.gbuf, nslices, n, grad_canon);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fthmc_grad_doubles(void) { return GRAD_DOUBLES; }
+
+extern "C" int fthmc_grad_unpack(const double* grad_canon_host, int n_layers, const int* mu_host, double* raw_host) {
+    if (!grad_canon_host || !mu_host || !raw_host || n_layers <= 0) return fail(FTHMC_E_ARG, "null pointer or n_layers <= 0");
+    for (int l = 0; l < n_layers; ++l)
+        unpack_grad_layer(grad_canon_host + (size_t)l * GRAD_DOUBLES, mu_host[l], raw_host + (size_t)l * RAW_DOUBLES);
+    return 0;
 }

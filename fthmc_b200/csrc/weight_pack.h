@@ -54,4 +54,38 @@ inline void pack_layer(const double* raw, int mu, double* out) {
         out[OFF_W1T + ((o * 3 + a) * 3 + b) * 2 + ci] = W1(o, ci, a, b);
 }
 
+// Adjoint of the forward half of pack_layer: canonical gradient block (GRAD_DOUBLES doubles: conv1 [b][a][ci][o], the
+// column-class sums S_q[o] in the conv1-bias slots, conv2 [ci][a][b][o], bias2, conv3 [ci][a][b][4], bias3) -> gradient
+// with respect to the raw parameters in the reference's order (955 doubles).  The packed conv1 bias of class q is
+// b1[o] + sum_{b: class(q+b-1) not frozen} sum_a W1[o][0][a][b], hence db1[o] = sum_q S_q[o] and every W1[o][0][a][b]
+// collects S_q[o] of the classes q whose kernel column b looks at a non-frozen column.
+inline void unpack_grad_layer(const double* cg, int mu, double* raw) {
+    double* w1 = raw;
+    double* b1 = w1 + 144;
+    double* w2 = b1 + 8;
+    double* b2 = w2 + 576;
+    double* w3 = b2 + 8;
+    double* b3 = w3 + 216;
+    for (int i = 0; i < RAW_DOUBLES; ++i) raw[i] = 0.0;
+    auto I1 = [&](int o, int ci, int a, int b) { return mu == 0 ? ((o * 2 + ci) * 3 + a) * 3 + b : ((o * 2 + ci) * 3 + b) * 3 + a; };
+    auto I2 = [&](int o, int ci, int a, int b) { return mu == 0 ? ((o * 8 + ci) * 3 + a) * 3 + b : ((o * 8 + ci) * 3 + b) * 3 + a; };
+    for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) for (int ci = 0; ci < 2; ++ci) for (int o = 0; o < 8; ++o)
+        w1[I1(o, ci, a, b)] += cg[OFF_W1F + ((b * 3 + a) * 2 + ci) * 8 + o];
+    for (int q = 0; q < 4; ++q) for (int o = 0; o < 8; ++o) {
+        const double sq = cg[OFF_B1 + q * 8 + o];
+        b1[o] += sq;
+        for (int b = 0; b < 3; ++b) {
+            int cls = ((q + b - 1) % 4 + 4) % 4;
+            if (cls == 1 || cls == 2) continue;
+            for (int a = 0; a < 3; ++a) w1[I1(o, 0, a, b)] += sq;
+        }
+    }
+    for (int ci = 0; ci < 8; ++ci) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int o = 0; o < 8; ++o)
+        w2[I2(o, ci, a, b)] += cg[OFF_W2F + ((ci * 3 + a) * 3 + b) * 8 + o];
+    for (int o = 0; o < 8; ++o) b2[o] += cg[OFF_B2 + o];
+    for (int ci = 0; ci < 8; ++ci) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int o = 0; o < 3; ++o)
+        w3[I2(o, ci, a, b)] += cg[OFF_W3F + ((ci * 3 + a) * 3 + b) * 4 + o];
+    for (int o = 0; o < 3; ++o) b3[o] += cg[OFF_B3 + o];
+}
+
 }  // namespace fthmc

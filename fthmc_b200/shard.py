@@ -61,3 +61,19 @@ class Observables:
             raise ValueError("no chains in the observable sums")
         return Observables(plaq=s[0] / n, Q=s[1] / n, Q2=s[2] / n, acc_rate=s[3] / n, mean_dH=s[4] / n,
                            mean_exp_mdH=s[5] / n, count=int(round(n)))
+
+
+def allreduce_gradient(grad, sums=None, group=None):
+    """Sum the flow-training gradient (n_layers, 955) and an optional small vector of loss terms over all ranks
+    (BASELINE config 5: NCCL all-reduce of the flow-training gradient).  Host tensors are staged through the device
+    when the process group is NCCL.  A single process returns its inputs unchanged."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return grad, sums
+    nccl = dist.get_backend(group) == "nccl"
+    flat = torch.cat([grad.reshape(-1).double(), sums.reshape(-1).double() if sums is not None else grad.new_zeros(0)])
+    buf = flat.cuda() if nccl and not flat.is_cuda else flat
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    buf = buf.to(grad.device)
+    g = buf[:grad.numel()].reshape(grad.shape)
+    return g, (buf[grad.numel():].reshape(sums.shape) if sums is not None else None)

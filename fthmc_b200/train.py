@@ -1,0 +1,67 @@
+"""Reverse-KL flow training on top of the weight-gradient kernel (ipynb/ft_hmc.py:253-346, fthmc/train.py:162-228).
+
+The reference's train_step draws a batch from the uniform prior, flows it, forms loss = mean(logq - logp) and calls
+loss.backward() / optimizer.step().  With logq = log prior - sum logJ and logp = -S the loss is mean_b ft_action(xi_b) +
+const, so its gradient is (1/B) d/dweights sum_b ft_action(xi_b): one launch of fthmc_ft_action_grad.  The weights live in
+ONE (n_layers, 955) tensor in the reference's parameter order; the optimizer is torch's (host side, 23k parameters).
+With several GPUs every rank draws its own prior batch, the gradient (and the loss terms) are all-reduced over NCCL
+(shard.allreduce_gradient) and every rank takes the same optimizer step."""
+import math
+
+import numpy as np
+import torch
+
+from . import shard
+from .api import ft_action_grad
+from .flow import PackedFlow
+
+
+class FlowTrainer:
+    def __init__(self, raw_weights, lattice, beta, lr=1e-4, activation="silu", convention=0, seed=None):
+        self.raw = torch.nn.Parameter(torch.as_tensor(np.asarray(raw_weights), dtype=torch.float64).clone())
+        self.lattice, self.beta = tuple(lattice), float(beta)
+        self.activation, self.convention = activation, convention
+        self.opt = torch.optim.Adam([self.raw], lr=lr)           # base_lr = 1e-4, ipynb/ft_hmc.py:316-317
+        self.gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        self.history = {"loss": [], "dkl": [], "ess": []}
+        self._pf = None
+
+    # ---- model pieces -------------------------------------------------------------------------------
+    def packed(self):
+        if self._pf is None:
+            self._pf = PackedFlow(self.raw.detach().numpy(), activation=self.activation, convention=self.convention)
+        return self._pf
+
+    def sample_prior(self, batch_size):
+        """MultivariateUniform(0, 2pi).sample_n (ipynb/ft_hmc.py:304)."""
+        shape = (batch_size, 2) + self.lattice
+        return torch.rand(shape, dtype=torch.float64, generator=self.gen) * (2 * math.pi)
+
+    def log_prior(self):
+        return -2 * self.lattice[0] * self.lattice[1] * math.log(2 * math.pi)
+
+    # ---- one optimizer step -------------------------------------------------------------------------
+    def train_step(self, batch_size, xi=None, group=None):
+        """train_step(model, action, optimizer, metrics, batch_size, param) (ipynb/ft_hmc.py:253) without its force-norm
+        option: loss = dkl = mean(logq - logp) with logq = log prior - sum logJ, logp = -S, i.e. mean ft_action + log prior.
+        Returns the metrics of this step (also appended to self.history)."""
+        class _P:                                   # ft_action_grad reads only beta
+            beta = self.beta
+        if xi is None:
+            xi = self.sample_prior(batch_size)
+        act, grad = ft_action_grad(_P, self.packed(), xi.cuda())
+        act = act.cpu()
+        sums = torch.stack([act.sum(), torch.tensor(float(act.numel()), dtype=torch.float64)])
+        grad, sums = shard.allreduce_gradient(grad, sums, group=group)      # all ranks: same gradient, same step
+        nb = float(sums[1])
+        dkl = float(sums[0]) / nb + self.log_prior()
+        self.opt.zero_grad()
+        self.raw.grad = (grad / nb).to(torch.float64)
+        self.opt.step()
+        self._pf = None                              # weights changed: re-pack lazily
+        logw = -(act + self.log_prior())             # logp - logq of this rank's batch
+        ess = float(torch.exp(2 * torch.logsumexp(logw, 0) - torch.logsumexp(2 * logw, 0)) / act.numel())   # compute_ess
+        m = {"loss": dkl, "dkl": dkl, "ess": ess}
+        for k, v in m.items():
+            self.history[k].append(v)
+        return m

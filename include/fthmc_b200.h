@@ -125,6 +125,20 @@ int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, double* field_ou
                      double* dH, double* exp_mdH, int* acc, double* plaq, double* topo,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---- flow training gradient ---------------------------------------------------------------------------- */
+/* The reverse-KL training step (train_step, ipynb/ft_hmc.py:253-295; fthmc/train.py:162-228) minimises
+ * mean_b [logq - logp] = mean_b ft_action(xi_b) + const over prior samples xi_b, and gets d/dweights from loss.backward().
+ * fthmc_ft_action_grad computes action_out[b] = ft_action(x_b) and the gradient of sum_b ft_action(x_b) with respect to
+ * the CNN weights of every layer in ONE launch: the input-gradient sweep of ft_force extended by the weight-gradient
+ * GEMMs (fp64 tensor path).  grad_canon (device, n_layers x fthmc_grad_doubles()) is in the kernels' packed layout;
+ * fthmc_grad_unpack (host) converts it to the reference's parameter order (n_layers x 955, the layout of raw_host in
+ * fthmc_flow_pack).  force_out (B,2,L0,L1) optional: d/dx of the same sum.  Needs L0, L1 multiples of 8, L0*L1 <= 1024. */
+size_t fthmc_grad_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1);
+int fthmc_ft_action_grad(fthmc_flow_t flow, const double* x, double beta, double* action_out, double* grad_canon, double* force_out,
+                         int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream);
+int fthmc_grad_doubles(void);
+int fthmc_grad_unpack(const double* grad_canon_host, int n_layers, const int* mu_host, double* raw_host);
+
 /* diagnostic: launch `blocks` x 256 threads of pure fp64 FMA chains (2*16*iters flop per thread); *flop_out (host)
  * receives the flop count.  Used by bench.py to measure the fp64 roofline denominator on the device. */
 int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);

@@ -506,3 +506,24 @@ def ft_force_adjoint(beta: float, flow: Flow, fld: torch.Tensor) -> torch.Tensor
         x1 = g[:, 1] - Pbar + torch.roll(Pbar, 1, 1)
         g = torch.stack((x0, x1), dim=1)
     return g
+
+
+def ft_action_weight_grad(beta: float, flow: Flow, fld: torch.Tensor):
+    """The gradient the reference's reverse-KL train_step back-propagates (ipynb/ft_hmc.py:253-295: loss = mean(logq - logp)
+    = mean_b ft_action(xi_b) + const): d/d(weights) of sum_b ft_action(x_b) by torch.autograd, flattened per layer in the
+    parameter order of layer.plaq_coupling.net (conv0.weight, conv0.bias, conv1.weight, ...): (n_layers, 955).
+    Also returns ft_action (B,)."""
+    leaves = []
+    layers = []
+    for lw in flow.layers:
+        w = [t.detach().clone().requires_grad_(True) for t in lw.w]
+        b = [t.detach().clone().requires_grad_(True) for t in lw.b]
+        leaves.append((w, b))
+        layers.append(LayerWeights(w=w, b=b, mu=lw.mu, off=lw.off))
+    f2 = Flow(layers=layers, activation=flow.activation, convention=flow.convention)
+    act = ft_action(beta, f2, fld.detach())
+    flat = [t for w, b in leaves for pair in zip(w, b) for t in pair]
+    grads = torch.autograd.grad(torch.sum(act), flat)
+    per = len(flat) // len(flow.layers)
+    rows = [torch.cat([g.reshape(-1) for g in grads[i * per:(i + 1) * per]]) for i in range(len(flow.layers))]
+    return act.detach(), torch.stack(rows)

@@ -76,6 +76,31 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
 }
 
 
+// Training gradient (MODE_FT_GRAD): action (B) and d/d(raw weights) of sum_b ft_action(x_b), (nlayers, 955).
+// Needs the tensor-core code path (FT_EMUL_MMA) and L0, L1 multiples of 8.
+extern "C" int emul_grad(int B, int L0, int L1, int nlayers, const double* raw, const int* mu, const int* off,
+                         int act, int conv, double beta, const double* field_in, double* action_out, double* grad_raw, double* force_out) {
+    using namespace fthmc;
+    if (L0 % 8 || L1 % 8 || nlayers <= 0) return -1;
+    std::vector<double> pack((size_t)nlayers * PACK_DOUBLES);
+    for (int l = 0; l < nlayers; ++l) pack_layer(raw + (size_t)l * RAW_DOUBLES, mu[l], pack.data() + (size_t)l * PACK_DOUBLES);
+    std::vector<double> smem(engine_smem_doubles(L0, L1, true) + 8), ws(engine_ws_doubles(L0, L1, nlayers, 1, true) + 8);
+    std::vector<double> gbuf((size_t)nlayers * GRAD_DOUBLES, 0.0);
+    ChainArgs a{};
+    a.mode = MODE_FT_GRAD; a.B = B; a.ntraj = 1;
+    a.pr.L0 = L0; a.pr.L1 = L1; a.pr.nlayers = nlayers; a.pr.act = act; a.pr.conv = conv;
+    a.pr.inv_tol = 1e-6; a.pr.inv_max_iter = 1000; a.pr.wpack = pack.data(); a.pr.lmu = mu; a.pr.loff = off; a.pr.train = 1;
+    a.beta = beta; a.field_in = field_in; a.field_out = force_out; a.s_out = action_out;
+    SerialExec ex{ smem.data() };
+    if (!ex.use_mma()) return -3;
+    Engine<SerialExec> en(ex, a.pr, ws.data());
+    en.gW = gbuf.data();
+    en.load_geom_table();
+    for (int b = 0; b < B; ++b) run_chain(en, a, b);
+    for (int l = 0; l < nlayers; ++l) unpack_grad_layer(gbuf.data() + (size_t)l * GRAD_DOUBLES, mu[l], grad_raw + (size_t)l * RAW_DOUBLES);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Cluster mode: nr host threads stand in for the nr CTAs of a thread-block cluster (one "thread" per
 // CTA), std::barrier for the cluster barrier, plain pointers into the other ranks' arenas for

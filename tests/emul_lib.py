@@ -33,6 +33,7 @@ def lib():
         _lib = ctypes.CDLL(build())
         _lib.emul_run.restype = ctypes.c_int
         _lib.emul_run_cluster.restype = ctypes.c_int
+        _lib.emul_grad.restype = ctypes.c_int
     return _lib
 
 
@@ -67,3 +68,22 @@ def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, 
     lib().emul_set_ntraj(1)
     assert rc == 0, rc
     return out
+
+
+def grad(raw_weights, field, *, beta=1.0, act="silu", conv=0, mu=None, off=None):
+    """MODE_FT_GRAD on the CPU build: ft_action (B,), d/d(raw weights) of its sum (n_layers, 955), force (B,2,L0,L1)."""
+    os.environ["FT_EMUL_MMA"] = "1"
+    field = np.ascontiguousarray(field, dtype=np.float64)
+    B, _, L0, L1 = field.shape
+    raw = np.ascontiguousarray(raw_weights, dtype=np.float64)
+    n = raw.shape[0]
+    mu = np.array([i % 2 for i in range(n)] if mu is None else mu, dtype=np.int32)
+    off = np.array([(i // 2) % 4 for i in range(n)] if off is None else off, dtype=np.int32)
+    action, g, force = np.zeros(B), np.zeros((n, 955)), np.zeros_like(field)
+    try:
+        rc = lib().emul_grad(B, L0, L1, n, _p(raw), _p(mu, ctypes.c_int), _p(off, ctypes.c_int), ACTS[act], conv,
+                             ctypes.c_double(beta), _p(field), _p(action), _p(g), _p(force))
+    finally:
+        os.environ.pop("FT_EMUL_MMA", None)
+    assert rc == 0, rc
+    return dict(action=action, grad=g, force=force)

@@ -192,3 +192,25 @@ def test_run_loops_resident_chain(golden, nranks):
         r = E.run("ft_hmc", g["weights"], cur, p=p[t][None], u=u[t:t + 1], nranks=nranks, **kw)
         assert r["s"][0] == o["s"][t] and r["acc"][0] == o["acc"][t]
         cur = r["field"]
+
+
+@pytest.mark.parametrize("shape,act", [((2, 8, 8), "silu"), ((1, 8, 16), "silu"), ((1, 16, 8), "leaky_relu")])
+def test_weight_gradient_matches_autograd(shape, act):
+    """MODE_FT_GRAD (the flow-training gradient: input-gradient sweep + weight-gradient GEMMs, unpacked through the
+    adjoint of the weight packing) against torch.autograd on the oracle, both mask orientations, constant-input terms
+    of conv1 included."""
+    import torch
+    from oracle import fthmc_oracle as O
+    B, L0, L1 = shape
+    flow = O.random_flow(n_layers=6, seed=B + L0, activation=act, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()])
+                                    for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    torch.manual_seed(3)
+    x = torch.empty(B, 2, L0, L1).uniform_(0, 2 * np.pi)
+    a_ref, g_ref = O.ft_action_weight_grad(2.5, flow, x)
+    o = E.grad(raw, x.numpy(), beta=2.5, act=act)
+    assert relerr(o["action"], a_ref.numpy()) < 1e-12
+    assert relerr(o["force"], O.ft_force(2.5, flow, x).numpy()) < 1e-10
+    g = g_ref.numpy()
+    for l in range(g.shape[0]):
+        assert relerr(o["grad"][l], g[l]) < 1e-9, l

@@ -403,6 +403,56 @@ def test_checkpoint_load_and_lattice_transfer(golden, tmp_path):
     assert float(torch.max(torch.abs(torch.remainder(xi - x + np.pi, 2 * np.pi) - np.pi))) < 5e-5 and abs(float(lj + lji)) < 1e-2
 
 
+# ---------------------------------------------------------------- flow training gradient
+@pytest.mark.parametrize("L,layers,B", [(8, 6, 5), (16, 8, 3), (32, 24, 2)])
+def test_weight_gradient_vs_autograd(L, layers, B):
+    """fthmc_ft_action_grad (weight-gradient GEMMs on the tensor path + host-side unpacking) against torch.autograd on
+    the oracle: the gradient the reference's reverse-KL train_step back-propagates."""
+    flow = O.random_flow(n_layers=layers, seed=L, scale=1.5 if layers < 24 else 1.0)
+    pf = ft.PackedFlow(_raw_of(flow))
+    gen = torch.Generator().manual_seed(2 * L)
+    x = torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 * np.pi
+    P = ft.Param(beta=3.0, lat=(L, L))
+    a_ref, g_ref = O.ft_action_weight_grad(3.0, flow, x)
+    act, g, frc = ft.ft_action_grad(P, pf, x, want_force=True)
+    assert relerr(act.numpy(), a_ref.numpy()) < REL
+    assert relerr(frc.numpy(), O.ft_force(3.0, flow, x).numpy()) < REL
+    for l in range(layers):
+        assert relerr(g[l].numpy(), g_ref[l].numpy()) < 1e-9, l
+    # more chains than resident CTAs: the per-CTA accumulators add up over the persistent loop
+    xb = torch.cat([x] * 80)[:200] if L == 8 else x
+    if L == 8:
+        act2, g2 = ft.ft_action_grad(P, pf, xb)
+        reps = torch.tensor([(200 - i + B - 1) // B for i in range(B)], dtype=torch.float64)      # copies of each chain
+        a3, g3 = O.ft_action_weight_grad(3.0, flow, x)
+        want = sum(float(reps[i]) * O.ft_action_weight_grad(3.0, flow, x[i:i + 1])[1] for i in range(B))
+        assert relerr(g2.numpy(), want.numpy()) < 1e-9
+
+
+def test_train_step_follows_autograd_adam():
+    """FlowTrainer.train_step == the reference's step (reverse-KL loss, loss.backward(), Adam) done with autograd on the
+    oracle, for the same prior batch; a few steps reduce the loss."""
+    L, layers = 8, 4
+    raw0 = ft.default_init_raw(layers, 11)
+    tr = ft.FlowTrainer(raw0, (L, L), beta=2.0, lr=1e-3, seed=5)
+    xi = tr.sample_prior(16)
+    # autograd twin
+    flow = oracle_flow_from_golden(dict(weights=raw0, activation="silu", convention=0))
+    params = [t.requires_grad_(True) for lw in flow.layers for pair in zip(lw.w, lw.b) for t in pair]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    loss = torch.mean(O.ft_action(2.0, flow, xi)) + tr.log_prior()
+    opt.zero_grad(); loss.backward(); opt.step()
+    m = tr.train_step(16, xi=xi)
+    assert abs(m["dkl"] - float(loss.detach())) < 1e-9 * abs(float(loss.detach()))
+    twin = np.stack([np.concatenate([np.concatenate([w.detach().numpy().ravel(), b.detach().numpy().ravel()])
+                                     for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    assert np.max(np.abs(tr.raw.detach().numpy() - twin)) < 1e-9
+    first = m["dkl"]
+    for _ in range(30):
+        m = tr.train_step(64)
+    assert np.mean(tr.history["dkl"][-5:]) < first and 0 < m["ess"] <= 1.0
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:

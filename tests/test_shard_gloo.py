@@ -64,3 +64,27 @@ def test_allreduce_observables_world2_matches_single_process(tmp_path, total):
 def test_single_process_is_identity():
     s = shard.local_observable_sums(fake_result(0, 5))
     assert torch.equal(shard.allreduce_observables(s.clone()), s)
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.arange(24 * 955, dtype=torch.float64).reshape(24, 955) * (rank + 1)
+        sums = torch.tensor([10.0 * (rank + 1), 64.0], dtype=torch.float64)
+        g2, s2 = shard.allreduce_gradient(g, sums)
+        if rank == 0:
+            torch.save((g2, s2), out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_gradient_world2(tmp_path):
+    """the flow-training gradient (n_layers x 955) and the loss sums travel in one all-reduce"""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    g, s = torch.load(out)
+    base = torch.arange(24 * 955, dtype=torch.float64).reshape(24, 955)
+    assert torch.equal(g, base * 3) and torch.equal(s, torch.tensor([30.0, 128.0], dtype=torch.float64))
+    g1, s1 = shard.allreduce_gradient(base, None)
+    assert g1 is base and s1 is None
