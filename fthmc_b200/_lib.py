@@ -28,6 +28,7 @@ SIGNATURES = {
     "fthmc_flow_pack": (c_int, [c_dp, c_int, c_dp, c_dp, c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int,
                                 ctypes.POINTER(c_dp)]),
     "fthmc_flow_free": (c_int, [c_dp]),
+    "fthmc_flow_update": (c_int, [c_dp, c_dp]),
     "fthmc_flow_n_layers": (c_int, [c_dp]),
     "fthmc_flow_fwd": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_sz, c_dp]),
     "fthmc_flow_inv": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_sz, c_dp]),

@@ -786,6 +786,18 @@ extern "C" int fthmc_flow_pack(const double* raw_host, int n_layers, const int* 
     return 0;
 }
 
+// new weights into an existing handle (same layer count and masks): the training loop's per-step re-pack without
+// re-allocating device memory.  Synchronous (it uploads); no launch using the handle may be in flight.
+extern "C" int fthmc_flow_update(fthmc_flow_t f, const double* raw_host) {
+    if (!f || !raw_host) return fail(FTHMC_E_ARG, "null pointer");
+    std::vector<int> mu(f->n_layers);
+    CK(cudaMemcpy(mu.data(), f->lmu, f->n_layers * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<double> pack((size_t)f->n_layers * PACK_DOUBLES);
+    for (int l = 0; l < f->n_layers; ++l) pack_layer(raw_host + (size_t)l * RAW_DOUBLES, mu[l], pack.data() + (size_t)l * PACK_DOUBLES);
+    CK(cudaMemcpy(f->wpack, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 extern "C" int fthmc_flow_free(fthmc_flow_t f) {
     if (!f) return 0;
     cudaFree(f->wpack); cudaFree(f->lmu); cudaFree(f->loff);

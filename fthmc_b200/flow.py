@@ -50,6 +50,16 @@ class PackedFlow:
     def __len__(self):
         return self.n_layers
 
+    def update(self, raw):
+        """Replace the CNN weights in place (same layer count and masks): the per-step re-pack of a training loop."""
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        if raw.shape != (self.n_layers, RAW_PER_LAYER):
+            raise _lib.FthmcError(-5, f"expected ({self.n_layers},{RAW_PER_LAYER}) raw weights, got {raw.shape}")
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _lib.check(_lib.lib().fthmc_flow_update(self.handle, raw.ctypes.data))
+        return self
+
 
 def raw_weights_of(flow_module):
     """(n_layers,955) float64 in the reference's parameter order of layer.plaq_coupling.net."""

@@ -22,20 +22,26 @@ class FlowTrainer:
         self.lattice, self.beta = tuple(lattice), float(beta)
         self.activation, self.convention = activation, convention
         self.opt = torch.optim.Adam([self.raw], lr=lr)           # base_lr = 1e-4, ipynb/ft_hmc.py:316-317
-        self.gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(int(seed) if seed is not None else torch.seed())
         self.history = {"loss": [], "dkl": [], "ess": []}
-        self._pf = None
+        self._pf, self._stale = None, True
 
     # ---- model pieces -------------------------------------------------------------------------------
     def packed(self):
+        """device copy of the current weights (re-uploaded into the same handle after every optimizer step)"""
         if self._pf is None:
-            self._pf = PackedFlow(self.raw.detach().numpy(), activation=self.activation, convention=self.convention)
+            self._pf = PackedFlow(self.raw.detach().numpy(), activation=self.activation, convention=self.convention, device=self.dev)
+        elif self._stale:
+            self._pf.update(self.raw.detach().numpy())
+        self._stale = False
         return self._pf
 
     def sample_prior(self, batch_size):
-        """MultivariateUniform(0, 2pi).sample_n (ipynb/ft_hmc.py:304)."""
+        """MultivariateUniform(0, 2pi).sample_n (ipynb/ft_hmc.py:304), drawn on the device."""
         shape = (batch_size, 2) + self.lattice
-        return torch.rand(shape, dtype=torch.float64, generator=self.gen) * (2 * math.pi)
+        return torch.rand(shape, dtype=torch.float64, generator=self.gen, device=self.dev) * (2 * math.pi)
 
     def log_prior(self):
         return -2 * self.lattice[0] * self.lattice[1] * math.log(2 * math.pi)
@@ -49,7 +55,7 @@ class FlowTrainer:
             beta = self.beta
         if xi is None:
             xi = self.sample_prior(batch_size)
-        act, grad = ft_action_grad(_P, self.packed(), xi.cuda())
+        act, grad = ft_action_grad(_P, self.packed(), xi.to(self.dev))
         act = act.cpu()
         sums = torch.stack([act.sum(), torch.tensor(float(act.numel()), dtype=torch.float64)])
         grad, sums = shard.allreduce_gradient(grad, sums, group=group)      # all ranks: same gradient, same step
@@ -58,7 +64,7 @@ class FlowTrainer:
         self.opt.zero_grad()
         self.raw.grad = (grad / nb).to(torch.float64)
         self.opt.step()
-        self._pf = None                              # weights changed: re-pack lazily
+        self._stale = True                           # weights changed: re-upload lazily
         logw = -(act + self.log_prior())             # logp - logq of this rank's batch
         ess = float(torch.exp(2 * torch.logsumexp(logw, 0) - torch.logsumexp(2 * logw, 0)) / act.numel())   # compute_ess
         m = {"loss": dkl, "dkl": dkl, "ess": ess}

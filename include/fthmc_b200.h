@@ -80,6 +80,8 @@ int fthmc_hmc_traj(const double* x_in, double* x_out, const double* p_in, const 
 int fthmc_flow_pack(const double* raw_host, int n_layers, const int* mu_host, const int* off_host,
                     int hidden0, int hidden1, int n_mix, int ksize, int activation, int convention,
                     double inv_tol, int inv_max_iter, fthmc_flow_t* out);
+/* new weights (same n_layers / masks) into an existing handle; synchronous, no launch on the handle may be in flight */
+int fthmc_flow_update(fthmc_flow_t flow, const double* raw_host);
 int fthmc_flow_free(fthmc_flow_t flow);
 int fthmc_flow_n_layers(fthmc_flow_t flow);
 

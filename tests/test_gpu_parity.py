@@ -435,7 +435,7 @@ def test_train_step_follows_autograd_adam():
     L, layers = 8, 4
     raw0 = ft.default_init_raw(layers, 11)
     tr = ft.FlowTrainer(raw0, (L, L), beta=2.0, lr=1e-3, seed=5)
-    xi = tr.sample_prior(16)
+    xi = tr.sample_prior(16).cpu()
     # autograd twin
     flow = oracle_flow_from_golden(dict(weights=raw0, activation="silu", convention=0))
     params = [t.requires_grad_(True) for lw in flow.layers for pair in zip(lw.w, lw.b) for t in pair]
