@@ -453,6 +453,41 @@ def test_train_step_follows_autograd_adam():
     assert np.mean(tr.history["dkl"][-5:]) < first and 0 < m["ess"] <= 1.0
 
 
+def test_flow_independence_sampler():
+    """apply_flow_to_prior / make_mcmc_ensemble (ipynb/field_transformation.py:37-83) on the forward-flow kernel: logq
+    and logp of the proposals against the oracle, and the accept/reject chain against a replay of the reference's loop."""
+    from fthmc_b200 import sampler
+    flow = O.random_flow(n_layers=8, seed=6, scale=1.5)
+    pf = ft.PackedFlow(_raw_of(flow))
+    L, beta = 8, 2.0
+    gen = torch.Generator(device="cuda"); gen.manual_seed(9)
+    xi, x, logq = sampler.apply_flow_to_prior(pf, (L, L), 16, generator=gen)
+    y, lj = O.ft_flow_logJ(flow, xi.cpu())
+    assert np.max(np.abs(x.cpu().numpy() - y.numpy())) < 1e-11
+    assert relerr(logq.cpu().numpy(), (-2 * L * L * np.log(2 * np.pi) - lj).numpy()) < REL
+    gen.manual_seed(9)
+    torch.manual_seed(4)
+    h = sampler.make_mcmc_ensemble(pf, beta, (L, L), 16, 40, generator=gen)
+    assert len(h["x"]) == 40 and h["accepted"][0] is True and 0 < sum(h["accepted"]) <= 40
+    # replay: same proposals (same device generator), same uniforms (same host generator)
+    gen.manual_seed(9)
+    torch.manual_seed(4)
+    last = None
+    for i in range(40):
+        if i % 16 == 0:
+            _, xb, lq = sampler.apply_flow_to_prior(pf, (L, L), 16, generator=gen)
+            lp = -O.u1_action(beta, xb.cpu()); lq = lq.cpu()
+        cur = (float(lp[i % 16]), float(lq[i % 16]))
+        if last is None:
+            acc = True
+        else:
+            acc = bool(torch.rand(1) < min(1.0, float(np.exp((cur[0] - cur[1]) - (last[0] - last[1])))))
+        if acc:
+            last = cur
+        assert acc == h["accepted"][i] and abs(float(h["logp"][i]) - last[0]) < 1e-9 * abs(last[0])
+    assert 0 < float(sampler.compute_ess(torch.stack(h["logp"]), torch.stack(h["logq"]))) <= 1
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
