@@ -106,7 +106,7 @@ FT_HD double regularize1(double f) {
     return TWO_PI_D * (g - floor(g) - 0.5);
 }
 
-// e^x for |x| <= 708 with ~1 ulp error: x = (16 k + j) ln2/16 + r with |r| <= ln2/32, e^x = 2^k * 2^(j/16) * e^r.
+// e^x with ~1 ulp error for |x| <= 708 (finite and monotone-saturated beyond): x = (16 k + j) ln2/16 + r with |r| <= ln2/32, e^x = 2^k * 2^(j/16) * e^r.
 // 2^(j/16) comes from a 16-entry table (on the device: 128 bytes of shared memory, one bank each -- conflict free
 // for any index pattern), the power of two goes into its exponent bits with an integer add, and e^r - 1 needs a
 // degree-7 Taylor polynomial only (remainder r^8/8! < 1.3e-18).  8 fp64 operations after the range reduction instead of
@@ -131,16 +131,6 @@ FT_HD double exp_fast(double x) {
     const double K[10] = FT_EXP_COEFS;
     static const double TAB[16] = FT_EXP_TABLE;
 #endif
-    // clamp to [-708, 708] (a NaN maps to +-708).  On the device: integer compare/select on the high word (708.0 ==
-    // 0x40862000'00000000) instead of DSETP/FSEL pairs on the fp64 pipe
-#ifdef __CUDA_ARCH__
-    {
-        const int hi = __double2hiint(x);
-        if ((hi & 0x7fffffff) >= 0x40862000) x = __hiloint2double((hi & 0x80000000) | 0x40862000, 0);
-    }
-#else
-    x = fmin(fmax(x, -708.0), 708.0);
-#endif
     const double t = x * K[6];                                               // 16 x / ln2
     const double nm = t + K[7];                                              // rint(t) in the low mantissa bits
     const double n = nm - K[7];
@@ -150,18 +140,25 @@ FT_HD double exp_fast(double x) {
 #pragma unroll
     for (int i = 1; i < 6; ++i) w = fma(w, r, K[i]);
     const double q = r * fma(r, w, 1.0);                                     // e^r - 1
+    // 2^k * 2^(j/16): k goes into the exponent bits of the table entry.  |x| <= 708 keeps the exponent in range; beyond
+    // that k saturates (integer min/max, off the critical path) so that the result stays finite and SiLU keeps its
+    // limits (0 and z) instead of producing garbage bits.  A NaN propagates.
     int ni;
 #ifdef __CUDA_ARCH__
     ni = __double2loint(nm);                                                 // n as a two's complement integer
-    const double tj = TAB[ni & 15];
-    const double sc = __hiloint2double(__double2hiint(tj) + ((ni >> 4) << 20), __double2loint(tj));   // 2^k * 2^(j/16)
 #else
-    ni = (int)n;
+    ni = (int)(long long)fmin(fmax(n, -2147483647.0), 2147483647.0);
+#endif
     const double tj = TAB[ni & 15];
+    int k = ni >> 4;
+    k = k < -1022 ? -1022 : (k > 1021 ? 1021 : k);
+    double sc;
+#ifdef __CUDA_ARCH__
+    sc = __hiloint2double(__double2hiint(tj) + (k << 20), __double2loint(tj));
+#else
     long long bits;
     memcpy(&bits, &tj, sizeof(bits));
-    bits += (long long)(ni >> 4) << 52;
-    double sc;
+    bits += (long long)k << 52;
     memcpy(&sc, &bits, sizeof(sc));
 #endif
     return fma(sc, q, sc);
@@ -1037,6 +1034,11 @@ struct Engine {
             for (int o = 0; o < NOUT; ++o)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) ob[o][a] = OUT[o * T + gi * R + rs[a]];
+            double d2v[3][CH];                               // act'(z2) of this task's outputs, fetched before the MAC chains
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int ci = 0; ci < CH; ++ci) d2v[k][ci] = C[(CH * h + ci) * sB + (3 * gi + k) * R + r];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 double acc[CH];
@@ -1055,7 +1057,7 @@ struct Engine {
 #pragma unroll
                 for (int ci = 0; ci < CH; ++ci) {
                     int idx = (CH * h + ci) * sB + (3 * gi + k) * R + r;
-                    C[idx] = acc[ci] * C[idx];
+                    C[idx] = acc[ci] * d2v[k][ci];
                 }
             }
         }
@@ -1082,12 +1084,13 @@ struct Engine {
 #pragma unroll
             for (int c = 0; c < 18; ++c) bf[c][ls] = W[OFF_W2T + ((4 * (c & 1) + j) * 9 + (c >> 1)) * NH + n];
         }
+        wait_bar(BAR_D1);                                    // act'(z1) has landed in A (issued a layer ago)
         for (int st = ex.warp(); st < G * RB; st += ex.nwarps()) {
             const int gi = st / RB, rb = 8 * (st - gi * RB);
             const int gn = gi + 1 == G ? 0 : gi + 1;
             // source column slots m = 0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1, 4g, 4g+1, 4g+3, 4g+4
             const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
-            double acc0[4][NL], acc1[4][NL];
+            double acc0[4][NL], acc1[4][NL], d1a[4][NL], d1b[4][NL];
             int rowa[3][NL];                                 // output row r reads source row r - a + 1
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3, r = rb + i;
@@ -1095,7 +1098,10 @@ struct Engine {
                 rowa[1][ls] = j * sB + r;
                 rowa[2][ls] = j * sB + (r == 0 ? R - 1 : r - 1);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { acc0[q][ls] = 0.0; acc1[q][ls] = 0.0; }
+                for (int q = 0; q < 4; ++q) {                // act'(z1) of this lane's outputs: fetched under the DMMAs
+                    const double* p = A + 2 * j * sA + (4 * gi + q) * R + rb + i;
+                    acc0[q][ls] = 0.0; acc1[q][ls] = 0.0; d1a[q][ls] = p[0]; d1b[q][ls] = p[sA];
+                }
             }
 #pragma unroll
             for (int c = 0; c < 18; ++c) {
@@ -1111,14 +1117,13 @@ struct Engine {
                     }
                 }
             }
-            wait_bar(BAR_D1);                                // act'(z1) has landed in A
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     double* p = A + 2 * j * sA + (4 * gi + q) * R + rb + i;
-                    p[0] = acc0[q][ls] * p[0];
-                    p[sA] = acc1[q][ls] * p[sA];
+                    p[0] = acc0[q][ls] * d1a[q][ls];
+                    p[sA] = acc1[q][ls] * d1b[q][ls];
                 }
             }
         }
