@@ -882,7 +882,8 @@ struct Engine {
 
     // one coupling layer forward on the resident field; returns logJ (valid on all threads) if asked.
     // save: also write the layer block the reverse sweep of ft_force needs.
-    FT_HD double layer_forward(int l, bool want_logJ, bool save) {
+    // TRAIN (compile time): also save the activations h1, h2 for the weight-gradient phases
+    template <bool TRAIN = false> FT_HD double layer_forward(int l, bool want_logJ, bool save) {
         LayerGeom g = geom(l);
         double lj = 0.0, tot = 0.0;
         FT_T(PF_PLANES, issue_weights(l, false);              // lands while the plaquette planes are computed
@@ -890,7 +891,7 @@ struct Engine {
              wait_bar(BAR_W);
              ex.sync();
              advance_bar(BAR_W));
-        const bool tr = save && pr.train;
+        const bool tr = TRAIN && save;
         FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr, tr ? wsH1(l) : nullptr); ex.sync());
         if constexpr (CL) { push_halo_h1(g); ex.sync(); }
         FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr, tr ? wsH2(l) : nullptr); ex.sync());
@@ -1292,22 +1293,22 @@ struct Engine {
     FT_HD void issue_so(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_SO, sm(oOUT), wsSO(l), 3 * VQ); }
 
     // in flight on entry: d2(l) [, d2(l-1)], Wt(l), d1(l), cs(l)
-    FT_HD void layer_adjoint(int l) {
+    template <bool TRAIN = false> FT_HD void layer_adjoint(int l) {
         LayerGeom g = geom(l);
         FT_T(PF_OUTGRAD, ph_outgrad(g);            // waits for so/sv(l)
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
              ex.sync();
              advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
-        if (pr.train) ph_wgrad3(g, wsH2(l), gslice(l));                 // OUT = (s1bar, s2bar, tbar) is complete and intact
+        if (TRAIN) ph_wgrad3(g, wsH2(l), gslice(l));                 // OUT = (s1bar, s2bar, tbar) is complete and intact
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
-        if (pr.train) ph_wgrad2(g, zbuf(l), wsH1(l), gslice(l));        // zbar2 complete; reads it only
+        if (TRAIN) ph_wgrad2(g, zbuf(l), wsH1(l), gslice(l));        // zbar2 complete; reads it only
         FT_T(PF_ISSUE, issue_so(l - 1));           // OUT is free again
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.sync();
              advance_bar(BAR_D1));
         FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
-        if (pr.train) ph_wgrad1(g, gslice(l));                          // zbar1 complete in A; reads A and CS only
+        if (TRAIN) ph_wgrad1(g, gslice(l));                          // zbar1 complete in A; reads A and CS only
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
              ex.sync();
              advance_bar(BAR_CS));
@@ -1321,10 +1322,10 @@ struct Engine {
     // chain programs on the resident field X
     // =============================================================================================
     // X <- F(X); returns sum of logJ (if asked).  save: write the layer blocks for the reverse sweep
-    FT_HD double flow_forward(bool want_logJ, bool save, double* layer_logJ = nullptr) {
+    template <bool TRAIN = false> FT_HD double flow_forward(bool want_logJ, bool save, double* layer_logJ = nullptr) {
         double tot = 0.0;
         for (int l = 0; l < pr.nlayers; ++l) {
-            double lj = layer_forward(l, want_logJ, save);
+            double lj = layer_forward<TRAIN>(l, want_logJ, save);
             tot += lj;
             if (layer_logJ && ex.tid() == 0) layer_logJ[l] = lj;
         }
@@ -1348,8 +1349,8 @@ struct Engine {
     }
     // ft_force (ipynb/ft_hmc.py:240-249): GR <- d/dx [S(F(x)) - sum logJ]; X is preserved.
     // want_logJ (training): the forward sweep also accumulates sum logJ and ft_action(x) = S(F(x)) - sum logJ is returned
-    FT_HD double ft_force(double beta, bool want_logJ = false) {
-        double lj = flow_forward(want_logJ, true);
+    template <bool TRAIN = false> FT_HD double ft_force(double beta, bool want_logJ = false) {
+        double lj = flow_forward<TRAIN>(want_logJ, true);
         if (want_logJ) lj = wilson_action(beta, pr.conv) - lj;          // ft_action(x) = S(F(x)) - sum logJ
         ex.proxy_fence();                 // the layer blocks just written are read back by bulk copies (async proxy)
         ex.sync();
@@ -1361,7 +1362,7 @@ struct Engine {
              issue_cs(last));
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         FT_T(PF_ISSUE, issue_so(last));
-        for (int l = last; l >= 0; --l) layer_adjoint(l);
+        for (int l = last; l >= 0; --l) layer_adjoint<TRAIN>(l);
         return lj;
     }
 

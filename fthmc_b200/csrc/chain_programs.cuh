@@ -81,7 +81,7 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
     } break;
     case MODE_FT_GRAD: {
         en.load_field(en.oX, fin); ex.sync();
-        double s = en.ft_force(a.beta, true);                // weight gradients accumulate into en.gW along the adjoint sweep
+        double s = en.template ft_force<true>(a.beta, true); // weight gradients accumulate into en.gW along the adjoint sweep
         if (a.s_out && ex.tid() == 0) a.s_out[b] = s;
         if (fout) en.store_field(fout, en.oGR);              // optional: the force on the input field
         ex.sync();
