@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
     const T* f = links + (size_t)b * 2 * L0 * L1;
     T* o = out + (size_t)b * 2 * L0 * L1;
     const int r0 = c * rows, r1 = min(L0, r0 + rows), nr = r1 - r0;
-    if (VEC) {
+    if constexpr (VEC) {
         constexpr int N = Vec<T>::N;
         using VT = typename Vec<T>::type;
         const int W = L1 / N, dr = (int)blockDim.x / W, dc = (int)blockDim.x - dr * W;
@@ -437,18 +437,18 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
             col += dc; row += dr;
             if (col >= W) { col -= W; ++row; }
         }
-        return;
-    }
-    for (int i = threadIdx.x; i < (nr + 1) * L1; i += blockDim.x) {
-        int n0 = r0 - 1 + i / L1; if (n0 < 0) n0 += L0;
-        S[i] = M<T>::sinv(plaq_g(f, L0, L1, n0, i % L1, order));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nr * L1; i += blockDim.x) {
-        const int rr = i / L1, n1 = i % L1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
-        const T s = S[(rr + 1) * L1 + n1];
-        o[(r0 + rr) * L1 + n1] = beta * (s - S[(rr + 1) * L1 + n1m]);
-        o[(L0 + r0 + rr) * L1 + n1] = beta * (S[rr * L1 + n1] - s);
+    } else {
+        for (int i = threadIdx.x; i < (nr + 1) * L1; i += blockDim.x) {
+            int n0 = r0 - 1 + i / L1; if (n0 < 0) n0 += L0;
+            S[i] = M<T>::sinv(plaq_g(f, L0, L1, n0, i % L1, order));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * L1; i += blockDim.x) {
+            const int rr = i / L1, n1 = i % L1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+            const T s = S[(rr + 1) * L1 + n1];
+            o[(r0 + rr) * L1 + n1] = beta * (s - S[(rr + 1) * L1 + n1m]);
+            o[(L0 + r0 + rr) * L1 + n1] = beta * (S[rr * L1 + n1] - s);
+        }
     }
 }
 
