@@ -178,6 +178,29 @@ def measured_peaks():
         return None
 
 
+def stencil_rooflines(ft, P, hbm_peak, dev):
+    """Supplementary: the HBM-bound drop-ins (action / force / topological charge) on a batch larger than L2, algorithmic
+    bytes over CUDA-event time against the measured copy bandwidth (scripts/stencil_bench.py has the full table)."""
+    L = P.lat[0]
+    B = min(65535, (768 << 20) // (2 * L * L * 8))
+    x = (torch.rand(B, 2, L, L, dtype=torch.float64, device=dev) * 2 - 1) * 3.0
+    nbytes = x.numel() * 8
+    out = {"batch": B, "lattice": [L, L], "dtype": "f64", "peak_gbs": hbm_peak}
+    for name, fn, traffic in (("action", lambda: ft.action(P, x), nbytes), ("topocharge", lambda: ft.topocharge(x), nbytes),
+                              ("force", lambda: ft.force(P, x), 2 * nbytes)):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        gbs = traffic / (sorted(ts)[len(ts) // 2] * 1e-3) / 1e9
+        out[name] = {"gbs": gbs, "frac": gbs / hbm_peak}
+    del x
+    return out
+
+
 def run_ours(a):
     import torch.distributed as dist
     import fthmc_b200 as ft
@@ -312,6 +335,7 @@ def run_ours(a):
             "gpu_launches": int(launches), "clocks": clk,
             "observables": {"plaq": float(obs_h[0] / obs_h[6]), "acc_rate": float(obs_h[3] / obs_h[6]),
                             "mean_dH": float(obs_h[4] / obs_h[6]), "Q2": float(obs_h[2] / obs_h[6])}}
+    line["stencils"] = stencil_rooflines(ft, P, hbm_peak, dev)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     print(json.dumps(line), flush=True)

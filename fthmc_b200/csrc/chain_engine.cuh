@@ -270,6 +270,8 @@ FT_HD double u53(uint32_t hi, uint32_t lo) {
 // ------------------------------------------------------------------------------------------------
 // The engine.  E is the execution policy (device: a CTA; host emulation: one serial thread).
 //   E::tid(), E::nt(), E::sync(), E::sum(v), E::maxv(v), E::all(pred) (block/cluster-wide AND, a barrier)
+//   E::lsync()                        CTA-local barrier (== sync() without a cluster): for phase boundaries across which
+//                                     only this rank's own shared memory is produced and consumed
 //   E::kLanes, E::warp(), E::nwarps(), E::lane0(), E::use_mma(), E::mma884(d0, d1, a, b)
 //                                     warp-level fp64 tensor-core tile D(8x8) += A(8x4) B(4x8) with the PTX m8n8k4 fragment
 //                                     layout.  Device: kLanes == 1, every thread holds its own lane's fragment elements;
@@ -672,8 +674,9 @@ struct Engine {
     FT_HD bool fine_tasks() const { return ex.fine(VQ); }
 
     // h2 = act(conv2) on the columns {4g-1,4g,4g+1} -> B[o][3g+k][r];  d2_save: act'(z2) to global
-    // tensor-core (DMMA) form of the two big convolutions: single-CTA chains whose stripe length is a multiple of 8
-    FT_HD bool mma_ok() const { return !CL && (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
+    // tensor-core (DMMA) form of the two big convolutions: stripe lengths that are multiples of 8 (in cluster mode the
+    // halo columns of a rank's first / last stripe group come from the halo buffers AH / ZH, channel stride 2R)
+    FT_HD bool mma_ok() const { return (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
     FT_HD void ph_conv2(const LayerGeom g, double* d2_save, double* h2_save = nullptr) {
         if (mma_ok()) {
             if (pr.act == ACT_SILU) ph_conv2_mma<ACT_SILU>(g, d2_save, h2_save);
@@ -703,11 +706,17 @@ struct Engine {
             const int gi = st / RB, rb = 8 * (st - gi * RB);
             int cc[5];                                       // columns 4g-2 .. 4g+2 (offsets in doubles)
 #pragma unroll
-            for (int m = 0; m < 5; ++m) { const int c = 4 * gi - 2 + m; cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            for (int m = 0; m < 5; ++m) {
+                const int c = 4 * gi - 2 + m;
+                if (CL && c < 0) cc[m] = (oC - oA) + (c + 2) * R;          // halo AH[ci][c+2][r]
+                else cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R;
+            }
             double acc0[3][NL], acc1[3][NL];
             int rowa[3][NL];                                 // A fragment: row i = lane / 4 (site rb + i), column j = lane % 4 (channel)
+            int hcj[NL];                                     // cluster mode: channel-stride correction of the halo columns
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3, r = rb + i;
+                hcj[ls] = CL ? j * (2 * R - sA) : 0;
                 rowa[0][ls] = j * sA + (r == 0 ? R - 1 : r - 1);
                 rowa[1][ls] = j * sA + r;
                 rowa[2][ls] = j * sA + (r + 1 == R ? 0 : r + 1);
@@ -721,7 +730,9 @@ struct Engine {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     double av[NL];
-                    FT_LANES(ln, ls) av[ls] = A[rowa[a][ls] + cc[k + b] + hoff];
+                    const bool halo = CL && gi == 0 && k + b < 2;
+                    const int hcorr = halo ? 4 * (c & 1) * (2 * R - sA) : 0;
+                    FT_LANES(ln, ls) av[ls] = A[rowa[a][ls] + cc[k + b] + hoff + (halo ? hcj[ls] + hcorr : 0)];
                     ex.mma884(acc0[k], acc1[k], av, bf[c]);
                 }
             }
@@ -889,12 +900,12 @@ struct Engine {
         FT_T(PF_PLANES, issue_weights(l, false);              // lands while the plaquette planes are computed
              ph_planes(g, save ? wsCS(l) : nullptr);
              wait_bar(BAR_W);
-             ex.sync();
+             ex.lsync();                                      // CS / UA are produced and consumed by this rank only
              advance_bar(BAR_W));
         const bool tr = TRAIN && save;
-        FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr, tr ? wsH1(l) : nullptr); ex.sync());
-        if constexpr (CL) { push_halo_h1(g); ex.sync(); }
-        FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr, tr ? wsH2(l) : nullptr); ex.sync());
+        FT_T(PF_CONV1, ph_conv1(g, save ? wsD1(l) : nullptr, tr ? wsH1(l) : nullptr); ex.lsync());
+        if constexpr (CL) { push_halo_h1(g); ex.sync(); }     // the neighbour must see the halo: cluster-wide
+        FT_T(PF_CONV2, ph_conv2(g, save ? wsD2(l) : nullptr, tr ? wsH2(l) : nullptr); ex.lsync());
         FT_T(PF_CONV3F, lj = ph_conv3_forward(g, want_logJ, save ? wsSV(l) : nullptr, save ? wsSO(l) : nullptr);
              tot = want_logJ ? ex.sum(lj) : 0.0;
              ex.sync());
@@ -922,7 +933,7 @@ struct Engine {
             Y[t] = mod_2pi(UA[t] - out[2], conv);
             LO[t] = lo0; HI[t] = hi0;
         }
-        ex.sync();     // (A was the conv2 input; all conv3 reads of B are unaffected)
+        ex.lsync();    // (A was the conv2 input; all conv3 reads of B are unaffected)
         int it = 0;
         for (; it < pr.inv_max_iter; ++it) {
             double err = 0.0;
@@ -964,11 +975,11 @@ struct Engine {
         FT_T(PF_PLANES, issue_weights(l, false);
              ph_planes(g, nullptr);
              wait_bar(BAR_W);
-             ex.sync();
+             ex.lsync();                                      // CS / UA are produced and consumed by this rank only
              advance_bar(BAR_W));
-        FT_T(PF_CONV1, ph_conv1(g, nullptr); ex.sync());
+        FT_T(PF_CONV1, ph_conv1(g, nullptr); ex.lsync());
         if constexpr (CL) { push_halo_h1(g); ex.sync(); }
-        FT_T(PF_CONV2, ph_conv2(g, nullptr); ex.sync());
+        FT_T(PF_CONV2, ph_conv2(g, nullptr); ex.lsync());
         int iters = 0;
         double lj = 0.0, tot = 0.0;
         FT_T(PF_CONV3R, lj = ph_conv3_reverse(g, want_logJ, &iters);
@@ -1090,11 +1101,15 @@ struct Engine {
             const int gi = st / RB, rb = 8 * (st - gi * RB);
             const int gn = gi + 1 == G ? 0 : gi + 1;
             // source column slots m = 0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1, 4g, 4g+1, 4g+3, 4g+4
-            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
+            const bool hal = CL && gi + 1 == G;              // cluster mode: slots 3, 4 of the last group sit in ZH[o][m-3][r]
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R,
+                                hal ? (oC - oZ) : 3 * gn * R, hal ? (oC - oZ) + R : (3 * gn + 1) * R };
             double acc0[4][NL], acc1[4][NL], d1a[4][NL], d1b[4][NL];
             int rowa[3][NL];                                 // output row r reads source row r - a + 1
+            int hcj[NL];
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3, r = rb + i;
+                hcj[ls] = CL ? j * (2 * R - sB) : 0;
                 rowa[0][ls] = j * sB + (r + 1 == R ? 0 : r + 1);
                 rowa[1][ls] = j * sB + r;
                 rowa[2][ls] = j * sB + (r == 0 ? R - 1 : r - 1);
@@ -1113,7 +1128,9 @@ struct Engine {
                     const int m = co == -1 ? 0 : co == 0 ? 1 : co == 1 ? 2 : co == 3 ? 3 : co == 4 ? 4 : -1;
                     if (m >= 0) {
                         double av[NL];
-                        FT_LANES(ln, ls) av[ls] = C[rowa[a][ls] + sc[m] + hoff];
+                        const bool halo = hal && m >= 3;
+                        const int hcorr = halo ? 4 * (c & 1) * (2 * R - sB) : 0;
+                        FT_LANES(ln, ls) av[ls] = C[rowa[a][ls] + sc[m] + hoff + (halo ? hcj[ls] + hcorr : 0)];
                         ex.mma884(acc0[q], acc1[q], av, bf[c]);
                     }
                 }
@@ -1297,20 +1314,20 @@ struct Engine {
         LayerGeom g = geom(l);
         FT_T(PF_OUTGRAD, ph_outgrad(g);            // waits for so/sv(l)
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
-             ex.sync();
+             ex.lsync();                           // (restored links / GR reads cross ranks, but are ordered by the cluster barriers around)
              advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
         if (TRAIN) ph_wgrad3(g, wsH2(l), gslice(l));                 // OUT = (s1bar, s2bar, tbar) is complete and intact
-        FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.sync());
+        FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.lsync());
         if (TRAIN) ph_wgrad2(g, zbuf(l), wsH1(l), gslice(l));        // zbar2 complete; reads it only
         FT_T(PF_ISSUE, issue_so(l - 1));           // OUT is free again
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
-             ex.sync();
+             ex.lsync();
              advance_bar(BAR_D1));
         FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
         if (TRAIN) ph_wgrad1(g, gslice(l));                          // zbar1 complete in A; reads A and CS only
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
-             ex.sync();
+             ex.lsync();
              advance_bar(BAR_CS));
         FT_T(PF_ISSUE, issue_weights(l - 1, true); // W(transposed), A and CS are free
              issue_d1(l - 1);

@@ -163,6 +163,11 @@ struct CtaExec {
         __syncthreads();
 #endif
     }
+    __host__ __device__ void lsync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
     __host__ __device__ double sum(double v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll

@@ -43,6 +43,7 @@ struct SerialExec {
             }
     }
     void sync() const {}
+    void lsync() const {}
     double sum(double v) const { return v; }
     double maxv(double v) const { return v; }
     bool all(bool pred) const { return pred; }
@@ -144,6 +145,7 @@ struct ThreadExec {
             }
     }
     void sync() const { sh->bar.arrive_and_wait(); }
+    void lsync() const {}          // one "thread" per CTA: a CTA-local barrier is a no-op
     double sum(double v) const {
         sh->slots[rk] = v; sh->bar.arrive_and_wait();
         double t = 0.0; for (int i = 0; i < sh->nr; ++i) t += sh->slots[i];
