@@ -609,13 +609,22 @@ static int check_lattice(int B, int L0, int L1, bool flow, int* nr_out) {
     return 0;
 }
 
+// chains resident at once on this device for (lattice, flow): what the persistent grid will be; falls back to an upper
+// bound when no device can be queried
+static long long resident_bound(int L0, int L1, bool flow, int nr) {
+    DevInfo& d = devinfo();
+    if (d.ok) {
+        const int r = chain_resident(L0, L1, flow, nr);
+        if (r > 0) return r;
+    }
+    return nr == 1 ? (long long)(d.sm > 0 ? d.sm : 148) * 32 : (long long)(d.sm > 0 ? d.sm : 148) / nr;
+}
+
 extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
     if (B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
-    DevInfo& d = devinfo();
     int nr = chain_ranks(L0, L1, flow != nullptr);
     if (nr == 0) nr = 1;
-    // upper bound on the chains resident at once: 32 CTAs per SM without a cluster, one CTA per SM with one
-    long long g = nr == 1 ? (long long)(d.sm > 0 ? d.sm : 148) * 32 : (long long)(d.sm > 0 ? d.sm : 148) / nr;
+    long long g = resident_bound(L0, L1, flow != nullptr, nr);
     if (B < g) g = B;
     if (g < 1) g = 1;
     return (size_t)g * engine_ws_doubles(L0, L1, flow ? flow->n_layers : 0, nr) * sizeof(double) + 256;
@@ -925,9 +934,9 @@ extern "C" int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, doubl
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t fthmc_grad_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
     if (!flow || B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
-    DevInfo& d = devinfo();
-    long long g = (long long)(d.sm > 0 ? d.sm : 148) * 32;
+    long long g = resident_bound(L0, L1, true, 1);
     if (B < g) g = B;
+    if (g < 1) g = 1;
     return (size_t)g * (engine_ws_doubles(L0, L1, flow->n_layers, 1, true) + (size_t)(FT_THREADS / 32) * flow->n_layers * GRAD_DOUBLES)
                * sizeof(double) + 256;
 }
