@@ -488,6 +488,40 @@ def test_flow_independence_sampler():
     assert 0 < float(sampler.compute_ess(torch.stack(h["logp"]), torch.stack(h["logq"]))) <= 1
 
 
+def test_field_transformation_class(golden):
+    """The package's class form (fthmc/ft_hmc.py:108-257) in the package conventions ([-pi,pi) torch_mod): action / force /
+    flow_forward / flow_backward against the oracle with convention 1, and a latent-space trajectory against the same
+    steps done with the oracle (the reference's buggy leapfrog / calc_energy are deliberately not reproduced)."""
+    import types
+    g = golden("copyB_L8")
+    flow_o = oracle_flow_from_golden(g)
+    assert flow_o.convention == 1
+    cfg = types.SimpleNamespace(beta=2.0, volume=64, lat=[8, 8], nd=2)
+    lf = types.SimpleNamespace(dt=0.05, tau=0.2, nstep=4)
+    FT = ft.FieldTransformation(ft.PackedFlow(g["weights"], activation=str(g["activation"]), convention=1), cfg, lf)
+    x = T(g["x"])
+    assert relerr(FT.action(x).numpy(), O.ft_action(cfg.beta, flow_o, x).numpy()) < REL
+    assert relerr(FT.force(x).numpy(), O.ft_force(cfg.beta, flow_o, x).numpy()) < REL
+    y, lj = FT.flow_forward(x)
+    assert np.max(np.abs(y.numpy() - g["flow_fwd"])) < 1e-12 and relerr(lj.numpy(), g["logJ"]) < 1e-12
+    xi, lji = FT.flow_backward(y)
+    assert np.max(np.abs(xi.numpy() - g["flow_inv_of_fwd"])) < 1e-11
+    torch.manual_seed(21)
+    xn, m = FT.hmc(x)
+    torch.manual_seed(21)
+    xc = x.cuda()
+    v = torch.randn_like(xc).cpu()
+    h0 = O.ft_action(cfg.beta, flow_o, x) + 0.5 * (v * v).flatten(1).sum(-1)
+    x_, v_ = O.ft_leapfrog(cfg.beta, lf.dt, lf.nstep, flow_o, x, v)
+    x_ = torch.remainder(x_ + np.pi, 2 * np.pi) - np.pi
+    h1 = O.ft_action(cfg.beta, flow_o, x_) + 0.5 * (v_ * v_).flatten(1).sum(-1)
+    assert np.max(np.abs(m["dh"].cpu().numpy() - (h1 - h0).numpy())) < 1e-8
+    acc = m["acc"].cpu()
+    assert np.max(np.abs(xn.cpu().numpy() - torch.where(acc[:, None, None, None], x_, x).numpy())) < 1e-9
+    lm = FT.lattice_metrics(xn, torch.zeros(x.shape[0], dtype=torch.float64, device=xn.device))
+    assert lm["plaq"].shape == (x.shape[0],) and float(lm["plaq"].abs().max()) <= 1.0
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
