@@ -477,7 +477,13 @@ struct Engine {
     // -beta * sum cos P   (order 0: U1GaugeAction, order 1: hmc_2dU1.action)
     FT_PHASE double wilson_action(double beta, int order) {
         double acc = 0.0;
-        for (int i = ex.tid(); i < V; i += ex.nt()) { int n0, n1; site_map(i, n0, n1); acc += cos(plaq(oX, n0, n1, order)); }
+        const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1;
+        int n0 = ex.tid() / L1, n1 = ex.tid() - n0 * L1;
+        if constexpr (CL) n0 += rk * H;
+        for (int i = ex.tid(); i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            acc += cos(plaq(oX, n0, n1, order));
+        }
         return -beta * ex.sum(acc);
     }
     // floor(0.1 + sum regularize(P) / 2pi)   hmc_2dU1.py:123-124
@@ -502,10 +508,15 @@ struct Engine {
             return;
         }
         double* S = sm(oS);                              // scratch plane, pitch L1
-        for (int i = ex.tid(); i < V; i += ex.nt()) S[i] = sin(plaq(oX, i / L1, i % L1, order));
+        // (n0, n1) of the sites a thread visits advance without divisions: i += nt  <=>  n0 += nt / L1, n1 += nt % L1
+        const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1, s0 = ex.tid() / L1, s1 = ex.tid() - s0 * L1;
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            S[i] = sin(plaq(oX, n0, n1, order));
+        }
         ex.sync();
-        for (int i = ex.tid(); i < V; i += ex.nt()) {
-            int n0 = i / L1, n1 = i % L1;
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
             int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
             double s = S[i];
             *xat(oGR, 0, n0, n1) = beta * (s - S[n0 * L1 + n1m]);
