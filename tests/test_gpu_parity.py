@@ -522,6 +522,24 @@ def test_field_transformation_class(golden):
     assert lm["plaq"].shape == (x.shape[0],) and float(lm["plaq"].abs().max()) <= 1.0
 
 
+def test_statistical_known_answers():
+    """The reference's recorded physics: <cos P> = I1(beta)/I0(beta) (PLAQ_EXACT, fthmc/config.py:37-47:
+    0.69777 at beta=2) and <Q^2> = 1.23 +- 0.02 at L=8, beta=2 (hmc_2dU1.py:661), from 2048 device-RNG chains of plain HMC
+    and of FT-HMC through the random-init flow.  Tolerances are > 5 sigma of the chain-to-chain spread."""
+    L, beta, B, ntraj = 8, 2.0, 2048, 80
+    P = ft.Param(beta=beta, lat=(L, L), tau=1.0, nstep=10)
+    x0 = torch.zeros(B, 2, L, L, dtype=torch.float64).cuda()
+    pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
+    for r in (ft.hmc_run_batch(P, x0, ntraj, seed=11), ft.ft_hmc_run_batch(P, pf, x0, ntraj, seed=12)):
+        tail = slice(ntraj // 2, None)
+        assert float(r["acc"][tail].double().mean()) > 0.8
+        assert abs(float(r["plaq"][tail].mean()) - 0.69777) < 2.5e-3
+        q = r["topo"][tail]
+        assert torch.equal(q, torch.round(q))
+        assert abs(float((q * q).mean()) - 1.23) < 0.08
+        assert abs(float(torch.exp(-r["dH"][tail]).mean()) - 1.0) < 0.02          # <exp(-dH)> = 1
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
