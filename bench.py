@@ -130,29 +130,71 @@ def run_reference(a):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock / power / throttle-reason samples of one GPU during the timed region: an in-process NVML polling
+    thread (no start-up lag, 20 ms period); falls back to an `nvidia-smi -lms` subprocess when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self._physical_index())], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append([str(self.index), str(sm), str(self.mx), str(pw)] +
+                                 ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
@@ -165,7 +207,7 @@ class Clocks:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,6 +250,11 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout must carry exactly ONE JSON line, but NCCL prints its version banner there: park the real stdout and
+    # point fd 1 at stderr for the whole run; the result line is written to the parked descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -338,7 +385,8 @@ def run_ours(a):
     line["stencils"] = stencil_rooflines(ft, P, hbm_peak, dev)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
