@@ -355,7 +355,7 @@ struct Engine {
     int* iters_out;                                    // optional global: bisection iterations per layer
     // transaction barriers of the bulk (TMA) copies.  barcnt[b] counts completed uses: the k-th use of a barrier is
     // waited with parity k & 1.  Thread 0 advances a counter only after a block barrier that follows every thread's wait.
-    enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, BAR_SO, NBAR };
+    enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, BAR_SO, BAR_H1, NBAR };
     int barcnt[NBAR];
 
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
@@ -1320,23 +1320,59 @@ struct Engine {
     // (s_1, s_2) and the pre-update active links: contiguous in the layer block, same order as OUT
     FT_HD void issue_so(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_SO, sm(oOUT), wsSO(l), 3 * VQ); }
 
+    // Training-mode adjoint of one layer: the input-gradient phases plus the weight-gradient GEMMs, with the saved
+    // activations staged through shared memory.  Plane use: A = h1(l) for ph_wgrad2, then act'(z1)(l) for ph_conv2T;
+    // B = act'(z2)(l) (single-buffered); C = h2(l) for ph_wgrad3.  Every copy has its own transaction barrier and is issued
+    // as soon as its destination is free; only act'(z1), which has to wait for ph_wgrad2 to release A, is exposed.
+    FT_HD void issue_plane(int bar, int off, const double* src, int n) { if (ex.tid() == 0) ex.bulk_load(bar, sm(off), src, n); }
+    FT_HD void layer_adjoint_train(int l) {
+        LayerGeom g = geom(l);
+        ph_outgrad(g);                                        // waits for so/sv(l)
+        wait_bar(BAR_D2B); wait_bar(BAR_W);
+        ex.lsync();
+        advance_bar(BAR_D2B); advance_bar(BAR_W); advance_bar(BAR_SO);
+        wait_bar(BAR_D2C);                                    // h2(l) has landed in C
+        ph_wgrad3(g, sm(oC), gslice(l));
+        ph_conv3T(g, oB);
+        ex.lsync();
+        advance_bar(BAR_D2C);
+        issue_so(l - 1);                                      // OUT and C are free
+        if (l >= 1) issue_plane(BAR_D2C, oC, wsH2(l - 1), NH * sB);
+        wait_bar(BAR_H1);                                     // h1(l) has landed in A
+        ph_wgrad2(g, oB, sm(oA), gslice(l));
+        ex.lsync();
+        advance_bar(BAR_H1);
+        issue_plane(BAR_D1, oA, wsD1(l), NH * sA);            // act'(z1)(l) replaces h1(l)
+        ph_conv2T(g, oB);
+        ex.lsync();
+        advance_bar(BAR_D1);
+        if (l >= 1) issue_plane(BAR_D2B, oB, wsD2(l - 1), NH * sB);
+        ph_wgrad1(g, gslice(l));
+        ph_conv1T(g);
+        ex.lsync();
+        advance_bar(BAR_CS);
+        issue_weights(l - 1, true);
+        if (l >= 1) issue_plane(BAR_H1, oA, wsH1(l - 1), NH * sA);
+        issue_cs(l - 1);
+        ph_scatter(g);
+        ex.sync();
+    }
+
     // in flight on entry: d2(l) [, d2(l-1)], Wt(l), d1(l), cs(l)
     template <bool TRAIN = false> FT_HD void layer_adjoint(int l) {
+        if (TRAIN) { layer_adjoint_train(l); return; }
         LayerGeom g = geom(l);
         FT_T(PF_OUTGRAD, ph_outgrad(g);            // waits for so/sv(l)
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
              ex.lsync();                           // (restored links / GR reads cross ranks, but are ordered by the cluster barriers around)
              advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
-        if (TRAIN) ph_wgrad3(g, wsH2(l), gslice(l));                 // OUT = (s1bar, s2bar, tbar) is complete and intact
         FT_T(PF_CONV3T, ph_conv3T(g, zbuf(l)); ex.lsync());
-        if (TRAIN) ph_wgrad2(g, zbuf(l), wsH1(l), gslice(l));        // zbar2 complete; reads it only
         FT_T(PF_ISSUE, issue_so(l - 1));           // OUT is free again
         if constexpr (CL) { push_halo_zbar2(g, zbuf(l)); ex.sync(); }
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.lsync();
              advance_bar(BAR_D1));
         FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
-        if (TRAIN) ph_wgrad1(g, gslice(l));                          // zbar1 complete in A; reads A and CS only
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
              ex.lsync();
              advance_bar(BAR_CS));
@@ -1383,11 +1419,19 @@ struct Engine {
         ex.proxy_fence();                 // the layer blocks just written are read back by bulk copies (async proxy)
         ex.sync();
         const int last = pr.nlayers - 1;
-        FT_T(PF_ISSUE, issue_d2(last);
-             issue_d2(CL ? -1 : last - 1);
-             issue_weights(last, true);
-             issue_d1(last);
-             issue_cs(last));
+        if (TRAIN) {
+            issue_plane(BAR_D2B, oB, wsD2(last), NH * sB);
+            issue_weights(last, true);
+            issue_plane(BAR_H1, oA, wsH1(last), NH * sA);
+            issue_plane(BAR_D2C, oC, wsH2(last), NH * sB);
+            issue_cs(last);
+        } else {
+            FT_T(PF_ISSUE, issue_d2(last);
+                 issue_d2(CL ? -1 : last - 1);
+                 issue_weights(last, true);
+                 issue_d1(last);
+                 issue_cs(last));
+        }
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         FT_T(PF_ISSUE, issue_so(last));
         for (int l = last; l >= 0; --l) layer_adjoint<TRAIN>(l);
@@ -1398,8 +1442,8 @@ struct Engine {
     // weight gradients (flow training, ipynb/ft_hmc.py:253-295: d/dweights of sum_b [S(F(x_b)) - sum logJ]), accumulated
     // next to the input-gradient sweep.  Each is a GEMM with K = sites on the fp64 tensor path:
     //     D[8 output channels o][8 columns] += A[o][4 consecutive rows of one plane column] * B[those 4 sites][columns]
-    // with the adjoint signal (OUT, zbar2, zbar1; shared memory) as A and the saved activations (h2, h1 from the layer
-    // block in L2 -- no shared memory is left for them; cos/sin planes) as B.  One accumulator tile per kernel tap.
+    // with the adjoint signal (OUT, zbar2, zbar1; shared memory) as A and the saved activations (h2, h1: bulk-copied from
+    // the layer block into the planes C and A by layer_adjoint_train; cos/sin planes) as B.  One accumulator tile per kernel tap.
     // Every warp sums its share of the K chunks in registers and adds the result to ITS OWN slice of the CTA's gradient
     // buffer (no atomics; the host-side reduction over (CTA, warp) slices is in a fixed order).
     // =============================================================================================
