@@ -462,7 +462,7 @@ struct Engine {
             g[gi] = src[si];
         }
     }
-    // stage layer l's weights (cp.async, one commit group): the forward part [0,OFF_W3T) for the
+    // stage layer l's weights (one TMA bulk copy on BAR_W): the forward part [0,OFF_W3T) for the
     // forward/reverse sweeps, the transposed part [OFF_W3T,PACK) for the adjoint sweep
     FT_HD void issue_weights(int l, bool transposed) {
         const int lo = transposed ? OFF_W3T : 0, n = transposed ? PACK_DOUBLES - OFF_W3T : OFF_W3T;
