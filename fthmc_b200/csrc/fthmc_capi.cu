@@ -1,7 +1,9 @@
 // fthmc_capi.cu -- sm_100a kernels and the C ABI of libfthmc_b200.so (declared in include/fthmc_b200.h).
 //
-//   k_chain          persistent one-CTA-per-chain kernel: every flow / trajectory entry point
-//   k_action_topo    streaming Wilson action / topological charge  (HBM bound)
+//   k_chain          persistent one-CTA-per-chain kernel: every flow / trajectory / run-loop / training-gradient entry point
+//   k_chain_cluster  the same engine with one thread-block cluster (up to 16 CTAs, DSMEM halos) per chain: L = 48 .. 128
+//   k_grad_reduce    fixed-order sum of the per-(CTA, warp) weight-gradient slices
+//   k_action_topo    streaming Wilson action / topological charge, cluster-reduced per chain  (HBM bound)
 //   k_force          streaming Wilson force with a shared-memory sin(P) tile (HBM bound)
 //   k_regularize     elementwise wrap
 //

@@ -214,3 +214,23 @@ def test_weight_gradient_matches_autograd(shape, act):
     g = g_ref.numpy()
     for l in range(g.shape[0]):
         assert relerr(o["grad"][l], g[l]) < 1e-9, l
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 4), (1, 4, 8), (1, 8, 4)])
+def test_minimal_lattices(shape):
+    """L = 4: a single stripe group per orientation, every neighbour access wraps onto the group itself."""
+    import torch
+    from oracle import fthmc_oracle as O
+    B, L0, L1 = shape
+    flow = O.random_flow(n_layers=8, seed=3, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()])
+                                    for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    torch.manual_seed(8)
+    x = torch.empty(B, 2, L0, L1).uniform_(-np.pi, np.pi)
+    y, lj = O.ft_flow_logJ(flow, x)
+    o = E.run("flow_fwd", raw, x.numpy())
+    assert np.max(np.abs(o["field"] - y.numpy())) < 1e-12 and relerr(o["s"], lj.numpy()) < 1e-11
+    assert relerr(E.run("ft_force", raw, x.numpy(), beta=2.0)["field"], O.ft_force(2.0, flow, x).numpy()) < 1e-10
+    inv = E.run("flow_inv", raw, y.numpy())["field"]
+    for b in range(B):                   # the reference's stop test spans the whole tensor: compare chain by chain
+        assert np.max(np.abs(inv[b] - O.ft_flow_inv(flow, y[b:b + 1])[0].numpy())) < 1e-10

@@ -205,7 +205,7 @@ def module_like(g):
 
 
 # ---------------------------------------------------------------- fresh inputs vs the oracle
-@pytest.mark.parametrize("shape", [(3, 8, 8), (2, 8, 12), (2, 16, 16), (1, 12, 20)])
+@pytest.mark.parametrize("shape", [(2, 4, 4), (1, 4, 8), (3, 8, 8), (2, 8, 12), (2, 16, 16), (1, 12, 20), (1, 24, 40)])
 @pytest.mark.parametrize("act", ["silu", "leaky_relu", "relu"])
 def test_flow_vs_oracle_fresh(shape, act):
     B, L0, L1 = shape
