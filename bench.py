@@ -383,6 +383,16 @@ def run_ours(a):
             "observables": {"plaq": float(obs_h[0] / obs_h[6]), "acc_rate": float(obs_h[3] / obs_h[6]),
                             "mean_dH": float(obs_h[4] / obs_h[6]), "Q2": float(obs_h[2] / obs_h[6])}}
     line["stencils"] = stencil_rooflines(ft, P, hbm_peak, dev)
+    # supplementary: tau=1 / nstep=10 from a hot start has dH ~ 11 and accepts nothing; the same
+    # workload at an nstep that accepts (40) shows the sampler doing physics.  One untimed warm-up, one timed launch.
+    P40 = ft.Param(beta=a.beta, lat=(L, L), tau=a.tau, nstep=40)
+    ft.ft_hmc_batch(P40, pf, x, seed=7, traj=0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r40 = ft.ft_hmc_batch(P40, pf, x, seed=7, traj=1)
+    e1.record(); torch.cuda.synchronize()
+    line["nstep40"] = {"nstep": 40, "value": B / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "acc_rate": float(r40["acc"].double().mean()),
+                       "mean_dH": float(r40["dH"].mean()), "mean_exp_mdH": float(r40["exp_mdH"].mean())}
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     sys.stdout.flush()
