@@ -540,6 +540,27 @@ def test_statistical_known_answers():
         assert abs(float(torch.exp(-r["dH"][tail]).mean()) - 1.0) < 0.02          # <exp(-dH)> = 1
 
 
+def test_bitwise_reproducibility():
+    """Same inputs, same bits: the resident-chain kernels have fixed reduction orders (no atomics), on the single-CTA
+    path, the cluster path (DSMEM halos, cluster-wide reductions) and in the weight-gradient mode.  A missing barrier
+    shows up here as run-to-run differences."""
+    pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
+    for L, B in ((32, 300), (64, 40), (128, 9)):
+        gen = torch.Generator().manual_seed(L)
+        x = ((torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+        P = ft.Param(beta=4.0, lat=(L, L), tau=0.5, nstep=3)
+        ref = ft.ft_hmc_batch(P, pf, x, seed=5, traj=2)
+        for _ in range(3):
+            r = ft.ft_hmc_batch(P, pf, x, seed=5, traj=2)
+            assert torch.equal(r["field"], ref["field"]) and torch.equal(r["dH"], ref["dH"]) and torch.equal(r["topo"], ref["topo"])
+    x = torch.rand(200, 2, 32, 32, dtype=torch.float64, device="cuda") * 2 * np.pi
+    P = ft.Param(beta=4.0, lat=(32, 32))
+    a0, g0 = ft.ft_action_grad(P, pf, x)
+    for _ in range(3):
+        a1, g1 = ft.ft_action_grad(P, pf, x)
+        assert torch.equal(a0, a1) and torch.equal(g0, g1)
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
