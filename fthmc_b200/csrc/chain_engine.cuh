@@ -1642,6 +1642,55 @@ FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, For
     }
 }
 
+// Plain-HMC leapfrog (hmc_2dU1.py:132-141) with everything on chip: the momenta live in the (otherwise unused) gradient
+// plane, and every MD step is two phases -- S = sin(plaquette), then per SITE the force of its two links from S, the
+// momentum update and the position update -- with division-free site stepping.  Same operations in the same order as
+// leapfrog_resident + wilson_force (bit-identical results), without the per-step trips of the momenta through L2, the
+// separate gradient plane and a third barrier.  Single-CTA chains only; clusters use the generic path.
+template <class E>
+FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep, double* Pg) {
+    auto& ex = en.ex;
+    const int L0 = en.L0, L1 = en.L1, LP = en.LP, V = en.V;
+    const double hdt = 0.5 * dt;
+    double* X = en.sm(en.oX);
+    double* P = en.sm(en.oGR);                               // momenta, same pitch as X
+    double* S = en.sm(en.oS);
+    const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1, s0 = ex.tid() / L1, s1 = ex.tid() - s0 * L1;
+    // rows of the (2 L0, L1) link matrix: row = mu * L0 + n0
+    for (int i = ex.tid(), row = s0, n1 = s1; i < 2 * V; i += ex.nt(), row += d0, n1 += d1) {
+        if (n1 >= L1) { n1 -= L1; ++row; }
+        const double p = Pg[i];
+        P[row * LP + n1] = p;
+        X[row * LP + n1] = X[row * LP + n1] + hdt * p;
+    }
+    ex.sync();
+    for (int st = 0; st < nstep; ++st) {
+        const double step = st == nstep - 1 ? hdt : dt;
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            S[i] = sin(en.plaq(en.oX, n0, n1, 1));
+        }
+        ex.sync();
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            const int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+            const double sv = S[i];
+            const double f0 = beta * (sv - S[n0 * L1 + n1m]), f1 = beta * (S[n0m * L1 + n1] - sv);
+            const int i0 = n0 * LP + n1, i1 = (L0 + n0) * LP + n1;
+            const double p0 = P[i0] + (-dt) * f0, p1 = P[i1] + (-dt) * f1;
+            P[i0] = p0; P[i1] = p1;
+            X[i0] = X[i0] + step * p0;
+            X[i1] = X[i1] + step * p1;
+        }
+        ex.sync();
+    }
+    for (int i = ex.tid(), row = s0, n1 = s1; i < 2 * V; i += ex.nt(), row += d0, n1 += d1) {
+        if (n1 >= L1) { n1 -= L1; ++row; }
+        Pg[i] = P[row * LP + n1];
+    }
+    ex.sync();
+}
+
 // FT-HMC trajectory (ipynb/ft_hmc.py:420-435)
 template <class E>
 FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
@@ -1715,7 +1764,8 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     k0 = ex.sum(k0);
     double s0 = en.wilson_action(io.beta, 1);
     double h0 = s0 + 0.5 * k0;
-    leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.wilson_force(io.beta, 1); });
+    if constexpr (E::kCluster) leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.wilson_force(io.beta, 1); });
+    else leapfrog_plain_fused(en, io.beta, io.dt, io.nstep, P);
     en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;

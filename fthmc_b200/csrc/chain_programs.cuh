@@ -94,7 +94,8 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
         if (a.mode == MODE_FT_LEAPFROG)
             leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.ft_force(a.beta); });
         else
-            leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
+            if constexpr (E::kCluster) leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
+            else leapfrog_plain_fused(en, a.beta, a.dt, a.nstep, en.wsP);
         en.store_field(fout, en.oX);
         en.for_links([&](int, int gi) { a.p_out[(size_t)b * fs + gi] = en.wsP[gi]; });
         ex.sync();
@@ -125,6 +126,47 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
         }
     } break;
     default: break;
+    }
+}
+
+// the plain-HMC programs only (no flow): what k_chain_plain runs.  Same code as the corresponding cases of run_chain, but
+// a kernel that contains nothing else needs a fifth of the registers and several CTAs fit on an SM.
+template <class E>
+FT_HD void run_chain_plain(Engine<E>& en, const ChainArgs& a, int b) {
+    E& ex = en.ex;
+    const size_t fs = (size_t)2 * en.Vg;
+    const double* fin = a.field_in + (size_t)b * fs;
+    double* fout = a.field_out ? a.field_out + (size_t)b * fs : nullptr;
+    ex.sync();
+    if (a.mode == MODE_LEAPFROG) {
+        en.load_field(en.oX, fin);
+        en.for_links([&](int, int gi) { en.wsP[gi] = a.p_in[(size_t)b * fs + gi]; });
+        ex.sync();
+        if constexpr (E::kCluster) leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
+        else leapfrog_plain_fused(en, a.beta, a.dt, a.nstep, en.wsP);
+        en.store_field(fout, en.oX);
+        en.for_links([&](int, int gi) { a.p_out[(size_t)b * fs + gi] = en.wsP[gi]; });
+        ex.sync();
+        return;
+    }
+    const int nt = a.ntraj < 1 ? 1 : a.ntraj;
+    for (int t = 0; t < nt; ++t) {
+        const size_t row = (size_t)t * a.B + b;
+        TrajIO io;
+        io.field_in = fin; io.field_out = fout;
+        io.p_in = a.p_in ? a.p_in + row * fs : nullptr;
+        io.u_in = a.u_in ? a.u_in + row : nullptr;
+        io.p_out = (a.p_out && t == nt - 1) ? a.p_out + (size_t)b * fs : nullptr;
+        io.seed = a.seed; io.chain = a.chain0 + (uint64_t)b; io.traj = a.traj + (uint64_t)t;
+        io.beta = a.beta; io.dt = a.dt; io.nstep = a.nstep;
+        io.out_dH = a.s_out ? a.s_out + row : nullptr;
+        io.out_expmdH = a.expmdH ? a.expmdH + row : nullptr;
+        io.out_acc = a.acc ? a.acc + row : nullptr;
+        io.out_plaq = a.plaq ? a.plaq + row : nullptr;
+        io.out_Q = a.topo ? a.topo + row : nullptr;
+        io.out_h0 = nullptr; io.out_h1 = nullptr;
+        io.first = t == 0; io.last = t == nt - 1;
+        hmc_trajectory(en, io);
     }
 }
 

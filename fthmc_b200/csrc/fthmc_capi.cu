@@ -269,6 +269,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
     cl.sync();                                   // no CTA may exit while a peer can still address its shared memory
 }
 
+// plain HMC / leapfrog only: no flow phases in the kernel, a quarter of the registers, four CTAs per SM
+__global__ void __launch_bounds__(256, 4) k_chain_plain(const ChainArgs a) {
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<CtaExec>)];
+    Engine<CtaExec>* en = reinterpret_cast<Engine<CtaExec>*>(en_buf);
+    if (threadIdx.x == 0) {
+        CtaExec ex{ fthmc_dyn_smem };
+        new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
+        en->gW = nullptr;
+    }
+    __syncthreads();
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain_plain(*en, a, b);
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
     // the engine object lives in (static) shared memory: its members are read by every noinline phase
@@ -583,8 +597,9 @@ static int chain_resident(int L0, int L1, bool flow, int nr) {
     const int nt = chain_threads(L0, L1, flow, nr);
     if (nr == 1) {
         int occ = 1;
-        cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(false));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain, nt, smem) != cudaSuccess || occ < 1) occ = 1;
+        auto kern = flow ? k_chain : k_chain_plain;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(false));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem) != cudaSuccess || occ < 1) occ = 1;
         return d.sm * occ;
     }
     cudaFuncSetAttribute(k_chain_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(true));
@@ -667,7 +682,8 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
     if (train) CK(cudaMemsetAsync(a.gbuf, 0, (size_t)chains * a.gbuf_stride * sizeof(double), (cudaStream_t)stream));
     const size_t smem = chain_smem_bytes(L0, L1, has_flow, nr);
     if (nr == 1) {
-        k_chain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
+        if (has_flow) k_chain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
+        else k_chain_plain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(chains * nr); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

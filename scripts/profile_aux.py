@@ -12,9 +12,14 @@ if what == "stencils":
     for _ in range(2):
         ft.action(P, x); ft.topocharge(x); ft.force(P, x); ft.regularize(x)
     torch.cuda.synchronize()
-else:
+elif what == "grad":
     pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
     P = ft.Param(beta=4.0, lat=(32, 32))
     x = torch.rand(148, 2, 32, 32, dtype=torch.float64, device="cuda") * 2 * np.pi
     ft.ft_action_grad(P, pf, x)
+    torch.cuda.synchronize()
+if what == "plain":
+    P = ft.Param(beta=2.0, lat=(32, 32), tau=1.0, nstep=10)
+    xb = ((torch.rand(740 * 4, 2, 32, 32, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+    ft.hmc_run_batch(P, xb, 2, seed=1)
     torch.cuda.synchronize()
