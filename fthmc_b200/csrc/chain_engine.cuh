@@ -1,13 +1,20 @@
 // chain_engine.cuh -- one Markov chain's FT-HMC state machine, resident in shared memory.
 //
-// One CTA owns one chain.  The chain's link field, the gradient (force) field and every CNN
-// activation plane live in shared memory for the whole call; HBM/L2 is touched only to load/store
-// the field at the boundaries and for a small per-CTA workspace (momenta, saved active links).
+// One CTA (or, for lattices beyond one SM, one thread-block cluster) owns one chain.  The chain's link
+// field, the gradient (force) field and every CNN activation plane live in shared memory for the whole
+// call; HBM/L2 is touched only to load/store the field at the boundaries and for the per-chain workspace
+// (momenta, and the layer blocks the forward sweep of ft_force leaves for its adjoint sweep).
 //
 // The code is written as block-cooperative *phases*: each phase is a strided loop over "tasks"
-// (task = one row of one 4-column stripe group) followed by a barrier.  Every phase is correct
-// for ANY thread count, including 1: that is what lets tests/emul compile this same header with
-// g++ and run it serially on the CPU (test infrastructure only; the product is the CUDA build).
+// (task = one row of one 4-column stripe group; the tensor-core phases: one 8-row tile per warp)
+// followed by a barrier.  Every phase is correct for ANY thread count, including 1, and the warp-level
+// phases carry their lanes in arrays (FT_LANES): that is what lets tests/emul compile this same header
+// with g++ and run it on the CPU (test infrastructure only; the product is the CUDA build).
+//
+// Contents: scalar helpers (exp_fast, activations, Philox) | Engine: geometry and field access, Wilson
+// pieces, coupling-layer phases (planes, conv1, conv2 [DFMA and DMMA forms], conv3 forward / reverse), adjoint
+// phases (outgrad, conv3^T, conv2^T, conv1^T, scatter), TMA prefetch and the per-layer sweeps, weight-gradient
+// phases (training) | trajectory programs (leapfrog, ft_hmc, hmc).
 //
 // Reference semantics (paths relative to nftqcd/fthmc):
 //   coupling layer forward/reverse  ipynb/field_transformation.py:152-174, 288-338
@@ -314,7 +321,7 @@ struct EngineParams {
     int train;             // 1: the forward sweep also saves the activations h1, h2 and the adjoint accumulates weight gradients
 };
 
-// Shared-memory arena (doubles) of one rank; V = sites per rank.  Flow: X GR | CS UA OUT | A(8V) B(6V) C(6V) | W.
+// Shared-memory arena (doubles) of one rank; V = sites per rank.  Flow: X GR | CS UA OUT | A B C (8 channels each, padded) | W.
 // Plain HMC: X GR | S(V).
 FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true, int nr = 1) {
     size_t V = (size_t)L0 * L1 / nr, LP = L1 + 1, H = L0 / nr;
