@@ -85,6 +85,8 @@ def _back(out, like):
     """result on the device `like` lives on.  Host results land in page-locked memory (torch's caching host
     allocator recycles the blocks), so a D2H copy runs at link speed and a result that is fed back as the next
     input -- the run loops do exactly that with the field -- is also a fast H2D source."""
+    if out.is_floating_point() and like.is_floating_point() and out.dtype != like.dtype:
+        out = out.to(like.dtype)          # fp32 callers (the package copy's default dtype) get fp32 back; the kernels compute in fp64
     if like.is_cuda:
         return out
     host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)

@@ -561,6 +561,23 @@ def test_bitwise_reproducibility():
         assert torch.equal(a0, a1) and torch.equal(g0, g1)
 
 
+def test_float32_callers_get_float32_back():
+    """The package copy runs in fp32 by default (fthmc/config.py:25-31): fp32 tensors are accepted by every flow entry
+    point, computed in fp64 on the device and returned as fp32 (agreement with the fp64 result at fp32 resolution)."""
+    flow = O.random_flow(n_layers=4, seed=9)
+    pf = ft.PackedFlow(_raw_of(flow))
+    x64 = (torch.rand(2, 2, 8, 8, dtype=torch.float64) * 2 - 1) * np.pi
+    x32 = x64.float()
+    P = ft.Param(beta=2.0, lat=(8, 8), tau=0.2, nstep=2)
+    y32 = ft.ft_flow(pf, x32)
+    assert y32.dtype == torch.float32
+    assert float((y32.double() - ft.ft_flow(pf, x32.double())).abs().max()) < 1e-6
+    assert ft.ft_force(P, pf, x32).dtype == torch.float32 and ft.ft_action(P, pf, x32).dtype == torch.float32
+    r = ft.ft_hmc_batch(P, pf, x32.cuda(), seed=1)
+    assert r["field"].dtype == torch.float32 and r["field"].is_cuda and r["acc"].dtype == torch.bool
+    assert ft.action(P, x32[0]).dtype == torch.float32        # the stencils have native fp32 kernels
+
+
 def test_errors_are_loud():
     P = ft.Param(beta=1.0, lat=(6, 6))
     with pytest.raises(ft.FthmcError) as e:
