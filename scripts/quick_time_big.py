@@ -1,4 +1,5 @@
-"""Timing of the cluster path (development aid): ft_force / ft_hmc at L=64 and L=128."""
+"""Timing across lattice sizes: BASELINE config 2 (L=16, 64 chains) and a full batch at L=16, the cluster path at L=64 and
+L=128 (config 4), one wave at L=32."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +14,7 @@ def timeit(fn, n=2):
     return min(ts)
 
 pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
-for L, Bs in ((64, (33, 66)), (128, (7, 14)), (32, (148,))):
+for L, Bs in ((16, (64, 4096)), (64, (33, 66)), (128, (7, 14)), (32, (148,))):
     P = ft.Param(beta=6.0, lat=(L, L), tau=1.0, nstep=10)
     for B in Bs:
         x = ((torch.rand(B, 2, L, L, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
