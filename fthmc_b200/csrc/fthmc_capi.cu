@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <new>
@@ -558,12 +559,28 @@ static DevInfo& devinfo() {
     return d;
 }
 
-static int chain_threads(int L0, int L1, bool flow, int nr) {
+// one thread per task (a task = one row of one stripe group; plain HMC: one site)
+static int chain_threads_narrow(int L0, int L1, bool flow, int nr) {
     int tasks = (flow ? (L0 * L1) / 4 : L0 * L1) / nr;
     if (flow && FT_THREADS > 256) tasks *= 2;           // the two big convolutions split their tasks by channel pairs
     int nt = ((tasks + 31) / 32) * 32;
     return nt < 32 ? 32 : (nt > FT_THREADS ? FT_THREADS : nt);
 }
+// the tensor-core phases hand one 8-row tile of a stripe group to a warp: a warp per tile (the other phases leave the
+// extra warps idle) shortens a chain's critical path on lattices whose task count is below 256
+static int chain_threads_wide(int L0, int L1, bool flow, int nr) {
+    int nt = chain_threads_narrow(L0, L1, flow, nr);
+    if (flow && (L0 & 7) == 0 && (L1 & 7) == 0) {
+        const int tiles = ((L0 > L1 ? L0 : L1) / 8) * ((L0 < L1 ? L0 : L1) / 4) / nr;      // max over the two orientations of G * R/8
+        if (32 * tiles > nt) nt = 32 * tiles;
+    }
+    return nt > FT_THREADS ? FT_THREADS : nt;
+}
+static int chain_occupancy(int nt, size_t smem, bool flow);
+// Threads per CTA for a batch of B chains.  Wide blocks cost registers, i.e. co-resident CTAs: take them when that costs
+// nothing (shared memory already limits the SM to as few CTAs) or when the whole batch is resident at once anyway
+// (latency matters, not throughput).
+static int chain_threads(int L0, int L1, bool flow, int nr, int B);
 static size_t chain_smem_bytes(int L0, int L1, bool flow, int nr) { return (engine_smem_doubles(L0, L1, flow, nr) + 64) * sizeof(double); }
 
 // static shared memory of the chain kernels (the engine object), which counts against the per-block opt-in limit
@@ -591,17 +608,28 @@ static int chain_ranks(int L0, int L1, bool flow) {
 }
 
 // number of chains (CTAs, or clusters) resident at once on the device
-static int chain_resident(int L0, int L1, bool flow, int nr) {
+static int chain_occupancy(int nt, size_t smem, bool flow) {
+    DevInfo& d = devinfo();
+    int occ = 1;
+    auto kern = flow ? k_chain : k_chain_plain;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(false));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem) != cudaSuccess || occ < 1) occ = 1;
+    return occ;
+}
+static int chain_threads(int L0, int L1, bool flow, int nr, int B) {
+    const int n0 = chain_threads_narrow(L0, L1, flow, nr), n1 = chain_threads_wide(L0, L1, flow, nr);
+    if (n1 == n0 || nr != 1) return n1;
+    DevInfo& d = devinfo();
+    if (!d.ok) return n0;
+    const size_t smem = chain_smem_bytes(L0, L1, flow, nr);
+    const int o0 = chain_occupancy(n0, smem, flow), o1 = chain_occupancy(n1, smem, flow);
+    return (o1 >= o0 || (long long)B <= (long long)d.sm * o1) ? n1 : n0;
+}
+static int chain_resident(int L0, int L1, bool flow, int nr, int B) {
     DevInfo& d = devinfo();
     const size_t smem = chain_smem_bytes(L0, L1, flow, nr);
-    const int nt = chain_threads(L0, L1, flow, nr);
-    if (nr == 1) {
-        int occ = 1;
-        auto kern = flow ? k_chain : k_chain_plain;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(false));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem) != cudaSuccess || occ < 1) occ = 1;
-        return d.sm * occ;
-    }
+    const int nt = chain_threads(L0, L1, flow, nr, B);
+    if (nr == 1) return d.sm * chain_occupancy(nt, smem, flow);
     cudaFuncSetAttribute(k_chain_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - chain_static_smem(true));
     cudaFuncSetAttribute(k_chain_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
@@ -628,10 +656,10 @@ static int check_lattice(int B, int L0, int L1, bool flow, int* nr_out) {
 
 // chains resident at once on this device for (lattice, flow): what the persistent grid will be; falls back to an upper
 // bound when no device can be queried
-static long long resident_bound(int L0, int L1, bool flow, int nr) {
+static long long resident_bound(int L0, int L1, bool flow, int nr, int B) {
     DevInfo& d = devinfo();
     if (d.ok) {
-        const int r = chain_resident(L0, L1, flow, nr);
+        const int r = chain_resident(L0, L1, flow, nr, B);
         if (r > 0) return r;
     }
     return nr == 1 ? (long long)(d.sm > 0 ? d.sm : 148) * 32 : (long long)(d.sm > 0 ? d.sm : 148) / nr;
@@ -641,7 +669,7 @@ extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1
     if (B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
     int nr = chain_ranks(L0, L1, flow != nullptr);
     if (nr == 0) nr = 1;
-    long long g = resident_bound(L0, L1, flow != nullptr, nr);
+    long long g = resident_bound(L0, L1, flow != nullptr, nr, B);
     if (B < g) g = B;
     if (g < 1) g = 1;
     return (size_t)g * engine_ws_doubles(L0, L1, flow ? flow->n_layers : 0, nr) * sizeof(double) + 256;
@@ -665,11 +693,11 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
     a.pr.train = train ? 1 : 0;
     if (train && (nr != 1 || (L0 & 7) || (L1 & 7)))
         return fail(FTHMC_E_LATTICE, "the weight-gradient path needs L0, L1 multiples of 8 and a lattice that fits one SM (L0*L1 <= 1024)");
-    int res = chain_resident(L0, L1, has_flow, nr);
+    int res = chain_resident(L0, L1, has_flow, nr, a.B);
     if (res < 1) return fail(FTHMC_E_LATTICE, "the device cannot co-schedule a thread-block cluster of the size this lattice needs");
     const int chains = a.B < res ? a.B : res;
     a.ws_stride = engine_ws_doubles(L0, L1, a.pr.nlayers, nr, train);
-    const int nt = chain_threads(L0, L1, has_flow, nr);
+    const int nt = chain_threads(L0, L1, has_flow, nr, a.B);
     size_t need = (size_t)chains * a.ws_stride * sizeof(double);
     if (train) {            // gradient accumulators behind the chain workspaces: [CTA][warp][layer][GRAD_DOUBLES]
         a.gbuf_stride = (size_t)(nt / 32) * a.pr.nlayers * GRAD_DOUBLES;
@@ -952,7 +980,7 @@ extern "C" int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, doubl
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t fthmc_grad_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
     if (!flow || B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
-    long long g = resident_bound(L0, L1, true, 1);
+    long long g = resident_bound(L0, L1, true, 1, B);
     if (B < g) g = B;
     if (g < 1) g = 1;
     return (size_t)g * (engine_ws_doubles(L0, L1, flow->n_layers, 1, true) + (size_t)(FT_THREADS / 32) * flow->n_layers * GRAD_DOUBLES)
