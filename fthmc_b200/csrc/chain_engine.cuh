@@ -742,6 +742,9 @@ struct Engine {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { acc0[k][ls] = b0; acc1[k][ls] = b1; }
             }
+#ifdef FT_PROFILE
+            long long tp0 = ex.clock();
+#endif
 #pragma unroll
             for (int c = 0; c < 18; ++c) {
                 const int tap = c >> 1, a = tap / 3, b = tap - 3 * a, hoff = 4 * (c & 1) * sA;
@@ -754,6 +757,9 @@ struct Engine {
                     ex.mma884(acc0[k], acc1[k], av, bf[c]);
                 }
             }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_MAC, ex.clock() - tp0); tp0 = ex.clock();
+#endif
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3;
                 const int i0 = 2 * j * sB + 3 * gi * R + rb + i;
@@ -776,6 +782,9 @@ struct Engine {
                     for (int e = 0; e < 6; ++e) B[i0 + (e & 1) * sB + (e >> 1) * R] = h[e];
                 }
             }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_ACT, ex.clock() - tp0);
+#endif
         }
     }
     template <int CH> FT_PHASE void ph_conv2_t(const LayerGeom g, double* d2_save) {
@@ -1137,6 +1146,9 @@ struct Engine {
                     acc0[q][ls] = 0.0; acc1[q][ls] = 0.0; d1a[q][ls] = p[0]; d1b[q][ls] = p[sA];
                 }
             }
+#ifdef FT_PROFILE
+            long long tq0 = ex.clock();
+#endif
 #pragma unroll
             for (int c = 0; c < 18; ++c) {
                 const int tap = c >> 1, a = tap / 3, b = tap - 3 * a, hoff = 4 * (c & 1) * sB;
@@ -1153,6 +1165,9 @@ struct Engine {
                     }
                 }
             }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2T_MAC, ex.clock() - tq0);
+#endif
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3;
 #pragma unroll
