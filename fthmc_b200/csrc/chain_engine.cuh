@@ -138,8 +138,7 @@ FT_HD double exp_fast(double x) {
     const double K[10] = FT_EXP_COEFS;
     static const double TAB[16] = FT_EXP_TABLE;
 #endif
-    const double t = x * K[6];                                               // 16 x / ln2
-    const double nm = t + K[7];                                              // rint(t) in the low mantissa bits
+    const double nm = fma(x, K[6], K[7]);                                    // rint(16 x / ln2) in the low mantissa bits
     const double n = nm - K[7];
     double r = fma(n, K[8], x);                                              // Cody-Waite: ln2/16 in two pieces
     r = fma(n, K[9], r);
