@@ -47,6 +47,10 @@
 #define FT_T(id, ...) do { __VA_ARGS__; } while (0)
 #endif
 
+#ifndef FT_WINOGRAD
+#define FT_WINOGRAD 1
+#endif
+
 // loop over the lanes a "thread" carries: exactly one iteration (its own lane) on the device, 32 in the serial emulation
 #define FT_LANES(ln, ls) for (int ls = 0, ln = ex.lane0(); ls < E::kLanes; ++ls, ++ln)
 
@@ -207,7 +211,7 @@ template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
 // derivative goes to the same index of the global layer block.  Blocks of U elements: all loads, then U
 // independent chains, then all stores (a load after a store to the same array would serialise them).
 template <int ACT, int N, class IndexFn> FT_HD void act_pass(double* buf, double* dsave, double* hsave, IndexFn index) {
-    constexpr int U = 4;
+    constexpr int U = 4;      // (blocks of 8, and a two-stage software pipeline of the exp / reciprocal halves, measured no faster)
     static_assert(N % U == 0, "element count must be a multiple of the block");
 #pragma unroll 1
     for (int e0 = 0; e0 < N; e0 += U) {
@@ -694,8 +698,17 @@ struct Engine {
     // tensor-core (DMMA) form of the two big convolutions: stripe lengths that are multiples of 8 (in cluster mode the
     // halo columns of a rank's first / last stripe group come from the halo buffers AH / ZH, channel stride 2R)
     FT_HD bool mma_ok() const { return (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
+    // Winograd F(2,3) along the stripe direction for the two big convolutions (single-CTA chains whose stripes split
+    // into 16-row blocks with at least one block per warp; -DFT_WINOGRAD=0 keeps the direct tensor-core form)
+    FT_HD bool wino_ok(const LayerGeom& g) const {
+        return FT_WINOGRAD && !CL && mma_ok() && (g.R & 15) == 0 && g.G * (g.R >> 4) >= ex.nwarps();
+    }
     FT_HD void ph_conv2(const LayerGeom g, double* d2_save, double* h2_save = nullptr) {
-        if (mma_ok()) {
+        if (wino_ok(g)) {
+            if (pr.act == ACT_SILU) ph_conv2_wino<ACT_SILU>(g, d2_save, h2_save);
+            else if (pr.act == ACT_LEAKY) ph_conv2_wino<ACT_LEAKY>(g, d2_save, h2_save);
+            else ph_conv2_wino<ACT_RELU>(g, d2_save, h2_save);
+        } else if (mma_ok()) {
             if (pr.act == ACT_SILU) ph_conv2_mma<ACT_SILU>(g, d2_save, h2_save);
             else if (pr.act == ACT_LEAKY) ph_conv2_mma<ACT_LEAKY>(g, d2_save, h2_save);
             else ph_conv2_mma<ACT_RELU>(g, d2_save, h2_save);
@@ -779,6 +792,111 @@ struct Engine {
                     for (int e = 0; e < 6; ++e) act_fwd_t<ACT>(z[e], h[e]);
 #pragma unroll
                     for (int e = 0; e < 6; ++e) B[i0 + (e & 1) * sB + (e >> 1) * R] = h[e];
+                }
+            }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_ACT, ex.clock() - tp0);
+#endif
+        }
+    }
+    // conv2 as Winograd F(2,3) along the rows of a stripe on the fp64 tensor path.  A pair of output rows (2i, 2i+1) of
+    // one column needs the input rows d0..d3 = 2i-1 .. 2i+2 of the three neighbouring columns:
+    //     t = (d0 - d2, d1 + d2, d2 - d1, d1 - d3),   u_b = (g0, (g0+g1+g2)/2, (g0-g1+g2)/2, g2)  (g_a = W[.][a][b][.]),
+    //     m_j = sum_{b, ci} t_j[ci][col+b-1] u_b,j[ci][o]   (4 GEMMs of depth 24 instead of 9 taps x 2 rows of depth 8),
+    //     out(2i) = m0 + m1 + m2,  out(2i+1) = m1 - m2 - m3.
+    // 4 DMMAs per (column tap, channel half) feed TWO rows: 24 DMMAs per 16 sites instead of 36.  One warp task = 8 row
+    // pairs of one stripe group, the three output columns (twelve accumulator tiles in flight); the transformed input
+    // fragments of a source column are built once (three loads, four DADD) and used by every output column that sees it.
+    // The transformed weight fragments are built from the packed forward weights at phase entry and stay in registers.
+    template <int ACT> FT_PHASE void ph_conv2_wino(const LayerGeom g, double* d2_save, double* h2_save) {
+        constexpr int NL = E::kLanes;
+        const double* A = sm(oA); const double* W = sm(oW);
+        double* B = sm(oB);
+        const int R = g.R, Cn = g.Cn, RB = R >> 4;
+        double bf[3][2][4][NL];                              // [column tap b][channel half][j]
+        FT_LANES(ln, ls) {
+            const int j = ln & 3, n = ln >> 2;               // B fragment: row j (input channel 4*half + j), column n (output channel)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const double* wp = W + OFF_W2F + ((4 * hf + j) * 9 + b) * NH + n;
+                    const double g0 = wp[0], g1 = wp[3 * NH], g2 = wp[6 * NH], gs = g0 + g2;
+                    bf[b][hf][0][ls] = g0; bf[b][hf][1][ls] = 0.5 * (gs + g1); bf[b][hf][2][ls] = 0.5 * (gs - g1); bf[b][hf][3][ls] = g2;
+                }
+        }
+        for (int st = ex.warp(); st < g.G * RB; st += ex.nwarps()) {
+            const int gi = st / RB, rb = 16 * (st - gi * RB);
+            int cc[5];                                       // columns 4g-2 .. 4g+2 (offsets in doubles)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) { const int c = 4 * gi - 2 + m; cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            double acc0[3][4][NL], acc1[3][4][NL];
+            int rm[NL], r1[NL], rp[NL];                      // lane (i, j): row pair i, channel j of the half
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3, r0 = rb + 2 * i;
+                rm[ls] = j * sA + (r0 == 0 ? R - 1 : r0 - 1);
+                r1[ls] = j * sA + r0;
+                rp[ls] = j * sA + (r0 + 2 == R ? 0 : r0 + 2);
+                const double b0 = W[OFF_B2 + 2 * j], b1 = W[OFF_B2 + 2 * j + 1];     // the bias rides on m1 (in both outputs with +1)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { acc0[k][m][ls] = m == 1 ? b0 : 0.0; acc1[k][m][ls] = m == 1 ? b1 : 0.0; }
+            }
+#ifdef FT_PROFILE
+            long long tp0 = ex.clock();
+#endif
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    double t[4][NL];
+                    FT_LANES(ln, ls) {
+                        const double* pc = A + cc[c] + 4 * hf * sA;
+                        const double d0 = pc[rm[ls]], d3 = pc[rp[ls]];
+                        const dbl2 d12 = ld2(pc + r1[ls]);
+                        t[0][ls] = d0 - d12.y; t[1][ls] = d12.x + d12.y; t[2][ls] = d12.y - d12.x; t[3][ls] = d12.x - d3;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int b = c - k;
+                        if (b >= 0 && b < 3) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) ex.mma884(acc0[k][m], acc1[k][m], t[m], bf[b][hf][m]);
+                        }
+                    }
+                }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2_MAC, ex.clock() - tp0); tp0 = ex.clock();
+#endif
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3;
+                const int i0 = 2 * j * sB + 3 * gi * R + rb + 2 * i;
+                double z[12], h[12], d[12];                  // element e = (k * 2 + channel parity) * 2 + row parity
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    z[4 * k + 0] = (acc0[k][0][ls] + acc0[k][1][ls]) + acc0[k][2][ls];
+                    z[4 * k + 1] = (acc0[k][1][ls] - acc0[k][2][ls]) - acc0[k][3][ls];
+                    z[4 * k + 2] = (acc1[k][0][ls] + acc1[k][1][ls]) + acc1[k][2][ls];
+                    z[4 * k + 3] = (acc1[k][1][ls] - acc1[k][2][ls]) - acc1[k][3][ls];
+                }
+                if (d2_save) {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) act_fwd_der_t<ACT>(z[e], h[e], d[e]);
+#pragma unroll
+                    for (int e = 0; e < 12; e += 2) {
+                        const int idx = i0 + ((e >> 1) & 1) * sB + (e >> 2) * R;
+                        st2(B + idx, h[e], h[e + 1]); st2(d2_save + idx, d[e], d[e + 1]);
+                    }
+                    if (h2_save) {
+#pragma unroll
+                        for (int e = 0; e < 12; e += 2) st2(h2_save + i0 + ((e >> 1) & 1) * sB + (e >> 2) * R, h[e], h[e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) act_fwd_t<ACT>(z[e], h[e]);
+#pragma unroll
+                    for (int e = 0; e < 12; e += 2) st2(B + i0 + ((e >> 1) & 1) * sB + (e >> 2) * R, h[e], h[e + 1]);
                 }
             }
 #ifdef FT_PROFILE
@@ -1103,7 +1221,8 @@ struct Engine {
 
     // zbar1 = conv2^T(zbar2) * act'(z1)  (in place in A, which holds act'(z1)); same task shape as ph_conv2
     FT_HD void ph_conv2T(const LayerGeom g, int oZ) {
-        if (mma_ok()) ph_conv2T_mma(g, oZ);
+        if (wino_ok(g)) ph_conv2T_wino(g, oZ);
+        else if (mma_ok()) ph_conv2T_mma(g, oZ);
         else if (fine_tasks()) ph_conv2T_t<2>(g, oZ);
         else ph_conv2T_t<4>(g, oZ);
     }
@@ -1174,6 +1293,85 @@ struct Engine {
                     double* p = A + 2 * j * sA + (4 * gi + q) * R + rb + i;
                     p[0] = acc0[q][ls] * d1a[q][ls];
                     p[sA] = acc1[q][ls] * d1b[q][ls];
+                }
+            }
+        }
+    }
+    // conv2^T in the same Winograd F(2,3) form: output row r reads source row r - a + 1, i.e. a row kernel flipped
+    // (g'_a' = W[2 - a']), so u' = (g2, (g0+g1+g2)/2, (g0-g1+g2)/2, g0).  One warp task = 8 row pairs of one stripe
+    // group, the four output columns (sixteen accumulator tiles); the five source slots feed 1,2,3,2,1 of them.
+    FT_PHASE void ph_conv2T_wino(const LayerGeom g, int oZ) {
+        constexpr int NL = E::kLanes;
+        const double* C = sm(oZ); const double* W = sm(oW);
+        double* A = sm(oA);
+        const int R = g.R, G = g.G, RB = R >> 4;
+        double bf[3][2][4][NL];                              // rows o = 4*half + j, columns ci = n
+        FT_LANES(ln, ls) {
+            const int j = ln & 3, n = ln >> 2;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const double* wp = W + OFF_W2T + ((4 * hf + j) * 9 + b) * NH + n;
+                    const double g0 = wp[0], g1 = wp[3 * NH], g2 = wp[6 * NH], gs = g0 + g2;
+                    bf[b][hf][0][ls] = g2; bf[b][hf][1][ls] = 0.5 * (gs + g1); bf[b][hf][2][ls] = 0.5 * (gs - g1); bf[b][hf][3][ls] = g0;
+                }
+        }
+        wait_bar(BAR_D1);                                    // act'(z1) has landed in A (issued a layer ago)
+        for (int st = ex.warp(); st < G * RB; st += ex.nwarps()) {
+            const int gi = st / RB, rb = 16 * (st - gi * RB);
+            const int gn = gi + 1 == G ? 0 : gi + 1;
+            // source column slots s = 0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1, 4g, 4g+1, 4g+3, 4g+4
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
+            double acc0[4][4][NL], acc1[4][4][NL];
+            int rm[NL], r1[NL], rp[NL];
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3, r0 = rb + 2 * i;
+                rm[ls] = j * sB + (r0 == 0 ? R - 1 : r0 - 1);
+                r1[ls] = j * sB + r0;
+                rp[ls] = j * sB + (r0 + 2 == R ? 0 : r0 + 2);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { acc0[q][m][ls] = 0.0; acc1[q][m][ls] = 0.0; }
+            }
+#ifdef FT_PROFILE
+            long long tq0 = ex.clock();
+#endif
+#pragma unroll
+            for (int s5 = 0; s5 < 5; ++s5)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    double t[4][NL];
+                    FT_LANES(ln, ls) {
+                        const double* pc = C + sc[s5] + 4 * hf * sB;
+                        const double d0 = pc[rm[ls]], d3 = pc[rp[ls]];
+                        const dbl2 d12 = ld2(pc + r1[ls]);
+                        t[0][ls] = d0 - d12.y; t[1][ls] = d12.x + d12.y; t[2][ls] = d12.y - d12.x; t[3][ls] = d12.x - d3;
+                    }
+                    const int co = s5 < 3 ? s5 - 1 : s5;     // source column relative to 4g: -1, 0, 1, 3, 4
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const int q = co + b - 1;            // the output column that sees this source through tap b
+                        if (q >= 0 && q < 4) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) ex.mma884(acc0[q][m], acc1[q][m], t[m], bf[b][hf][m]);
+                        }
+                    }
+                }
+#ifdef FT_PROFILE
+            ex.prof_add(PF_C2T_MAC, ex.clock() - tq0);
+#endif
+            FT_LANES(ln, ls) {
+                const int i = ln >> 2, j = ln & 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double* p = A + 2 * j * sA + (4 * gi + q) * R + rb + 2 * i;
+                    const dbl2 da = ld2(p), db = ld2(p + sA);     // act'(z1) of rows (2i, 2i+1), channels 2j and 2j+1
+                    st2(p, ((acc0[q][0][ls] + acc0[q][1][ls]) + acc0[q][2][ls]) * da.x,
+                           ((acc0[q][1][ls] - acc0[q][2][ls]) - acc0[q][3][ls]) * da.y);
+                    st2(p + sA, ((acc1[q][0][ls] + acc1[q][1][ls]) + acc1[q][2][ls]) * db.x,
+                                ((acc1[q][1][ls] - acc1[q][2][ls]) - acc1[q][3][ls]) * db.y);
                 }
             }
         }

@@ -234,3 +234,23 @@ def test_minimal_lattices(shape):
     inv = E.run("flow_inv", raw, y.numpy())["field"]
     for b in range(B):                   # the reference's stop test spans the whole tensor: compare chain by chain
         assert np.max(np.abs(inv[b] - O.ft_flow_inv(flow, y[b:b + 1])[0].numpy())) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["ft_L16_b6", "ft_L32_b4"])
+def test_tensor_core_winograd_phases(golden, name, monkeypatch):
+    """FT_EMUL_MMA switches the CPU build to the warp-fragment (DMMA) form of conv2 / conv2^T, which for stripes of
+    16k rows is the Winograd F(2,3) variant: same parity bars as the scalar form, and a teacher-forced trajectory."""
+    monkeypatch.setenv("FT_EMUL_MMA", "1")
+    g = golden(name)
+    x, w, beta = g["x"], g["weights"], float(g["beta"])
+    o = E.run("flow_fwd", w, x)
+    assert np.max(np.abs(o["field"] - g["flow_fwd"])) < 1e-12
+    assert np.max(np.abs(o["layer_logJ"] - g["layer_logJ"].T)) < 1e-11
+    o = E.run("ft_force", w, x, beta=beta)
+    assert relerr(o["field"], g["ft_force"]) < 1e-11
+    o = E.run("flow_inv", w, g["flow_fwd"])
+    assert np.max(np.abs(o["field"] - g["flow_inv_of_fwd"])) < 1e-11
+    o = E.run("ft_hmc", w, g["traj_x"], beta=beta, dt=float(g["dt"]), nstep=int(g["nstep"]), p=g["traj_p"], u=g["traj_u"])
+    assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["traj_acc"])
+    assert np.array_equal(o["topo"], g["traj_topo"])
