@@ -117,40 +117,46 @@ FT_HD double regularize1(double f) {
     return TWO_PI_D * (g - floor(g) - 0.5);
 }
 
-// e^x with ~1 ulp error for |x| <= 708 (finite and monotone-saturated beyond): x = (16 k + j) ln2/16 + r with |r| <= ln2/32, e^x = 2^k * 2^(j/16) * e^r.
-// 2^(j/16) comes from a 16-entry table (on the device: 128 bytes of shared memory, one bank each -- conflict free
-// for any index pattern), the power of two goes into its exponent bits with an integer add, and e^r - 1 needs a
-// degree-7 Taylor polynomial only (remainder r^8/8! < 1.3e-18).  8 fp64 operations after the range reduction instead of
-// the 14 of a degree-13 polynomial on |r| <= ln2/2: the SiLU evaluations are a fifth of the trajectory's run time.
+// e^x with ~1 ulp error for |x| <= 708 (finite and monotone-saturated beyond): x = (64 k + j) ln2/64 + r with |r| <= ln2/128, e^x = 2^k * 2^(j/64) * e^r.
+// 2^(j/64) comes from a 64-entry table (on the device: 512 bytes of shared memory), the power of two goes into its
+// exponent bits with an integer add, and e^r - 1 needs a degree-5 Taylor polynomial only (remainder r^6/6! < 3.5e-17).
+// 6 fp64 operations after the range reduction instead of the 14 of a degree-13 polynomial on |r| <= ln2/2: the SiLU
+// evaluations are a sixth of the trajectory's run time.
 // The scalar constants sit in constant memory on the device (a DFMA takes a constant-bank operand directly).
 //
-// CONTRACT with the kernels: doubles [16, 32) of the dynamic shared memory hold FT_EXP_TABLE (chain kernels copy it
-// there before any phase runs, see fthmc_capi.cu).
-#define FT_EXP_TABLE { 1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951, 1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429, 1.7562521603732995, 1.8340080864093424, 1.9152065613971474 }
-#define FT_EXP_COEFS { 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, \
-                       23.083120654223414517, 6755399441055744.0, -0.04332169877307024, -1.1926343307941173e-11 }
+// CONTRACT with the kernels: the dynamic shared memory starts with FT_SMEM_PREFIX doubles of scratch -- [0, 64) the
+// executors' reduction slots and transaction barriers, [64, 128) FT_EXP_TABLE (the chain kernels copy it there before
+// any phase runs, see fthmc_capi.cu); the engine's arena follows.
+constexpr int FT_SMEM_PREFIX = 128;
+constexpr int FT_EXP_TAB_OFF = 64;
+#define FT_EXP_TABLE { 1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, \
+                       1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, 1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, 1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, 1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, \
+                       1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, 1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, 1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, 1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, \
+                       1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, 1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, 1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951 }
+#define FT_EXP_COEFS { 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, \
+                       92.33248261689366, 6755399441055744.0, -0.04332169877307024 / 4, -1.1926343307941173e-11 / 4 }
 #ifdef __CUDACC__
-__constant__ double c_exp[10] = FT_EXP_COEFS;
-__constant__ double c_exp_tab[16] = FT_EXP_TABLE;
+__constant__ double c_exp[8] = FT_EXP_COEFS;
+__constant__ double c_exp_tab[64] = FT_EXP_TABLE;
 #endif
 FT_HD double exp_fast(double x) {
 #ifdef __CUDA_ARCH__
     const double* K = c_exp;
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
-    const double* TAB = fthmc_dyn_smem + 16;
+    const double* TAB = fthmc_dyn_smem + FT_EXP_TAB_OFF;
 #else
-    const double K[10] = FT_EXP_COEFS;
-    static const double TAB[16] = FT_EXP_TABLE;
+    const double K[8] = FT_EXP_COEFS;
+    static const double TAB[64] = FT_EXP_TABLE;
 #endif
-    const double nm = fma(x, K[6], K[7]);                                    // rint(16 x / ln2) in the low mantissa bits
-    const double n = nm - K[7];
-    double r = fma(n, K[8], x);                                              // Cody-Waite: ln2/16 in two pieces
-    r = fma(n, K[9], r);
-    double w = K[0];                                                         // e^r = 1 + r (1 + r w),  w = 1/2 + r/6 + ... + r^5/5040
+    const double nm = fma(x, K[4], K[5]);                                    // rint(64 x / ln2) in the low mantissa bits
+    const double n = nm - K[5];
+    double r = fma(n, K[6], x);                                              // Cody-Waite: ln2/64 in two pieces
+    r = fma(n, K[7], r);
+    double w = K[0];                                                         // e^r = 1 + r (1 + r w),  w = 1/2 + r/6 + r^2/24 + r^3/120
 #pragma unroll
-    for (int i = 1; i < 6; ++i) w = fma(w, r, K[i]);
+    for (int i = 1; i < 4; ++i) w = fma(w, r, K[i]);
     const double q = r * fma(r, w, 1.0);                                     // e^r - 1
-    // 2^k * 2^(j/16): k goes into the exponent bits of the table entry.  |x| <= 708 keeps the exponent in range; beyond
+    // 2^k * 2^(j/64): k goes into the exponent bits of the table entry.  |x| <= 708 keeps the exponent in range; beyond
     // that k saturates (integer min/max, off the critical path) so that the result stays finite and SiLU keeps its
     // limits (0 and z) instead of producing garbage bits.  A NaN propagates.
     int ni;
@@ -159,8 +165,8 @@ FT_HD double exp_fast(double x) {
 #else
     ni = (int)(long long)fmin(fmax(n, -2147483647.0), 2147483647.0);
 #endif
-    const double tj = TAB[ni & 15];
-    int k = ni >> 4;
+    const double tj = TAB[ni & 63];
+    int k = ni >> 6;
     k = k < -1022 ? -1022 : (k > 1021 ? 1021 : k);
     double sc;
 #ifdef __CUDA_ARCH__

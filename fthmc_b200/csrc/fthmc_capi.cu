@@ -62,13 +62,13 @@ struct CtaExec {
     __device__ long long clock() const { return clock64(); }
     __device__ void prof_add(int id, long long c) const { if (threadIdx.x == 0) atomicAdd(&g_prof[id], (unsigned long long)c); }
 #endif
-    double* red;   // 64 doubles of shared scratch (the first 64 doubles of the dynamic shared memory)
+    double* red;   // 64 doubles of shared scratch (the first 64 of the FT_SMEM_PREFIX doubles that open the dynamic shared memory)
     // base of the engine's arena.  Naming the extern __shared__ symbol here (instead of carrying a
     // generic pointer in the engine) lets nvcc emit LDS/STS rather than generic LD/ST in every phase.
     __host__ __device__ double* smem() const {
 #ifdef __CUDA_ARCH__
         extern __shared__ __align__(16) double fthmc_dyn_smem[];
-        return fthmc_dyn_smem + 64;
+        return fthmc_dyn_smem + FT_SMEM_PREFIX;
 #else
         return nullptr;
 #endif
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
         new (en) Engine<ClusterExec>(ex, a.pr, a.ws + (size_t)cid * a.ws_stride);
         en->gW = nullptr;                                    // (the training mode runs on the single-CTA path)
     }
-    if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) fthmc_dyn_smem[FT_EXP_TAB_OFF + i] = c_exp_tab[i];   // exp_fast's 2^(j/64) table (blocks may be one warp)
     __syncthreads();
     en->ex.bar_init(Engine<ClusterExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
         new (en) Engine<CtaExec>(ex, a.pr, a.ws + (size_t)blockIdx.x * a.ws_stride);
         en->gW = a.gbuf ? a.gbuf + (size_t)blockIdx.x * a.gbuf_stride : nullptr;
     }
-    if (threadIdx.x < 16) fthmc_dyn_smem[16 + threadIdx.x] = c_exp_tab[threadIdx.x];     // exp_fast's 2^(j/16) table
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) fthmc_dyn_smem[FT_EXP_TAB_OFF + i] = c_exp_tab[i];   // exp_fast's 2^(j/64) table (blocks may be one warp)
     __syncthreads();
     en->ex.bar_init(Engine<CtaExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
@@ -581,7 +581,7 @@ static int chain_occupancy(int nt, size_t smem, bool flow);
 // nothing (shared memory already limits the SM to as few CTAs) or when the whole batch is resident at once anyway
 // (latency matters, not throughput).
 static int chain_threads(int L0, int L1, bool flow, int nr, int B);
-static size_t chain_smem_bytes(int L0, int L1, bool flow, int nr) { return (engine_smem_doubles(L0, L1, flow, nr) + 64) * sizeof(double); }
+static size_t chain_smem_bytes(int L0, int L1, bool flow, int nr) { return (engine_smem_doubles(L0, L1, flow, nr) + FT_SMEM_PREFIX) * sizeof(double); }
 
 // static shared memory of the chain kernels (the engine object), which counts against the per-block opt-in limit
 static int chain_static_smem(bool cluster) {
