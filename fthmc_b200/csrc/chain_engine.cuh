@@ -704,10 +704,10 @@ struct Engine {
     // tensor-core (DMMA) form of the two big convolutions: stripe lengths that are multiples of 8 (in cluster mode the
     // halo columns of a rank's first / last stripe group come from the halo buffers AH / ZH, channel stride 2R)
     FT_HD bool mma_ok() const { return (L0 & 7) == 0 && (L1 & 7) == 0 && ex.use_mma(); }
-    // Winograd F(2,3) along the stripe direction for the two big convolutions (single-CTA chains whose stripes split
-    // into 16-row blocks with at least one block per warp; -DFT_WINOGRAD=0 keeps the direct tensor-core form)
+    // Winograd F(2,3) along the stripe direction for the two big convolutions (stripes that split into 16-row blocks
+    // with at least one block per warp; -DFT_WINOGRAD=0 keeps the direct tensor-core form)
     FT_HD bool wino_ok(const LayerGeom& g) const {
-        return FT_WINOGRAD && !CL && mma_ok() && (g.R & 15) == 0 && g.G * (g.R >> 4) >= ex.nwarps();
+        return FT_WINOGRAD && mma_ok() && (g.R & 15) == 0 && g.G * (g.R >> 4) >= ex.nwarps();
     }
     FT_HD void ph_conv2(const LayerGeom g, double* d2_save, double* h2_save = nullptr) {
         if (wino_ok(g)) {
@@ -835,11 +835,17 @@ struct Engine {
             const int gi = st / RB, rb = 16 * (st - gi * RB);
             int cc[5];                                       // columns 4g-2 .. 4g+2 (offsets in doubles)
 #pragma unroll
-            for (int m = 0; m < 5; ++m) { const int c = 4 * gi - 2 + m; cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R; }
+            for (int m = 0; m < 5; ++m) {
+                const int c = 4 * gi - 2 + m;
+                if (CL && c < 0) cc[m] = (oC - oA) + (c + 2) * R;          // halo AH[ci][c+2][r], channel stride 2R
+                else cc[m] = (c < 0 ? c + Cn : (c >= Cn ? c - Cn : c)) * R;
+            }
             double acc0[3][4][NL], acc1[3][4][NL];
             int rm[NL], r1[NL], rp[NL];                      // lane (i, j): row pair i, channel j of the half
+            int hcj[NL];                                     // cluster mode: channel-stride correction of the halo columns
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3, r0 = rb + 2 * i;
+                hcj[ls] = CL ? j * (2 * R - sA) : 0;
                 rm[ls] = j * sA + (r0 == 0 ? R - 1 : r0 - 1);
                 r1[ls] = j * sA + r0;
                 rp[ls] = j * sA + (r0 + 2 == R ? 0 : r0 + 2);
@@ -857,8 +863,9 @@ struct Engine {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     double t[4][NL];
+                    const bool halo = CL && gi == 0 && c < 2;
                     FT_LANES(ln, ls) {
-                        const double* pc = A + cc[c] + 4 * hf * sA;
+                        const double* pc = A + cc[c] + 4 * hf * sA + (halo ? hcj[ls] + 4 * hf * (2 * R - sA) : 0);
                         const double d0 = pc[rm[ls]], d3 = pc[rp[ls]];
                         const dbl2 d12 = ld2(pc + r1[ls]);
                         t[0][ls] = d0 - d12.y; t[1][ls] = d12.x + d12.y; t[2][ls] = d12.y - d12.x; t[3][ls] = d12.x - d3;
@@ -1328,11 +1335,15 @@ struct Engine {
             const int gi = st / RB, rb = 16 * (st - gi * RB);
             const int gn = gi + 1 == G ? 0 : gi + 1;
             // source column slots s = 0..4: (gi,k=0),(gi,1),(gi,2),(gn,0),(gn,1) == columns 4g-1, 4g, 4g+1, 4g+3, 4g+4
-            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R, 3 * gn * R, (3 * gn + 1) * R };
+            const bool hal = CL && gi + 1 == G;              // cluster mode: slots 3, 4 of the last group sit in ZH[o][s-3][r]
+            const int sc[5] = { 3 * gi * R, (3 * gi + 1) * R, (3 * gi + 2) * R,
+                                hal ? (oC - oZ) : 3 * gn * R, hal ? (oC - oZ) + R : (3 * gn + 1) * R };
             double acc0[4][4][NL], acc1[4][4][NL];
             int rm[NL], r1[NL], rp[NL];
+            int hcj[NL];
             FT_LANES(ln, ls) {
                 const int i = ln >> 2, j = ln & 3, r0 = rb + 2 * i;
+                hcj[ls] = CL ? j * (2 * R - sB) : 0;
                 rm[ls] = j * sB + (r0 == 0 ? R - 1 : r0 - 1);
                 r1[ls] = j * sB + r0;
                 rp[ls] = j * sB + (r0 + 2 == R ? 0 : r0 + 2);
@@ -1349,8 +1360,9 @@ struct Engine {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     double t[4][NL];
+                    const bool halo = hal && s5 >= 3;
                     FT_LANES(ln, ls) {
-                        const double* pc = C + sc[s5] + 4 * hf * sB;
+                        const double* pc = C + sc[s5] + 4 * hf * sB + (halo ? hcj[ls] + 4 * hf * (2 * R - sB) : 0);
                         const double d0 = pc[rm[ls]], d3 = pc[rp[ls]];
                         const dbl2 d12 = ld2(pc + r1[ls]);
                         t[0][ls] = d0 - d12.y; t[1][ls] = d12.x + d12.y; t[2][ls] = d12.y - d12.x; t[3][ls] = d12.x - d3;

@@ -254,3 +254,19 @@ def test_tensor_core_winograd_phases(golden, name, monkeypatch):
     assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
     assert np.array_equal(o["acc"].astype(bool), g["traj_acc"])
     assert np.array_equal(o["topo"], g["traj_topo"])
+
+
+@pytest.mark.parametrize("name,nranks", [("ft_L16_b6", 2), ("ft_L32_b4", 4)])
+def test_tensor_core_winograd_phases_cluster(golden, name, nranks, monkeypatch):
+    """The same with the lattice split over the ranks of a cluster: the Winograd source columns of a rank's first /
+    last stripe group come from the halo buffers."""
+    monkeypatch.setenv("FT_EMUL_MMA", "1")
+    g = golden(name)
+    x, w, beta = g["x"], g["weights"], float(g["beta"])
+    o = E.run("flow_fwd", w, x, nranks=nranks)
+    assert np.max(np.abs(o["field"] - g["flow_fwd"])) < 1e-12
+    assert relerr(E.run("ft_force", w, x, beta=beta, nranks=nranks)["field"], g["ft_force"]) < 1e-11
+    o = E.run("ft_hmc", w, g["traj_x"], beta=beta, dt=float(g["dt"]), nstep=int(g["nstep"]), p=g["traj_p"], u=g["traj_u"],
+              nranks=nranks)
+    assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
+    assert np.array_equal(o["acc"].astype(bool), g["traj_acc"]) and np.array_equal(o["topo"], g["traj_topo"])
