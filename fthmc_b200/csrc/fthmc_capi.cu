@@ -420,6 +420,40 @@ __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links
     }
 }
 
+// Large batches of small lattices: ONE WARP per chain (8 chains per CTA).  No block barrier and no shared memory, and the
+// unrolled scan keeps four iterations of 16-byte loads in flight per lane, where the CTA-per-chain form above is bound by
+// the load -> cos -> block-reduce latency of its short-lived CTAs.  Deterministic: lane-sequential sums, then a shuffle tree.
+template <typename T>
+__global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ links, int B, int L0, int L1, int what, int order,
+                                                        double beta, int rounded, T* __restrict__ out) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const T* f = links + (size_t)b * 2 * L0 * L1;
+    constexpr int N = Vec<T>::N;
+    const int W = L1 / N, nvec = L0 * W, dr = 32 / W, dc = 32 - dr * W;
+    int row = lane / W, col = lane - row * W;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int i = lane; i < nvec; i += 32) {
+        T p[N];
+        plaq_vec<T>(f, L0, L1, row, col * N, order, p);
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
+        col += dc; row += dr;
+        if (col >= W) { col -= W; ++row; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        double r;
+        if (what == 0) r = -beta * acc;
+        else if (rounded) r = floor(0.1 + acc / TWO_PI_D);
+        else r = acc / TWO_PI_D;
+        out[b] = (T)r;
+    }
+}
+
 // grid (nchunk, B): rows [r0,r1) of one chain; sin P of rows r0-1..r1-1 staged in shared memory (one sine per site).
 // VEC: 16-byte loads / stores of consecutive sites and division-free (row, column) stepping; needs L1 % Vec<T>::N == 0.
 template <typename T, bool VEC>
@@ -741,6 +775,12 @@ static int reduce_launch(const void* links, int B, int L0, int L1, int what, int
     cfg.attrs = at; cfg.numAttrs = 1;
     // 16-byte vector path: whole vectors per row, 16-byte aligned rows
     const bool vec = L1 % Vec<T>::N == 0 && ((uintptr_t)links & 15) == 0;
+    if (nc == 1 && vec && (long long)L0 * L1 <= 4096 && L0 * (L1 / Vec<T>::N) >= 32 && B >= 16 * 148) {
+        k_action_topo_warp<T><<<(B + 7) / 8, 256, 0, st>>>((const T*)links, B, L0, L1, what, order, beta, rounded, (T*)out);
+        g_launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
     auto kern = vec ? k_action_topo<T, true> : k_action_topo<T, false>;
     if (nc > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, what, order, beta, rounded, (T*)out));
