@@ -57,7 +57,7 @@
 namespace fthmc {
 
 enum ProfId { PF_PLANES = 0, PF_CONV1, PF_CONV2, PF_CONV3F, PF_CONV3R, PF_OUTGRAD, PF_CONV3T, PF_CONV2T, PF_CONV1T,
-              PF_SCATTER, PF_ISSUE, PF_WFORCE, PF_LEAP, PF_MISC, PF_C2_MAC, PF_C2_ACT, PF_C1_MAC, PF_C1_ACT, PF_C2T_MAC, PF_C2T_MUL, PF_N };
+              PF_SCATTER, PF_ISSUE, PF_WFORCE, PF_LEAP, PF_MISC, PF_C2_MAC, PF_C2_ACT, PF_C1_MAC, PF_C1_ACT, PF_C2T_MAC, PF_C3_CONV, PF_N };
 
 // ---- network shape (every reference config: hidden_sizes=[8,8], n_mixture_comps=2, kernel 3) ----
 constexpr int NH = 8;          // hidden channels of both hidden layers
@@ -990,43 +990,64 @@ struct Engine {
         }
     }
 
-    // conv3 at the active site of task (gi,r): out[0..2] = (s_1, s_2, t)
-    FT_HD void conv3_out(const double* B, const double* W, const LayerGeom& g, int gi, int r, double out[NOUT]) const {
-        const int R = g.R;
-        int rr[3] = { r == 0 ? R - 1 : r - 1, r, r + 1 == R ? 0 : r + 1 };
-        // one accumulator per (output, kernel row): nine independent chains instead of three (this phase runs on
-        // a quarter of the sites and is latency bound)
-        double o[3][3];
+    // conv3 for the two active sites (gi, r), (gi, r+1), r even, of one thread -> OUT[o][t], t = gi R + r.  The phase is
+    // bound by shared-memory wavefronts (with one site per thread: three loads per three DFMA, the weight loads warp-uniform): two
+    // sites share every weight load and the four input rows r-1 .. r+2 of a column (17 wavefronts per (channel, column)
+    // for two sites instead of 30).  Per site one accumulator per (output, kernel row): nine independent chains, summed (bias + row 0) + row 1) + row 2.
+    FT_HD void conv3_pair(const double* B, const double* W, double* OUT, const LayerGeom& g, int gi, int r) const {
+        const int R = g.R, T = g.G * R;
+        const int rm = r == 0 ? R - 1 : r - 1, rp = r + 2 == R ? 0 : r + 2;
+        double o0[3][3], o1[3][3];                           // [kernel row a][output]: site r, site r+1
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { o[a][0] = 0.0; o[a][1] = 0.0; o[a][2] = 0.0; }
+        for (int a = 0; a < 3; ++a) { o0[a][0] = o0[a][1] = o0[a][2] = 0.0; o1[a][0] = o1[a][1] = o1[a][2] = 0.0; }
 #pragma unroll 2
         for (int ci = 0; ci < NH; ++ci) {
             const double* Bp = B + ci * sB + 3 * gi * R;
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                const dbl2 v12 = ld2(Bp + b * R + r);
+                const double v[4] = { Bp[b * R + rm], v12.x, v12.y, Bp[b * R + rp] };     // rows r-1, r, r+1, r+2
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    double v = Bp[b * R + rr[a]];
+                for (int a = 0; a < 3; ++a) {
                     const dbl2 w01 = ld2(W + OFF_W3F + ((ci * 3 + a) * 3 + b) * 4);
                     const double w2 = W[OFF_W3F + ((ci * 3 + a) * 3 + b) * 4 + 2];
-                    o[a][0] = fma(w01.x, v, o[a][0]); o[a][1] = fma(w01.y, v, o[a][1]); o[a][2] = fma(w2, v, o[a][2]);
+                    o0[a][0] = fma(w01.x, v[a], o0[a][0]); o0[a][1] = fma(w01.y, v[a], o0[a][1]); o0[a][2] = fma(w2, v[a], o0[a][2]);
+                    o1[a][0] = fma(w01.x, v[a + 1], o1[a][0]); o1[a][1] = fma(w01.y, v[a + 1], o1[a][1]); o1[a][2] = fma(w2, v[a + 1], o1[a][2]);
                 }
+            }
         }
-        out[0] = ((W[OFF_B3 + 0] + o[0][0]) + o[1][0]) + o[2][0];
-        out[1] = ((W[OFF_B3 + 1] + o[0][1]) + o[1][1]) + o[2][1];
-        out[2] = ((W[OFF_B3 + 2] + o[0][2]) + o[1][2]) + o[2][2];
+        const int t = gi * R + r;
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+            st2(OUT + o * T + t, ((W[OFF_B3 + o] + o0[0][o]) + o0[1][o]) + o0[2][o], ((W[OFF_B3 + o] + o1[0][o]) + o1[1][o]) + o1[2][o]);
+    }
+    // conv3 of every active site of this rank into OUT (s_1 | s_2 | t planes of T doubles), then a block barrier
+    FT_HD void conv3_all(const LayerGeom& g) {
+        const double* B = sm(oB); const double* W = sm(oW); double* OUT = sm(oOUT);
+        const int T = g.G * g.R, hR = g.R >> 1;
+        for (int t2 = ex.tid(); t2 < (T >> 1); t2 += ex.nt()) {
+            const int gi = t2 / hR;
+            conv3_pair(B, W, OUT, g, gi, 2 * (t2 - gi * hR));
+        }
+        ex.lsync();
     }
 
     // forward transform of the active plaquettes + link update; returns this thread's logJ partial.
     // sv/so != nullptr: the pre-update active links and (s_1,s_2) go to the global layer block.
     FT_PHASE double ph_conv3_forward(const LayerGeom g, bool want_logJ, double* sv, double* so) {
-        const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
+        const double* UA = sm(oUA); const double* OUT = sm(oOUT);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double lj = 0.0;
+#ifdef FT_PROFILE
+        long long tc0 = ex.clock();
+#endif
+        conv3_all(g);
+#ifdef FT_PROFILE
+        ex.prof_add(PF_C3_CONV, ex.clock() - tc0);
+#endif
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
-            double out[NOUT];
-            conv3_out(B, W, g, gi, r, out);
+            const double out[NOUT] = { OUT[t], OUT[T + t], OUT[2 * T + t] };
             double u = UA[t];
             double es0 = exp(out[0]), es1 = exp(out[1]);
             double fx1 = mixture_fwd(u, es0, es1, conv);
@@ -1075,19 +1096,16 @@ struct Engine {
     // fire within max_iter=1000 because non-active sites (y=0,f=0) keep halving towards 0 without
     // reaching it, so only the tolerance and max_iter exits exist.
     FT_PHASE double ph_conv3_reverse(const LayerGeom g, bool want_logJ, int* iters) {
-        const double* B = sm(oB); const double* W = sm(oW); const double* UA = sm(oUA);
+        const double* UA = sm(oUA);
         double* OUT = sm(oOUT); double* A = sm(oA);
         const int T = g.G * g.R, R = g.R, conv = pr.conv;
         double* Y = A; double* ES0 = A + T; double* ES1 = A + 2 * T; double* LO = A + 3 * T; double* HI = A + 4 * T;
         double* MID = A + 5 * T;
         const double lo0 = conv == 0 ? 0.0 : -PI_D, hi0 = conv == 0 ? TWO_PI_D : PI_D;
+        conv3_all(g);
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / R, r = t - gi * R;
-            double out[NOUT];
-            conv3_out(B, W, g, gi, r, out);
-            OUT[t] = out[0]; OUT[T + t] = out[1];
-            ES0[t] = exp(out[0]); ES1[t] = exp(out[1]);
-            Y[t] = mod_2pi(UA[t] - out[2], conv);
+            ES0[t] = exp(OUT[t]); ES1[t] = exp(OUT[T + t]);
+            Y[t] = mod_2pi(UA[t] - OUT[2 * T + t], conv);
             LO[t] = lo0; HI[t] = hi0;
         }
         ex.lsync();    // (A was the conv2 input; all conv3 reads of B are unaffected)
@@ -1466,7 +1484,7 @@ struct Engine {
                     st2(p, acc[0][q][ci] * d.x, acc[1][q][ci] * d.y);
                 }
 #ifdef FT_PROFILE
-            ex.prof_add(PF_C2T_MUL, ex.clock() - tp0);
+            ex.prof_add(PF_C3_CONV, ex.clock() - tp0);
 #endif
         }
     }

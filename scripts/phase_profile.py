@@ -15,7 +15,7 @@ import fthmc_b200._lib as L
 L.LIB_PATH = out
 import fthmc_b200 as ft
 lib = ft.lib()
-names = ["planes", "conv1", "conv2", "conv3_fwd", "conv3_rev", "outgrad", "conv3T", "conv2T", "conv1T", "scatter", "issue", "wilson_force", "leap", "misc", "  c2_mac", "  c2_act", "  c1_mac", "  c1_act", "  c2T_mac", "  c2T_wait_d1"]
+names = ["planes", "conv1", "conv2", "conv3_fwd", "conv3_rev", "outgrad", "conv3T", "conv2T", "conv1T", "scatter", "issue", "wilson_force", "leap", "misc", "  c2_mac", "  c2_act", "  c1_mac", "  c1_act", "  c2T_mac", "  c3_conv_all"]
 Lx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
