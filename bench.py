@@ -361,10 +361,12 @@ def run_ours(a):
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     alg_bytes = B * (2 * L * L * 8 * 2 + 32)
     traffic = None          # measured DRAM bytes per launch: ncu --set full capture of the same kernel, scaled per chain
+    smem_term = None        # shared-memory term: wavefronts moved against the SM's peak, from the same capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if (a.L, a.layers, a.nstep) == (32, 24, 10):
             traffic = tj["dram_bytes_per_chain_traj"] * B
+            smem_term = {"wavefronts_pct_of_peak": tj.get("smem_wavefronts_pct_of_peak"), "source": tj.get("source")}
     except Exception:
         pass
     roof = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
@@ -373,7 +375,8 @@ def run_ours(a):
                            "nominal B200 fp64 is 37 TFLOP/s",
             "alg_flop_per_chain_traj": alg_flop_per_chain_traj(a),
             "hbm_term": {"alg_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+            "smem_term": smem_term}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
