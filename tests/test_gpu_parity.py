@@ -66,6 +66,30 @@ def test_stencils_vs_oracle(shape, dtype):
         assert np.array_equal(ft.regularize(xd).cpu().numpy(), O.regularize(x64).numpy())
 
 
+@pytest.mark.parametrize("shape", [(4096, 32, 32), (2500, 16, 24), (3000, 64, 64)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_reduction_stencils_large_batch(shape, dtype):
+    """Batches of >= 2368 small lattices take the warp-per-chain form of the action / charge scans (k_action_topo_warp):
+    same parity bars as the CTA-per-chain form, against the batched oracle (one torch call for the whole batch)."""
+    B, L0, L1 = shape
+    gen = torch.Generator().manual_seed(B + L0)
+    x = (torch.rand(B, 2, L0, L1, generator=gen, dtype=torch.float64) * 2 - 1) * 3.0
+    xd = x.to(dtype).cuda()
+    x64 = xd.double().cpu()
+    P = ft.Param(beta=2.5, lat=(L0, L1))
+    tol = REL if dtype == torch.float64 else 2e-5
+    ref = O.u1_action(2.5, x64).numpy()
+    assert relerr(ft.u1_action(2.5, xd).double().cpu().numpy(), ref) < tol
+    # hmc_2dU1's plaquette term order differs from u1_plaq's in the last ulp only
+    assert relerr(ft.action(P, xd).double().cpu().numpy(), ref) < (1e-9 if dtype == torch.float64 else 2e-5)
+    if dtype == torch.float64:
+        assert np.max(np.abs(ft.topo_charge(xd).cpu().numpy() - O.topo_charge(x64).numpy())) < 1e-9
+        q = ft.topocharge(xd).cpu().numpy()
+        assert np.array_equal(q, np.floor(0.1 + O.topo_charge(x64).numpy()))
+        small = ft.topocharge(xd[:5]).cpu().numpy()          # CTA-per-chain form on the same chains
+        assert np.array_equal(q[:5], small)
+
+
 # ---------------------------------------------------------------- plain HMC
 def test_plain_hmc_teacher_forced_golden(golden):
     g = golden("plain_L8")
