@@ -816,9 +816,14 @@ extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta
     int rc = check_stencil(links, force_out, B, L0, L1, dtype); if (rc) return rc;
     if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
     const size_t es = dtype == FTHMC_F64 ? 8 : 4;
-    int rows = (int)((64 * 1024) / (es * L1)) - 1;
-    if (rows < 1) return fail(FTHMC_E_LATTICE, "L1 too large for the force tile");
+    // tile height: about 24 KB of sin(P) per CTA keeps eight CTAs (all 2048 threads) on an SM, so that the load / sine
+    // half of one tile overlaps the store half of others; very wide rows take what 64 KB hold (>= 1 halo row per 15)
+    const int rows_max = (int)((64 * 1024) / (es * L1)) - 1;
+    if (rows_max < 1) return fail(FTHMC_E_LATTICE, "L1 too large for the force tile");
+    int rows = (int)((24 * 1024) / (es * L1)) - 1;
+    if (rows < 15) rows = rows_max < 15 ? rows_max : 15;
     if (rows > L0) rows = L0;
+    rows = (L0 + (L0 + rows - 1) / rows - 1) / ((L0 + rows - 1) / rows);          // equal tiles
     // small batches of large lattices: shorter tiles until the grid fills the device
     while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) < 4 * 148) rows = (rows + 1) / 2;
     const int nchunk = (L0 + rows - 1) / rows;
