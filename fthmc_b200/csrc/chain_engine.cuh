@@ -180,6 +180,58 @@ FT_HD double exp_fast(double x) {
     return fma(sc, q, sc);
 }
 
+// sin / cos for the Wilson stencils: one branch-free evaluation with ~1 ulp error for |x| < 2^19 (beyond that, and for
+// non-finite arguments, the library function).  x = n pi/2 + r by a three-term Cody-Waite reduction (pi/2 in 33-bit
+// pieces, fdlibm's pio2_1 / pio2_2 / pio2_2t: n * piece is exact), then ONE degree-5 polynomial in r^2 whose coefficients
+// are selected per lane between fdlibm's sine and cosine kernels: 15 fp64 operations where the library's sin / cos
+// spends ~25 plus its slow-path bookkeeping -- the reduction scans are issue bound, not HBM bound, with the latter.
+// constants: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -pi/2 in three pieces, [5..10] sine kernel S6..S1, [11..16] C - S for C6..C1.
+// On the device they sit in constant memory (a DFMA takes a constant-bank operand directly; as 64-bit immediates every
+// use costs two extra moves, which made the scans issue bound).
+#define FT_TRIG_CONSTS { 0.63661977236758134308, 6755399441055744.0, \
+    -1.57079632673412561417e+00, -6.07710050630396597660e-11, -2.02226624879595063154e-21, \
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, \
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, \
+    -1.13596475577881948265e-11 - 1.58969099521155010221e-10, 2.08757232129817482790e-09 + 2.50507602534068634195e-08, \
+    -2.75573143513906633035e-07 - 2.75573137070700676789e-06, 2.48015872894767294178e-05 + 1.98412698298579493134e-04, \
+    -1.38888888888741095749e-03 - 8.33333333332248946124e-03, 4.16666666666666019037e-02 + 1.66666666666666324348e-01 }
+#ifdef __CUDACC__
+__constant__ double c_trig[17] = FT_TRIG_CONSTS;
+#endif
+FT_HD double sincos_kernel(double x, int quadrant_shift) {
+#ifdef __CUDA_ARCH__
+    const double* K = c_trig;
+#else
+    const double K[17] = FT_TRIG_CONSTS;
+#endif
+    const double t = fma(x, K[0], K[1]);                                      // n = rint(x * 2/pi) in the low mantissa bits
+    const double n = t - K[1];
+    int q;
+#ifdef __CUDA_ARCH__
+    q = __double2loint(t);
+#else
+    q = (int)(long long)n;
+#endif
+    q += quadrant_shift;                                                      // sin: 0, cos: +1  (cos x = sin(x + pi/2))
+    double r = fma(n, K[2], x);
+    r = fma(n, K[3], r);
+    r = fma(n, K[4], r);
+    // odd quadrant: cosine kernel.  The coefficients are blended arithmetically, k = S + odd * (C - S) (one DFMA with
+    // constant-bank operands each; exact to ~0.1 ulp of the result) instead of per-lane selects of 64-bit constants.
+    const bool odd = q & 1;
+    const double od = odd ? 1.0 : 0.0;
+    const double r2 = r * r;
+    double p = fma(od, K[11], K[5]);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) p = fma(p, r2, fma(od, K[11 + i], K[5 + i]));
+    const double a = (odd ? r2 : r) * r2;                                     // cos: r^4 P + (1 - r^2/2),  sin: r^3 P + r
+    const double b = odd ? fma(-0.5, r2, 1.0) : r;
+    const double v = fma(a, p, b);
+    return (q & 2) ? -v : v;
+}
+FT_HD double sin_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 0) : sin(x); }
+FT_HD double cos_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 1) : cos(x); }
+
 // 1/d for d >= 1 (one cubic Newton step on the hardware seed: three DFMA); host: plain division
 FT_HD double rcp_ge1(double d) {
 #ifdef __CUDA_ARCH__

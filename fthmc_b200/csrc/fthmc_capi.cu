@@ -49,6 +49,15 @@ extern "C" unsigned long long fthmc_launch_count(void) { return g_launches.load(
 __device__ unsigned long long g_prof[32];
 #endif
 
+#ifndef FT_TMA_STAGES
+#define FT_TMA_STAGES 2
+#endif
+#ifndef FT_STENCIL_TMA
+#define FT_STENCIL_TMA 1
+#endif
+#ifndef FT_FAST_TRIG
+#define FT_FAST_TRIG 1
+#endif
 #ifndef FT_THREADS
 #define FT_THREADS 256          // threads per CTA of the resident-chain kernels
 #endif
@@ -306,8 +315,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct M;
 template <> struct M<double> {
-    static __device__ double cosv(double x) { return cos(x); }
-    static __device__ double sinv(double x) { return sin(x); }
+    static __device__ double cosv(double x) { return FT_FAST_TRIG ? fthmc::cos_fast(x) : cos(x); }
+    static __device__ double sinv(double x) { return sin(x); }       // (sin_fast measured slower in k_force: 83 % vs 88 %)
     static __device__ double floorv(double x) { return floor(x); }
     static __device__ double modv(double x, double y) { return fmod(x, y); }
 };
@@ -365,9 +374,10 @@ __device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1
 // grid (nc, B), thread-block cluster (nc, 1, 1): the nc CTAs of a cluster split the rows of ONE chain, reduce in fp64,
 // hand their partial sums to rank 0 through distributed shared memory, and rank 0 writes the finished per-chain value.
 // One launch, no global scratch, deterministic summation order.  nc == 1 (large batches): a plain one-CTA-per-chain scan.
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links, int L0, int L1, int rows, int what, int order,
+template <typename T, bool VEC, int WHAT, int ORDER>
+__global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links, int L0, int L1, int rows,
                                                    double beta, int rounded, T* __restrict__ out) {
+    constexpr int what = WHAT, order = ORDER;                // compile time: a run-time switch evaluates every branch's arithmetic
     __shared__ double red[8];
     __shared__ double part[16];                              // rank 0: one slot per rank of the cluster
     namespace cg = cooperative_groups;
@@ -423,9 +433,10 @@ __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links
 // Large batches of small lattices: ONE WARP per chain (8 chains per CTA).  No block barrier and no shared memory, and the
 // unrolled scan keeps four iterations of 16-byte loads in flight per lane, where the CTA-per-chain form above is bound by
 // the load -> cos -> block-reduce latency of its short-lived CTAs.  Deterministic: lane-sequential sums, then a shuffle tree.
-template <typename T>
-__global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ links, int B, int L0, int L1, int what, int order,
+template <typename T, int WHAT, int ORDER>
+__global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ links, int B, int L0, int L1,
                                                         double beta, int rounded, T* __restrict__ out) {
+    constexpr int what = WHAT, order = ORDER;
     const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     const T* f = links + (size_t)b * 2 * L0 * L1;
@@ -451,6 +462,92 @@ __global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ 
         else if (rounded) r = floor(0.1 + acc / TWO_PI_D);
         else r = acc / TWO_PI_D;
         out[b] = (T)r;
+    }
+}
+
+// Large batches of lattices that fit a shared-memory stage (<= 32 KB per chain): persistent CTAs, each streaming its
+// chains through a ring of NSTAGE shared-memory buffers with TMA bulk copies (cp.async.bulk + mbarrier), one chain per
+// copy.  The copies of the next NSTAGE - 1 chains are in flight while the 256 threads reduce the current one out of
+// shared memory, so the HBM stream never waits for the cos / wrap arithmetic.  The scans are issue bound after that
+// (ncu: issue slots 74 % busy), so the ring is kept short (FT_TMA_STAGES = 2: six CTAs of 2 x 16 KB per SM at L = 32).  One block barrier per chain: it publishes the warps' partial sums (thread 0 adds them in warp order:
+// deterministic) and frees the stage for thread 0 to refill.
+template <typename T, int NSTAGE, int WHAT, int ORDER>
+__global__ void __launch_bounds__(256) k_action_topo_tma(const T* __restrict__ links, int B, int L0, int L1, int stage_elems,
+                                                       double beta, int rounded, T* __restrict__ out) {
+    constexpr int what = WHAT, order = ORDER;
+    extern __shared__ __align__(128) unsigned char tma_raw[];
+    T* buf = reinterpret_cast<T*>(tma_raw);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tma_raw + (size_t)NSTAGE * stage_elems * sizeof(T));
+    double* red = reinterpret_cast<double*>(bars + NSTAGE);                  // [2][8] partial sums, double-buffered by chain parity
+    const int tid = threadIdx.x, V = L0 * L1;
+    const unsigned bytes = (unsigned)(2 * V * sizeof(T));
+    const int nmine = B > (int)blockIdx.x ? (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto issue = [&](int k) {                                                // thread 0: chain k of this CTA into stage k % NSTAGE
+        const int st = k % NSTAGE;
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(bars + st), d = (unsigned)__cvta_generic_to_shared(buf + (size_t)st * stage_elems);
+        const T* src = links + (size_t)(blockIdx.x + (size_t)k * gridDim.x) * 2 * V;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(d), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        for (int k = 0; k < NSTAGE && k < nmine; ++k) issue(k);
+    }
+    __syncthreads();
+    constexpr int N = Vec<T>::N;
+    using VT = typename Vec<T>::type;
+    const int W = L1 / N, nvec = L0 * W, dr = 256 / W, dc = 256 - dr * W;
+    const int row0 = tid / W, col0 = tid - row0 * W;
+    for (int k = 0; k < nmine; ++k) {
+        const int st = k % NSTAGE;
+        {
+            const unsigned mb = (unsigned)__cvta_generic_to_shared(bars + st), parity = (unsigned)((k / NSTAGE) & 1);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra DONE_%=;\n"
+                "bra WAIT_%=;\n"
+                "DONE_%=:\n"
+                "}\n" ::"r"(mb), "r"(parity) : "memory");
+        }
+        const T* f = buf + (size_t)st * stage_elems;
+        double acc = 0.0;
+        int row = row0, col = col0;
+        for (int i = tid; i < nvec; i += 256) {
+            const int n1 = col * N, n0p = row + 1 == L0 ? 0 : row + 1, n1n = n1 + N == L1 ? 0 : n1 + N;
+            __align__(16) T t0[N + 1], t1[N], t1p[N];
+            *reinterpret_cast<VT*>(t0) = *reinterpret_cast<const VT*>(f + row * L1 + n1);
+            t0[N] = f[row * L1 + n1n];
+            *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + (L0 + row) * L1 + n1);
+            *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + (L0 + n0p) * L1 + n1);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+                acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+            }
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) red[(k & 1) * 8 + (tid >> 5)] = acc;
+        __syncthreads();                                     // partial sums published; every thread is done with stage st
+        if (tid == 0) {
+            if (k + NSTAGE < nmine) issue(k + NSTAGE);
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[(k & 1) * 8 + w];
+            double r;
+            if (what == 0) r = -beta * t;
+            else if (rounded) r = floor(0.1 + t / TWO_PI_D);
+            else r = t / TWO_PI_D;
+            out[blockIdx.x + (size_t)k * gridDim.x] = (T)r;
+        }
     }
 }
 
@@ -763,8 +860,8 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
 // C ABI: stencils
 // ------------------------------------------------------------------------------------------------
 // CTAs per chain of the reduction stencils: 1 when the batch alone fills the device, otherwise a cluster of up to 16
-template <typename T>
-static int reduce_launch(const void* links, int B, int L0, int L1, int what, int order, double beta, int rounded, void* out, cudaStream_t st) {
+template <typename T, int WHAT, int ORDER>
+static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta, int rounded, void* out, cudaStream_t st) {
     int nc = 1;
     while (nc < 16 && (long long)B * nc < 4 * 148 && 2 * nc <= L0 && (long long)(L0 / (2 * nc)) * L1 >= 1024) nc *= 2;
     const int rows = (L0 + nc - 1) / nc;
@@ -775,18 +872,40 @@ static int reduce_launch(const void* links, int B, int L0, int L1, int what, int
     cfg.attrs = at; cfg.numAttrs = 1;
     // 16-byte vector path: whole vectors per row, 16-byte aligned rows
     const bool vec = L1 % Vec<T>::N == 0 && ((uintptr_t)links & 15) == 0;
-    if (nc == 1 && vec && (long long)L0 * L1 <= 4096 && L0 * (L1 / Vec<T>::N) >= 32 && B >= 16 * 148) {
-        k_action_topo_warp<T><<<(B + 7) / 8, 256, 0, st>>>((const T*)links, B, L0, L1, what, order, beta, rounded, (T*)out);
+    const size_t chain_bytes = (size_t)2 * L0 * L1 * sizeof(T);
+    if (FT_STENCIL_TMA && nc == 1 && vec && chain_bytes <= 32 * 1024 && chain_bytes % 16 == 0 && L0 * (L1 / Vec<T>::N) >= 64 && B >= 16 * 148) {
+        constexpr int NSTAGE = FT_TMA_STAGES;
+        const int stage_elems = (int)(((chain_bytes + 127) / 128) * 128 / sizeof(T));
+        const size_t smem = (size_t)NSTAGE * stage_elems * sizeof(T) + NSTAGE * 8 + 16 * 8;
+        int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
+        int grid = 148 * per_sm; if (grid > B) grid = B;
+        auto kern = k_action_topo_tma<T, NSTAGE, WHAT, ORDER>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>((const T*)links, B, L0, L1, stage_elems, beta, rounded, (T*)out);
         g_launches += 1;
         CK(cudaGetLastError());
         return 0;
     }
-    auto kern = vec ? k_action_topo<T, true> : k_action_topo<T, false>;
+    if (nc == 1 && vec && (long long)L0 * L1 <= 4096 && L0 * (L1 / Vec<T>::N) >= 32 && B >= 16 * 148) {
+        k_action_topo_warp<T, WHAT, ORDER><<<(B + 7) / 8, 256, 0, st>>>((const T*)links, B, L0, L1, beta, rounded, (T*)out);
+        g_launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    auto kern = vec ? k_action_topo<T, true, WHAT, ORDER> : k_action_topo<T, false, WHAT, ORDER>;
     if (nc > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, what, order, beta, rounded, (T*)out));
+    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, beta, rounded, (T*)out));
     g_launches += 1;
     CK(cudaGetLastError());
     return 0;
+}
+// (what, order) pairs in use: action with either plaquette term order, floored charge (order 1), batched charge (order 0)
+template <typename T>
+static int reduce_launch(const void* links, int B, int L0, int L1, int what, int order, double beta, int rounded, void* out, cudaStream_t st) {
+    if (what == 0) return order == 0 ? reduce_launch_t<T, 0, 0>(links, B, L0, L1, beta, rounded, out, st)
+                                     : reduce_launch_t<T, 0, 1>(links, B, L0, L1, beta, rounded, out, st);
+    if (what == 1) return reduce_launch_t<T, 1, 1>(links, B, L0, L1, beta, rounded, out, st);
+    return reduce_launch_t<T, 2, 0>(links, B, L0, L1, beta, rounded, out, st);
 }
 
 static int check_stencil(const void* in, const void* out, int B, int L0, int L1, int dtype) {
