@@ -47,6 +47,9 @@
 #define FT_T(id, ...) do { __VA_ARGS__; } while (0)
 #endif
 
+#ifndef FT_BISECT_REPLAY
+#define FT_BISECT_REPLAY 1
+#endif
 #ifndef FT_WINOGRAD
 #define FT_WINOGRAD 1
 #endif
@@ -1161,21 +1164,67 @@ struct Engine {
             LO[t] = lo0; HI[t] = hi0;
         }
         ex.lsync();    // (A was the conv2 input; all conv3 reads of B are unaffected)
+#if FT_BISECT_REPLAY
+        // The reference's bisection costs ~23 evaluations of the mixture map f per site and layer.  f is smooth and strictly
+        // increasing, so its decisions can be REPLAYED instead of evaluated: a safeguarded Newton iteration first finds the
+        // root xs (f(xs) = y up to a residual rho <= 2e-13, ~5 evaluations), then every bisection step forms the same
+        // midpoint with the same arithmetic and decides from d = mid - xs:
+        //     y - f(mid) = -(f'(xs) d + R),   |R| <= K^3 d^2 / 4 + rho      (|f''| <= K^3 / 2,  K = max_k max(e^s_k, e^-s_k)),
+        //     |y - f(mid)| >= mmin |d| - rho,  mmin = mean_k min(e^s_k, e^-s_k) <= f'.
+        // When these bounds fix both the sign of y - f(mid) and the side of |y - f(mid)| relative to the tolerance (with a
+        // 2e-13 guard for the rounding of an evaluated f), the step needs no evaluation; otherwise -- d within ~1e-12 of
+        // zero, the error within ~1e-12 of the tolerance, or a Newton iteration that did not converge -- the step evaluates
+        // f(mid) exactly as before.  Midpoints, decisions and the iteration count are those of the plain loop.
+        double* XS = A + 6 * T; double* MS = A + 7 * T; double* QC = A + 8 * T; double* RH = A + 9 * T; double* MM = A + 10 * T;
+        for (int t = ex.tid(); t < T; t += ex.nt()) {
+            const double y = Y[t], es0 = ES0[t], es1 = ES1[t];
+            double a = lo0, b = hi0, x = y, fp = 1.0, rho = 1e300;
+            if (!(x > a && x < b)) x = 0.5 * (a + b);
+#pragma unroll 1
+            for (int k = 0; k < 12; ++k) {
+                // f as in mixture_fwd (same operations), f' = mean_k e^s_k (1 + th^2) / (1 + e^2s_k th^2) from the same tangent
+                const double th = tan(x / 2), t2 = th * th;
+                const double fx = (mod_2pi(2 * atan(es0 * th), conv) + mod_2pi(2 * atan(es1 * th), conv)) / 2, r = fx - y;
+                const double n0 = fma(es0 * es0, t2, 1.0), n1 = fma(es1 * es1, t2, 1.0);
+                fp = 0.5 * (1.0 + t2) * (es0 * n1 + es1 * n0) / (n0 * n1);
+                if (fabs(r) <= 2e-13) { rho = fabs(r); break; }
+                if (r > 0.0) b = x; else a = x;
+                double xn = x - r / fp;
+                if (!(xn > a && xn < b)) xn = 0.5 * (a + b);
+                x = xn;
+            }
+            const double i0 = 1.0 / es0, i1 = 1.0 / es1;
+            const double k0 = es0 > i0 ? es0 : i0, k1 = es1 > i1 ? es1 : i1, K = k0 > k1 ? k0 : k1;
+            XS[t] = x; MS[t] = fp; RH[t] = rho + 2e-13;
+            QC[t] = 0.25 * K * K * K;
+            MM[t] = 0.5 * ((es0 < i0 ? es0 : i0) + (es1 < i1 ? es1 : i1));
+        }
+#endif
         int it = 0;
         for (; it < pr.inv_max_iter; ++it) {
-            double err = 0.0;
+            bool conv_all = true;
             for (int t = ex.tid(); t < T; t += ex.nt()) {
                 double mid = (LO[t] + HI[t]) / 2;
+                MID[t] = mid;
+#if FT_BISECT_REPLAY
+                const double d = mid - XS[t], ad = fabs(d), rh = RH[t];
+                const double lin = MS[t] * ad, q = QC[t] * ad * ad + rh, glob = MM[t] * ad - rh;
+                const double lower = lin - q > glob ? lin - q : glob, upper = lin + q;
+                if (lower > 0.0 && (lower >= pr.inv_tol || upper < pr.inv_tol)) {
+                    conv_all = conv_all && upper < pr.inv_tol;
+                    if (d < 0.0) LO[t] = mid; else HI[t] = mid;          // y > f(mid)  <=>  mid left of the root
+                    continue;
+                }
+#endif
                 double f = mixture_fwd(mid, ES0[t], ES1[t], conv);
                 double y = Y[t];
                 double e = fabs(y - f);
-                err = e > err ? e : err;
-                MID[t] = mid;
+                conv_all = conv_all && e < pr.inv_tol;
                 if (y > f) LO[t] = mid; else HI[t] = mid;
             }
             // stop test max_t err_t < tol == AND_t (err_t < tol): one hardware barrier-reduction instead of a shuffle tree,
             // a shared-memory exchange and two barriers per iteration
-            if (ex.all(err < pr.inv_tol)) { ++it; break; }
+            if (ex.all(conv_all)) { ++it; break; }
         }
         if (iters) *iters = it;
         double lj = 0.0;
