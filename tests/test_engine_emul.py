@@ -270,3 +270,34 @@ def test_tensor_core_winograd_phases_cluster(golden, name, nranks, monkeypatch):
               nranks=nranks)
     assert np.max(np.abs(o["s"] - g["traj_dH"])) < 1e-8
     assert np.array_equal(o["acc"].astype(bool), g["traj_acc"]) and np.array_equal(o["topo"], g["traj_topo"])
+
+
+def test_bisection_replay_equals_plain_loop(golden, tmp_path):
+    """The inverse replays the reference's bisection from a Newton root and evaluates the mixture map only where its bounds do
+    not decide a step.  Against a build of the same engine with the plain loop (-DFT_BISECT_REPLAY=0): bit-identical fields
+    and iteration counts for tolerances from 1e-6 down to 1e-15 (where every late step takes the exact-evaluation
+    fallback), in both angle conventions."""
+    import subprocess
+    plain = str(tmp_path / "libfthmc_emul_plain.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off", "-mfma", "-shared", "-fPIC",
+                           "-DFT_BISECT_REPLAY=0", "-o", plain, E.SRC])
+    g = golden("ft_L16_b6")
+    y0 = g["flow_fwd"]
+    cases = [(tol, conv) for tol in (1e-6, 3e-7, 1e-10, 1e-13, 1e-15) for conv in (0, 1)]
+    out = {}
+    saved = (E._lib, E.build)
+    try:
+        for name, lib in (("replay", None), ("plain", plain)):
+            E._lib = None
+            if lib is not None:
+                E.build = lambda force=False, lib=lib: lib
+            for tol, conv in cases:
+                y = y0 if conv == 0 else wrap(y0)
+                o = E.run("flow_inv", g["weights"], y, tol=tol, max_iter=200, conv=conv)
+                out[(name, tol, conv)] = (o["field"].copy(), o["iters"].copy())
+    finally:
+        E._lib, E.build = None, saved[1]
+    for tol, conv in cases:
+        a, b = out[("replay", tol, conv)], out[("plain", tol, conv)]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tol, conv)
+    assert out[("replay", 1e-6, 0)][1].max() == 23 and out[("replay", 1e-13, 0)][1].min() > 40
