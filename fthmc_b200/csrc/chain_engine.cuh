@@ -1200,27 +1200,60 @@ struct Engine {
             MM[t] = 0.5 * ((es0 < i0 ? es0 : i0) + (es1 < i1 ? es1 : i1));
         }
 #endif
+        // one bisection step of site t on [lo, hi]: the midpoint, whether y > f(mid) (the root lies right of it), and
+        // whether |y - f(mid)| < tol -- from the bounds when they decide, from an evaluation of f otherwise
+        auto site_step = [&](int t, double lo, double hi, double& mid, bool& right) -> bool {
+            mid = (lo + hi) / 2;
+#if FT_BISECT_REPLAY
+            const double d = mid - XS[t], ad = fabs(d), rh = RH[t];
+            const double lin = MS[t] * ad, q = QC[t] * ad * ad + rh, glob = MM[t] * ad - rh;
+            const double lower = lin - q > glob ? lin - q : glob, upper = lin + q;
+            if (lower > 0.0 && (lower >= pr.inv_tol || upper < pr.inv_tol)) {
+                right = d < 0.0;                                     // y > f(mid)  <=>  mid left of the root
+                return upper < pr.inv_tol;
+            }
+#endif
+            const double f = mixture_fwd(mid, ES0[t], ES1[t], conv), y = Y[t];
+            right = y > f;
+            return fabs(y - f) < pr.inv_tol;
+        };
         int it = 0;
+#if FT_BISECT_REPLAY
+        // The tensor-wide stop test cannot succeed before every site has been within tolerance once: each site first
+        // replays on its own, without barriers, up to its first converged step a_t (not applied); one max-reduction gives
+        // A = max_t a_t, the sites catch up to step A, and the barrier loop below runs from there (one to three steps).
+        {
+            double* AT = A + 11 * T;
+            double amax = 0.0;
+            for (int t = ex.tid(); t < T; t += ex.nt()) {
+                double lo = LO[t], hi = HI[t], mid; bool right;
+                int i = 0;
+                for (; i < pr.inv_max_iter - 1; ++i) {
+                    if (site_step(t, lo, hi, mid, right)) break;
+                    if (right) lo = mid; else hi = mid;
+                }
+                LO[t] = lo; HI[t] = hi; AT[t] = (double)i;
+                amax = amax > (double)i ? amax : (double)i;
+            }
+            it = (int)ex.maxv(amax);
+            for (int t = ex.tid(); t < T; t += ex.nt()) {
+                double lo = LO[t], hi = HI[t], mid; bool right;
+                for (int i = (int)AT[t]; i < it; ++i) {
+                    site_step(t, lo, hi, mid, right);
+                    if (right) lo = mid; else hi = mid;
+                }
+                LO[t] = lo; HI[t] = hi;
+            }
+        }
+#endif
         for (; it < pr.inv_max_iter; ++it) {
             bool conv_all = true;
             for (int t = ex.tid(); t < T; t += ex.nt()) {
-                double mid = (LO[t] + HI[t]) / 2;
+                double mid; bool right;
+                const bool c = site_step(t, LO[t], HI[t], mid, right);
+                conv_all = conv_all && c;
                 MID[t] = mid;
-#if FT_BISECT_REPLAY
-                const double d = mid - XS[t], ad = fabs(d), rh = RH[t];
-                const double lin = MS[t] * ad, q = QC[t] * ad * ad + rh, glob = MM[t] * ad - rh;
-                const double lower = lin - q > glob ? lin - q : glob, upper = lin + q;
-                if (lower > 0.0 && (lower >= pr.inv_tol || upper < pr.inv_tol)) {
-                    conv_all = conv_all && upper < pr.inv_tol;
-                    if (d < 0.0) LO[t] = mid; else HI[t] = mid;          // y > f(mid)  <=>  mid left of the root
-                    continue;
-                }
-#endif
-                double f = mixture_fwd(mid, ES0[t], ES1[t], conv);
-                double y = Y[t];
-                double e = fabs(y - f);
-                conv_all = conv_all && e < pr.inv_tol;
-                if (y > f) LO[t] = mid; else HI[t] = mid;
+                if (right) LO[t] = mid; else HI[t] = mid;
             }
             // stop test max_t err_t < tol == AND_t (err_t < tol): one hardware barrier-reduction instead of a shuffle tree,
             // a shared-memory exchange and two barriers per iteration
