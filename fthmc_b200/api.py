@@ -198,8 +198,99 @@ def leapfrog(param, x, p):
     return (xo[0], po[0]) if single else (xo, po)
 
 
+_side_streams = {}
+
+
+def _pipelined_ok(x, p, u, flow_pf):
+    """Host batches of several device waves go through the chunked path: the copies of chunk i+1 / i-1 run on side
+    streams under the kernel of chunk i."""
+    if flow_pf is None or x.is_cuda or x.dtype != torch.float64 or x.dim() != 4 or not x.is_contiguous():
+        return False
+    for t in (p, u):
+        if t is not None and (t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous()):
+            return False
+    nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return x.shape[0] >= 8 * nsm
+
+
+def _traj_call_pipelined(flow_pf, beta, dt, nstep, x, p, u, seed, traj, chain0, want_h):
+    """FT-HMC trajectories of a HOST batch in (up to) four chunks of whole device waves.  The chains are independent and
+    the device RNG is keyed by the global chain index, so the chunks reproduce the single launch (fields and decisions
+    exactly; per-chain sums to rounding where the CTA width depends on the launch's batch size); what changes is that only
+    the first chunk's host-to-device copy and the last chunk's device-to-host copy are exposed."""
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        B, _, L0, L1 = x.shape
+        nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+        waves = -(-B // nsm)
+        per = -(-waves // 4) * nsm
+        bounds = [(a, min(B, a + per)) for a in range(0, B, per)]
+        main = torch.cuda.current_stream()
+        if dev not in _side_streams:
+            _side_streams[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = _side_streams[dev]
+        if u is not None:
+            u = u.reshape(-1)
+            if u.numel() != B:
+                raise _lib.FthmcError(-1, "u must have one entry per chain")
+        if p is not None and p.shape != x.shape:
+            raise _lib.FthmcError(-1, "p must have the shape of x")
+        xd, xo = torch.empty_like(x, device=dev), torch.empty_like(x, device=dev)
+        pd = None if p is None else torch.empty_like(p, device=dev)
+        ud = None if u is None else torch.empty_like(u, device=dev)
+        sc = torch.empty((6, B), dtype=torch.float64, device=dev)      # dH, exp(-dH), plaq, Q, h0, h1
+        acc = torch.empty(B, dtype=torch.int32, device=dev)
+        h_field = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)
+        h_sc = torch.empty((6, B), dtype=torch.float64, pin_memory=True)
+        h_acc = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        L = _lib.lib()
+        ws = _workspace(flow_pf.handle, min(B, per), L0, L1, dev)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+
+        def copy_in(a, b):                                   # (a pageable source blocks the host here, under the running kernel)
+            with torch.cuda.stream(s_in):
+                xd[a:b].copy_(x[a:b], non_blocking=True)
+                if pd is not None:
+                    pd[a:b].copy_(p[a:b], non_blocking=True)
+                if ud is not None:
+                    ud[a:b].copy_(u[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+            return e
+
+        ev = copy_in(*bounds[0])
+        for i, (a, b) in enumerate(bounds):
+            main.wait_event(ev)
+            _lib.check(L.fthmc_ft_hmc_traj(flow_pf.handle, xd[a:b].data_ptr(), xo[a:b].data_ptr(),
+                                           None if pd is None else pd[a:b].data_ptr(), None if ud is None else ud[a:b].data_ptr(),
+                                           seed, traj, chain0 + a, b - a, L0, L1, float(beta), float(dt), int(nstep),
+                                           sc[0, a:b].data_ptr(), sc[1, a:b].data_ptr(), acc[a:b].data_ptr(),
+                                           sc[2, a:b].data_ptr(), sc[3, a:b].data_ptr(),
+                                           sc[4, a:b].data_ptr() if want_h else None, sc[5, a:b].data_ptr() if want_h else None,
+                                           ws.data_ptr(), ws.numel(), main.cuda_stream))
+            k = torch.cuda.Event()
+            k.record(main)
+            if i + 1 < len(bounds):
+                ev = copy_in(*bounds[i + 1])
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(k)
+                h_field[a:b].copy_(xo[a:b], non_blocking=True)
+                for r in range(6 if want_h else 4):
+                    h_sc[r, a:b].copy_(sc[r, a:b], non_blocking=True)
+                h_acc[a:b].copy_(acc[a:b], non_blocking=True)
+        main.wait_stream(s_out)
+        main.synchronize()
+    res = dict(field=h_field, dH=h_sc[0], exp_mdH=h_sc[1], acc=h_acc.bool(), plaq=h_sc[2], topo=h_sc[3])
+    if want_h:
+        res.update(h0=h_sc[4], h1=h_sc[5])
+    return res
+
+
 def _traj_call(flow_pf, beta, dt, nstep, x, p, u, seed, traj, chain0, want_h=False):
     """shared body of hmc_batch / ft_hmc_batch.  x (B,2,L0,L1) on any device."""
+    if _pipelined_ok(x, p, u, flow_pf):
+        return _traj_call_pipelined(flow_pf, beta, dt, nstep, x, p, u, seed, traj, chain0, want_h)
     dev = _device(x)
     with torch.cuda.device(dev):
         xd = _dev_in(x, dev, torch.float64)

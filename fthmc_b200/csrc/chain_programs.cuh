@@ -20,6 +20,7 @@ enum ChainMode {
 struct ChainArgs {
     int mode;
     int B;
+    int b_begin, b_end;       // chains [b_begin, b_end) of the batch belong to this launch (set by the launcher)
     EngineParams pr;
     double beta, dt;
     int nstep;

@@ -58,6 +58,9 @@ __device__ unsigned long long g_prof[32];
 #ifndef FT_FAST_TRIG
 #define FT_FAST_TRIG 1
 #endif
+#ifndef FT_WAVE_LAUNCHES
+#define FT_WAVE_LAUNCHES 1
+#endif
 #ifndef FT_THREADS
 #define FT_THREADS 256          // threads per CTA of the resident-chain kernels
 #endif
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
     __syncthreads();
     en->ex.bar_init(Engine<ClusterExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
-    for (int b = cid; b < a.B; b += ncl) run_chain(*en, a, b);
+    for (int b = a.b_begin + cid; b < a.b_end; b += ncl) run_chain(*en, a, b);
     cl.sync();                                   // no CTA may exit while a peer can still address its shared memory
 }
 
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(256, 4) k_chain_plain(const ChainArgs a) {
         en->gW = nullptr;
     }
     __syncthreads();
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain_plain(*en, a, b);
+    for (int b = a.b_begin + blockIdx.x; b < a.b_end; b += gridDim.x) run_chain_plain(*en, a, b);
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
     __syncthreads();
     en->ex.bar_init(Engine<CtaExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) run_chain(*en, a, b);
+    for (int b = a.b_begin + blockIdx.x; b < a.b_end; b += gridDim.x) run_chain(*en, a, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -840,18 +843,29 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
     a.ws = (double*)ws;
     if (train) CK(cudaMemsetAsync(a.gbuf, 0, (size_t)chains * a.gbuf_stride * sizeof(double), (cudaStream_t)stream));
     const size_t smem = chain_smem_bytes(L0, L1, has_flow, nr);
-    if (nr == 1) {
-        if (has_flow) k_chain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
-        else k_chain_plain<<<chains, nt, smem, (cudaStream_t)stream>>>(a);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(chains * nr); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_chain_cluster, a));
+    // Flow programs run one device wave (the co-resident chains) per launch, back to back on the stream: the per-wave time
+    // of a long persistent launch creeps up as the SMs drift apart (6.70 ms for one wave, 6.90 ms per wave over 28 at
+    // L = 32, profiles/r1_wave_scaling.txt; 4096 chains: 192.9 ms in one launch, 186.2 ms in 28, profiles/r1_chunk_scaling.txt),
+    // and a launch boundary realigns them for a few microseconds.  Chains are addressed by their global index, so the
+    // split is invisible in the results.  The weight-gradient mode keeps one launch (its per-CTA accumulators are
+    // reduced after the launch), and so does plain HMC (a wave there lasts tens of microseconds).
+    const int per_launch = (has_flow && !train && FT_WAVE_LAUNCHES) ? chains : a.B;
+    for (int b0 = 0; b0 < a.B; b0 += per_launch) {
+        a.b_begin = b0; a.b_end = b0 + per_launch < a.B ? b0 + per_launch : a.B;
+        const int grid = a.b_end - a.b_begin < chains ? a.b_end - a.b_begin : chains;
+        if (nr == 1) {
+            if (has_flow) k_chain<<<grid, nt, smem, (cudaStream_t)stream>>>(a);
+            else k_chain_plain<<<grid, nt, smem, (cudaStream_t)stream>>>(a);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid * nr); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, k_chain_cluster, a));
+        }
+        g_launches++;
     }
-    g_launches++;
     CK(cudaGetLastError());
     return 0;
 }

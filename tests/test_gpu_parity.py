@@ -564,6 +564,30 @@ def test_statistical_known_answers():
         assert abs(float(torch.exp(-r["dH"][tail]).mean()) - 1.0) < 0.02          # <exp(-dH)> = 1
 
 
+def test_host_batches_pipelined_equal_single_launch():
+    """Host batches of >= 8 device waves run as chunks of whole waves with their copies on side streams: same fields,
+    decisions and charges as the single launch on device tensors (sums to rounding), in teacher-forced (p, u given) and
+    device-RNG mode."""
+    flow = O.random_flow(n_layers=4, seed=5, scale=2.0)
+    raw = np.stack([np.concatenate([np.concatenate([w.numpy().ravel(), b.numpy().ravel()]) for w, b in zip(lw.w, lw.b)])
+                    for lw in flow.layers])
+    pf = ft.PackedFlow(raw)
+    B = 8 * torch.cuda.get_device_properties(0).multi_processor_count + 37
+    gen = torch.Generator().manual_seed(99)
+    x = (torch.rand(B, 2, 8, 8, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi
+    p = torch.randn(B, 2, 8, 8, generator=gen, dtype=torch.float64)
+    u = torch.rand(B, generator=gen, dtype=torch.float64)
+    P = ft.Param(beta=2.0, lat=(8, 8), tau=0.4, nstep=4)
+    for kw_host, kw_dev in ((dict(p=p, u=u), dict(p=p.cuda(), u=u.cuda())), (dict(seed=7, traj=3, chain0=11),) * 2):
+        rh = ft.ft_hmc_batch(P, pf, x, want_h=True, **kw_host)
+        rd = ft.ft_hmc_batch(P, pf, x.cuda(), want_h=True, **kw_dev)
+        assert not rh["field"].is_cuda and rh["field"].is_pinned()
+        for k in ("field", "acc", "topo"):
+            assert torch.equal(rh[k], rd[k].cpu()), k
+        for k in ("dH", "exp_mdH", "plaq", "h0", "h1"):          # per-chain sums: the CTA width (hence the order of a chain's
+            assert float(torch.max(torch.abs(rh[k] - rd[k].cpu()))) < 1e-11, k      # reduction) may depend on the launch's batch
+
+
 def test_bitwise_reproducibility():
     """Same inputs, same bits: the resident-chain kernels have fixed reduction orders (no atomics), on the single-CTA
     path, the cluster path (DSMEM halos, cluster-wide reductions) and in the weight-gradient mode.  A missing barrier
