@@ -112,7 +112,7 @@ int fthmc_ft_hmc_traj(fthmc_flow_t flow, const double* field_in, double* field_o
 
 /* ---- run loops -------------------------------------------------------------------------------------------- */
 /* The trajectory loops of run(param, field) hmc_2dU1.py:697-707 / ipynb/ft_hmc.py:199-208 and ft_run(param, flow, field)
- * ipynb/ft_hmc.py:454-467: ntraj consecutive trajectories of every chain in ONE launch, the field resident in shared
+ * ipynb/ft_hmc.py:454-467: ntraj consecutive trajectories of every chain in ONE launch (one per device wave of chains), the field resident in shared
  * memory throughout.  Per-trajectory arrays are (ntraj, B) -- dH, exp(-dH), acc, and the two observables the
  * reference recomputes after every trajectory (plaq = action/(-beta V), floored topological charge) -- and p_in / u_in,
  * when given, are (ntraj, B, 2, L0, L1) / (ntraj, B) in trajectory order; NULL => Philox(seed, chain0+b, traj0+t). */
