@@ -17,6 +17,7 @@ SIGNATURES = {
     "fthmc_last_error_string": (ctypes.c_char_p, []),
     "fthmc_launch_count": (c_ull, []),
     "fthmc_diag_dfma_probe": (c_int, [c_dp, c_int, c_int, c_dp, ctypes.POINTER(c_dbl)]),
+    "fthmc_diag_dmma_probe": (c_int, [c_dp, c_int, c_int, c_dp, ctypes.POINTER(c_dbl)]),
     "fthmc_action": (c_int, [c_dp, c_int, c_int, c_int, c_dbl, c_int, c_dp, c_int, c_dp]),
     "fthmc_force": (c_int, [c_dp, c_int, c_int, c_int, c_dbl, c_int, c_dp, c_int, c_dp]),
     "fthmc_topo_charge": (c_int, [c_dp, c_int, c_int, c_int, c_int, c_dp, c_int, c_dp]),

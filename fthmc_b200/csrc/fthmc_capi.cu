@@ -651,6 +651,24 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* __restrict__ out, in
     if (s == 123.456) out[0] = s;      // keep the chains alive
 }
 
+// the same for the fp64 tensor path: 8 independent DMMA.8x8x4 accumulator tiles per warp; 512 flop per DMMA per warp
+__global__ void __launch_bounds__(256) k_dmma_probe(double* __restrict__ out, int iters) {
+    double c0[8], c1[8];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-3 + 1e-12 * blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c0[i] = 1.0 + i; c1[i] = 2.0 + i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+    if (s == 123.456) out[0] = s;
+}
+
 #ifdef FT_PROFILE
 extern "C" int fthmc_diag_profile(unsigned long long* out32_host, int reset) {
     if (out32_host) cudaMemcpyFromSymbol(out32_host, g_prof, sizeof(unsigned long long) * 32);
@@ -665,6 +683,15 @@ extern "C" int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void*
     g_launches++;
     CK(cudaGetLastError());
     if (flop_out) *flop_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    return 0;
+}
+
+extern "C" int fthmc_diag_dmma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out) {
+    if (!scratch || iters <= 0 || blocks <= 0) return fail(FTHMC_E_ARG, "bad probe arguments");
+    k_dmma_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)scratch, iters);
+    g_launches++;
+    CK(cudaGetLastError());
+    if (flop_out) *flop_out = 512.0 * 8.0 * (double)iters * 8.0 * (double)blocks;      // 8 tiles x 8 warps per CTA
     return 0;
 }
 

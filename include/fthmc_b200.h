@@ -144,6 +144,8 @@ int fthmc_grad_unpack(const double* grad_canon_host, int n_layers, const int* mu
 /* diagnostic: launch `blocks` x 256 threads of pure fp64 FMA chains (2*16*iters flop per thread); *flop_out (host)
  * receives the flop count.  Used by bench.py to measure the fp64 roofline denominator on the device. */
 int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);
+/* the same on the fp64 tensor path: 8 independent DMMA.8x8x4 accumulator tiles per warp (512 flop per DMMA per warp) */
+int fthmc_diag_dmma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);
 
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 unsigned long long fthmc_launch_count(void);

@@ -6,6 +6,8 @@ import csv, subprocess, sys, collections, re, os
 
 rep, out = sys.argv[1], sys.argv[2]
 note = sys.argv[3] if len(sys.argv) > 3 else ""
+json_out = sys.argv[4] if len(sys.argv) > 4 else None      # e.g. profiles/traffic.json: the figures bench.py quotes
+chains = int(sys.argv[5]) if len(sys.argv) > 5 else 148
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -18,11 +20,44 @@ keep = ['gpu__time_duration.sum', 'sm__throughput.avg.pct_of_peak_sustained_elap
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'launch__shared_mem_per_block_dynamic', 'launch__grid_size', 'launch__block_size',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'sm__cycles_active.avg']
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'sm__cycles_active.avg',
+        'sm__cycles_elapsed.avg', 'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__ops_path_tensor_src_fp64.sum', 'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed']
 lines = [f"# {os.path.basename(rep)}  {note}"]
 for h, u, v in zip(hdr, units, vals):
     if h in keep or (h.startswith('smsp__pcsamp_warps_issue_stalled') and not h.endswith('not_issued')):
         lines.append(f"{h} [{u}] = {v}")
+if json_out:
+    import json
+    m = {h_: float(v_.replace(",", "")) for h_, v_ in zip(hdr, vals) if h_ in keep and v_ not in ("", "no data")}
+    u_ = dict(zip(hdr, units))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    rd = m['dram__bytes_read.sum'] * scale.get(u_['dram__bytes_read.sum'], 1.0)
+    wr = m['dram__bytes_write.sum'] * scale.get(u_['dram__bytes_write.sum'], 1.0)
+    cyc = m['sm__cycles_elapsed.avg']
+    dfma = m['smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed'] * cyc
+    dadd = m['smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed'] * cyc
+    dmul = m['smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'] * cyc
+    tens = m['sm__ops_path_tensor_src_fp64.sum']               # flop on the fp64 tensor path (DMMA), 128 per cycle per SM at peak
+    json.dump({
+        "source": f"{os.path.basename(out)} (ncu --set full, one k_chain launch, {chains} chains, L=32, 24 layers, nstep=10)",
+        "chains": chains, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_chain_traj": (rd + wr) / chains,
+        "smem_wavefronts_pct_of_peak": m['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'],
+        "executed": {"dfma_thread_inst": dfma, "dadd_thread_inst": dadd, "dmul_thread_inst": dmul, "dmma_flop": tens,
+                     "flop_per_chain_traj": (2 * dfma + dadd + dmul + tens) / chains,
+                     "how": "2*DFMA + DADD + DMUL thread instructions (smsp__sass_thread_inst_executed_op_d*_pred_on) + "
+                            "sm__ops_path_tensor_src_fp64.sum, per launch / chains"},
+        "pipe_active": {"fp64_pct": m['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'],
+                        "dmma_subpipe_pct": m['sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active'],
+                        "issue_active_pct": m['smsp__issue_active.avg.pct_of_peak_sustained_active'],
+                        "note": "sm__pipe_fp64_cycles_active counts the DFMA/DADD/DMUL issue cycles only; the DMMA.8x8x4 tiles "
+                                "are counted by sm__pipe_tensor_subpipe_dmma_cycles_active.  Both run on one fp64 datapath "
+                                "(profiles/r1_fp64_pipes_probe.txt: 36.9 / 37.1 alone, 34.7 TFLOP/s together), so the datapath's "
+                                "duty is their sum"},
+        "kernel_ms": m['gpu__time_duration.sum'] if u_['gpu__time_duration.sum'] == 'ms' else None,
+    }, open(json_out, "w"), indent=1)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 h = rows[1]

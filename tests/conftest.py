@@ -47,10 +47,10 @@ def golden():
     return get
 
 
-def thousand_inputs(L, n=1000):
-    """Inputs of the 1000-trajectory parity runs (regenerated, not stored): see make_golden.thousand_inputs."""
+def thousand_inputs(L, n=1000, seed=None):
+    """Inputs of the many-trajectory parity runs (regenerated, not stored): see make_golden.thousand_inputs."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    return m.thousand_inputs(L, n)
+    return m.thousand_inputs(L, n) if seed is None else m.thousand_inputs(L, n, seed=seed)

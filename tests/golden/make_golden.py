@@ -295,6 +295,69 @@ def gen_thousand(plain, ftlib, ref, out):
     print("ft 1000: acc rate", np.mean(acc), "dH range", np.min(dH), np.max(dH))
 
 
+def headline_flow(ftlib, L, n_layers=24, seed_w=3647):
+    """The bench's flow: ipynb/ft_hmc.py:519 seeds 3647, :310-315 builds 24 layers, default Conv2d init."""
+    torch.manual_seed(seed_w)
+    flow = ftlib.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=n_layers, n_mixture_comps=2, hidden_sizes=[8, 8],
+                                      kernel_size=3)
+    flow.eval()
+    for prm in flow.parameters():
+        prm.requires_grad_(False)
+    return flow
+
+
+def gen_many(ftlib, ref, name, out, *, L, beta, legs, seed):
+    """BASELINE configs 2 and 3 at depth: teacher-forced ft_hmc (ipynb/ft_hmc.py:420-435) with the 24-layer seed-3647 flow,
+    every trajectory from its own input field / momentum / uniform (thousand_inputs(L, n, seed): regenerated by the tests,
+    not stored).  legs = [(nstep, n), ...]: consecutive slices of the inputs run at different nstep (tau = 1) so that the
+    set holds accepted AND rejected trajectories as well as the headline nstep=10."""
+    flow = headline_flow(ftlib, L)
+    ntot = sum(n for _, n in legs)
+    x, p, u = thousand_inputs(L, ntot, seed=seed)
+    dH, acc, topo, chk, nst = [], [], [], [], []
+    i = 0
+    for nstep, n in legs:
+        P = ref.Param(beta=beta, lat=(L, L), tau=1.0, nstep=nstep)
+        for _ in range(n):
+            with patched_rng(p[i][None], u[i]):
+                d, e, a, new = quiet(ref.ft_hmc, P, flow, x[i][None].clone())
+            dH.append(d); acc.append(bool(a)); topo.append(float(ref.topocharge(new[0]))); chk.append(float(new.sum()))
+            nst.append(nstep)
+            i += 1
+            if i % 20 == 0:
+                print(name, i, "/", ntot, "acc so far", np.mean(acc), flush=True)
+    np.savez_compressed(os.path.join(out, name + ".npz"), L=L, beta=beta, tau=1.0, n_layers=24, seed=seed,
+                        weights=flat_weights(flow), activation="silu", convention=0, nstep=np.array(nst),
+                        dH=np.array(dH), acc=np.array(acc), topo=np.array(topo), field_sum=np.array(chk))
+    print(name, "acc rate", np.mean(acc), "dH range", np.min(dH), np.max(dH))
+
+
+def gen_c4(ftlib, ref, out):
+    """BASELINE config 4: L=128 beta=6 with the L=16 flow transferred by the reference's own flow_resize
+    (ipynb/ft_hmc.py:489-513): one ft_action / ft_force and one teacher-forced trajectory."""
+    L = 128
+    flow16 = headline_flow(ftlib, 16)
+    flow = ref.flow_resize(flow16, (L, L))
+    flow.eval()
+    x, p, u = thousand_inputs(L, 1, seed=1284)
+    P = ref.Param(beta=6.0, lat=(L, L), tau=1.0, nstep=40)
+    rec = dict(L=L, beta=6.0, dt=P.dt, nstep=40, n_layers=24, weights=flat_weights(flow), activation="silu", convention=0,
+               seed=1284)
+    rec["ft_action"] = ref.ft_action(P, flow, x.clone()).detach().numpy().copy()
+    f = ref.ft_force(P, flow, x.clone()).numpy()
+    rec["ft_force_sum"] = np.array([f.sum(), np.abs(f).sum(), (f * f).sum()])
+    rec["ft_force_row0"] = f[0, :, 0, :].copy()
+    rec["ft_force_col5"] = f[0, :, :, 5].copy()
+    y = ref.ft_flow(flow, x.clone())
+    rec["flow_fwd_sum"] = np.array([float(y.sum()), float((y * y).sum())])
+    with patched_rng(p[0][None], u[0]):
+        d, e, a, new = quiet(ref.ft_hmc, P, flow, wrap(y).clone())
+    rec.update(traj_dH=d, traj_acc=bool(a), traj_topo=float(ref.topocharge(new[0])), traj_field_sum=float(new.sum()),
+               traj_plaq=float(ref.action(P, new[0]) / (-P.beta * P.volume)))
+    np.savez_compressed(os.path.join(out, "ft_L128_b6.npz"), **rec)
+    print("ft_L128_b6: dH", d, "acc", bool(a), "Q", rec["traj_topo"])
+
+
 def gen_run(plain, ftlib, ref, out):
     """The trajectory loops of run / ft_run (ipynb/ft_hmc.py:199-208, 454-467) seeded ONCE: a free-running chain whose
     momenta and uniforms come from consecutive draws of the torch generator, plus the block statistics of a synthetic
@@ -357,6 +420,15 @@ def main():
     if a.only == "run":
         gen_run(plain, ftlib, ref, a.out)
         return
+    if a.only == "c2":
+        gen_many(ftlib, ref, "ft_L16_b6_many", a.out, L=16, beta=6.0, legs=[(40, 200), (20, 30), (10, 30)], seed=20261016)
+        return
+    if a.only == "c3":
+        gen_many(ftlib, ref, "ft_L32_b4_many", a.out, L=32, beta=4.0, legs=[(40, 200), (20, 20), (10, 40)], seed=20261032)
+        return
+    if a.only == "c4":
+        gen_c4(ftlib, ref, a.out)
+        return
     gen_run(plain, ftlib, ref, a.out)
     gen_plain(plain, a.out)
     gen_flow_case(ftlib, ref, "ft_L8_n8", a.out, L=8, beta=2.0, n_layers=8, B=3, nstep=6, ntraj=6, scale=2.0)
@@ -366,6 +438,9 @@ def main():
                   tau=1.0)
     gen_leaky(plain, a.out)
     gen_thousand(plain, ftlib, ref, a.out)
+    gen_many(ftlib, ref, "ft_L16_b6_many", a.out, L=16, beta=6.0, legs=[(40, 200), (20, 30), (10, 30)], seed=20261016)
+    gen_many(ftlib, ref, "ft_L32_b4_many", a.out, L=32, beta=4.0, legs=[(40, 200), (20, 20), (10, 40)], seed=20261032)
+    gen_c4(ftlib, ref, a.out)
     try:
         gen_copyB(a.ref, a.out)
     except Exception as e:  # copy B is optional (it drags in the package's logger/config)

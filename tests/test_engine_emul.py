@@ -301,3 +301,20 @@ def test_bisection_replay_equals_plain_loop(golden, tmp_path):
         a, b = out[("replay", tol, conv)], out[("plain", tol, conv)]
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tol, conv)
     assert out[("replay", 1e-6, 0)][1].max() == 23 and out[("replay", 1e-13, 0)][1].min() > 40
+
+
+@pytest.mark.parametrize("name,picks", [("ft_L16_b6_many", (0, 3, 205, 240)), ("ft_L32_b4_many", (1, 230))])
+def test_headline_configs_sample(golden, name, picks):
+    """The engine (the code the GPU runs, compiled for the host) on a sample of the reference's 260-trajectory runs at
+    BASELINE configs 2 and 3: dH to 1e-8, decision and floored charge exact."""
+    from conftest import thousand_inputs
+    g = golden(name)
+    L = int(g["L"])
+    x, p, u = thousand_inputs(L, len(g["dH"]), seed=int(g["seed"]))
+    for i in picks:
+        nstep = int(g["nstep"][i])
+        o = E.run("ft_hmc", g["weights"], x[i:i + 1].numpy(), beta=float(g["beta"]), dt=float(g["tau"]) / nstep, nstep=nstep,
+                  p=p[i:i + 1].numpy(), u=u[i:i + 1].numpy())
+        assert abs(o["s"][0] - g["dH"][i]) < 1e-8
+        assert bool(o["acc"][0]) == bool(g["acc"][i]) and o["topo"][0] == g["topo"][i]
+        assert abs(o["field"].sum() - g["field_sum"][i]) < 2e-6

@@ -187,6 +187,51 @@ def test_thousand_trajectories_ft(golden):
     assert np.max(np.abs(r["field"].sum(dim=(1, 2, 3)).numpy() - g["field_sum"])) < 1e-7
 
 
+@pytest.mark.parametrize("name", ["ft_L16_b6_many", "ft_L32_b4_many"])
+def test_headline_configs_many_trajectories(golden, name):
+    """BASELINE configs 2 (L=16, beta=6) and 3 (L=32, beta=4) at depth: 260 teacher-forced trajectories of the REFERENCE
+    each (24-layer seed-3647 flow; 200 at nstep=40, where about half are accepted, the rest at nstep=20 and at the bench's
+    nstep=10), every one from its own field / momentum / uniform.  dH to 1e-8, accept/reject and floored charge bit-exact."""
+    g = golden(name)
+    pf = packed(g)
+    L, n = int(g["L"]), len(g["dH"])
+    x, p, u = thousand_inputs(L, n, seed=int(g["seed"]))
+    acc = g["acc"].astype(bool)
+    assert 0.25 < acc[g["nstep"] == 40].mean() < 0.75          # the decision check is not vacuous
+    assert len(np.unique(g["topo"])) > 3
+    for nstep in np.unique(g["nstep"]):
+        sel = np.nonzero(g["nstep"] == nstep)[0]
+        P = ft.Param(beta=float(g["beta"]), lat=(L, L), tau=float(g["tau"]), nstep=int(nstep))
+        r = ft.ft_hmc_batch(P, pf, x[sel], p[sel], u[sel])
+        assert np.max(np.abs(r["dH"].numpy() - g["dH"][sel])) < 1e-8, nstep
+        assert np.array_equal(r["acc"].numpy(), acc[sel]), nstep
+        assert np.array_equal(r["topo"].numpy(), g["topo"][sel]), nstep
+        assert np.max(np.abs(r["field"].sum(dim=(1, 2, 3)).numpy() - g["field_sum"][sel])) < 2e-6, nstep
+
+
+def test_config4_L128_reference_golden(golden):
+    """BASELINE config 4 pinned by the reference itself: L=128, beta=6, the L=16 flow transferred with the reference's
+    flow_resize (ipynb/ft_hmc.py:489-513), on the 16-CTA cluster path: ft_action, ft_force, the flowed field and one
+    teacher-forced trajectory (nstep=40)."""
+    g = golden("ft_L128_b6")
+    pf = ft.flow_resize(packed(g), (128, 128))
+    x, p, u = thousand_inputs(128, 1, seed=int(g["seed"]))
+    P = ft.Param(beta=6.0, lat=(128, 128), tau=float(g["dt"]) * int(g["nstep"]), nstep=int(g["nstep"]))
+    assert relerr(ft.ft_action(P, pf, x).numpy(), g["ft_action"]) < REL
+    f = ft.ft_force(P, pf, x).numpy()
+    assert relerr(np.array([f.sum(), np.abs(f).sum(), (f * f).sum()])[1:], g["ft_force_sum"][1:]) < REL
+    assert abs(f.sum() - g["ft_force_sum"][0]) < 1e-9 * g["ft_force_sum"][1]
+    assert relerr(f[0, :, 0, :], g["ft_force_row0"]) < REL and relerr(f[0, :, :, 5], g["ft_force_col5"]) < REL
+    y = ft.ft_flow(pf, x)
+    assert abs(float((y * y).sum()) - g["flow_fwd_sum"][1]) < 1e-10 * g["flow_fwd_sum"][1]
+    yw = torch.remainder(y + np.pi, 2 * np.pi) - np.pi
+    r = ft.ft_hmc_batch(P, pf, yw, p, u)
+    assert abs(float(r["dH"][0]) - float(g["traj_dH"])) < 1e-8
+    assert bool(r["acc"][0]) == bool(g["traj_acc"]) and float(r["topo"][0]) == float(g["traj_topo"])
+    assert abs(float(r["plaq"][0]) - float(g["traj_plaq"])) < 1e-11
+    assert abs(float(r["field"].sum()) - float(g["traj_field_sum"])) < 1e-5
+
+
 def test_ft_hmc_dropin_signature(golden):
     """ft_hmc(param, flow, field) on the reference's own kind of flow object (an nn.ModuleList-like
     container exposing layer.plaq_coupling.net), CPU tensors in, CPU tensors out."""

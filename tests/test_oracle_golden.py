@@ -160,3 +160,20 @@ def test_run_loops_follow_reference_chain(golden):
         assert abs(float(dH) - g["ft_dH"][i]) < 1e-8 and bool(acc) == bool(g["ft_acc"][i])
         assert float(O.topocharge(f)) == g["ft_topo"][i]
     assert np.max(np.abs(f.numpy() - g["ft_final"])) < 1e-8
+
+
+@pytest.mark.parametrize("name,picks", [("ft_L16_b6_many", (0, 3, 205, 240)), ("ft_L32_b4_many", (1, 230))])
+def test_headline_configs_sample(golden, name, picks):
+    """A sample of the 260-trajectory reference runs at BASELINE configs 2 and 3 (the GPU suite checks all of them): the
+    oracle reproduces the reference's dH bit for bit, its decision and its floored charge."""
+    from conftest import thousand_inputs
+    g = golden(name)
+    flow = oracle_flow_from_golden(g)
+    L = int(g["L"])
+    x, p, u = thousand_inputs(L, len(g["dH"]), seed=int(g["seed"]))
+    for i in picks:
+        nstep = int(g["nstep"][i])
+        dH, e, acc, new = O.ft_hmc(float(g["beta"]), float(g["tau"]) / nstep, nstep, flow, x[i][None], p=p[i][None], u=u[i])
+        assert dH == g["dH"][i] and bool(acc) == bool(g["acc"][i])
+        assert float(O.topocharge(new[0])) == g["topo"][i]
+        assert float(new.sum()) == g["field_sum"][i]
