@@ -41,15 +41,18 @@ class Param:
         self.randinit, self.nth, self.nth_interop = randinit, nth, nth_interop
 
     def initializer(self):
+        # float64 regardless of torch's default dtype: the reference scripts set the default tensor type to double
+        # (hmc_2dU1.py:684, ipynb/ft_hmc.py:522), and the momenta drawn by randn_like follow this dtype's RNG stream
         if self.randinit:
-            return torch.empty((self.nd,) + self.lat).uniform_(-math.pi, math.pi)
-        return torch.zeros((self.nd,) + self.lat)
+            return torch.empty((self.nd,) + self.lat, dtype=torch.float64).uniform_(-math.pi, math.pi)
+        return torch.zeros((self.nd,) + self.lat, dtype=torch.float64)
 
 
 # ------------------------------------------------------------------------------------------------
 # plumbing
 # ------------------------------------------------------------------------------------------------
-_ws = {}
+import threading
+_tls = threading.local()
 
 
 def _device(t=None):
@@ -60,12 +63,23 @@ def _device(t=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _workspace(flow_handle, B, L0, L1, dev):
-    need = _lib.lib().fthmc_workspace_bytes(flow_handle, B, L0, L1)
-    buf = _ws.get(dev)
+def _workspace(flow_handle, B, L0, L1, dev, need=None, kind="chain"):
+    """Scratch for one launch.  The kernels keep per-CTA state in it (momenta, the layer blocks of the adjoint, gradient
+    accumulators), so two launches in flight must never share one: buffers are cached per (device, STREAM, kind) -- launches
+    on one stream are ordered, launches on different streams get different buffers -- and per Python thread.  A buffer is
+    allocated while its stream is current, so the caching allocator's stream-ordered reuse makes replacing it safe."""
+    if need is None:
+        need = _lib.lib().fthmc_workspace_bytes(flow_handle, B, L0, L1)
+    cache = getattr(_tls, "ws", None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (dev.index, _stream(), kind)
+    buf = cache.get(key)
     if buf is None or buf.numel() < need:
+        if buf is not None:
+            buf.record_stream(torch.cuda.current_stream())
         buf = torch.empty(need, dtype=torch.uint8, device=dev)
-        _ws[dev] = buf
+        cache[key] = buf
     return buf
 
 
@@ -379,7 +393,11 @@ def ft_flow(flow, f, with_logJ=False):
 
 
 def ft_flow_inv(flow, f, with_logJ=False):
-    """ipynb/ft_hmc.py:225 -- F^{-1}(f) by per-chain bisection to 1e-6, decision for decision."""
+    """ipynb/ft_hmc.py:225 -- F^{-1}(f) by bisection to 1e-6, decision for decision.  The reference's stop test is the maximum
+    error over the WHOLE tensor it is given; its trajectory path always passes one chain, and the kernel applies the test
+    per chain.  For B > 1 the reference would keep halving every chain until the slowest one converges, so a batched call
+    here can stop a chain a few iterations earlier than a batched reference call would (difference <= 1e-6, the bisection
+    tolerance); decision-for-decision parity is for B = 1 calls, i.e. `ft_flow_inv(flow, f[b:b+1])` of the reference."""
     return _flow_call("inv", flow, f, want_logJ=with_logJ)
 
 
@@ -541,6 +559,39 @@ def ft_run(param, flow, field=None, out=None):
     return _run_loop(param, flow, field, out, topo_history)
 
 
+def run_hmc(param, x=None, out=None):
+    """run_hmc(param, x) (fthmc/hmc.py:57-175) without its directories, plots and dumps: `param.nrun` independent
+    experiments of `param.ntraj` plain-HMC trajectories each (every experiment restarts from `param.initializer()`, as the
+    reference does, unless x is given), one kernel launch per experiment with the chain resident on the SM.  Returns
+    (fields_arr, histories) like the reference: histories[n] has the lists traj / dt / acc / dH / plaq / q / dq; fields_arr[n]
+    holds the final field of experiment n (the reference keeps every intermediate field; the resident kernel does not
+    write them out).  Momenta and uniforms come from the torch generator in the reference's order."""
+    from timeit import default_timer as timer
+    fields_arr, histories = [], {}
+    for n in range(param.nrun):
+        t0 = timer()
+        f = param.initializer() if x is None else x
+        f = f.to(torch.float64)
+        q0 = float(topo_charge(f.unsqueeze(0))[0])
+        ps, us = [], []
+        for _ in range(param.ntraj):
+            ps.append(torch.randn_like(f))
+            us.append(torch.rand([], dtype=torch.float64))
+        r = hmc_run_batch(param, f.unsqueeze(0), param.ntraj, torch.stack(ps).unsqueeze(1), torch.stack(us).reshape(-1, 1))
+        dt = (timer() - t0) / param.ntraj
+        qs = [float(v) for v in r["topo"][:, 0]]
+        prev = [q0] + qs[:-1]
+        histories[n] = {"traj": [n * param.ntraj + i + 1 for i in range(param.ntraj)], "dt": [dt] * param.ntraj,
+                        "acc": [float(v) for v in r["acc"][:, 0]], "dH": [float(v) for v in r["dH"][:, 0]],
+                        "plaq": [float(v) for v in r["plaq"][:, 0]], "q": [int(v) for v in qs],
+                        "dq": [abs(a - b) for a, b in zip(qs, prev)]}
+        fields_arr.append([r["field"][0]])
+        if out is not None:
+            for line in _status_lines(n * param.ntraj, r):
+                out.write(line)
+    return fields_arr, histories
+
+
 # ------------------------------------------------------------------------------------------------
 # flow training: the gradient of the reverse-KL loss with respect to the CNN weights
 # ------------------------------------------------------------------------------------------------
@@ -557,12 +608,7 @@ def ft_action_grad(param, flow, x, want_force=False):
             raise _lib.FthmcError(-1, f"field must be (B,2,L0,L1), got {tuple(xd.shape)}")
         B, _, L0, L1 = xd.shape
         L = _lib.lib()
-        need = L.fthmc_grad_workspace_bytes(pf.handle, B, L0, L1)
-        key = ("grad", dev)
-        ws = _ws.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            _ws[key] = ws
+        ws = _workspace(pf.handle, B, L0, L1, dev, need=L.fthmc_grad_workspace_bytes(pf.handle, B, L0, L1), kind="grad")
         act = torch.empty(B, dtype=torch.float64, device=dev)
         gd = L.fthmc_grad_doubles()
         gc = torch.empty((pf.n_layers, gd), dtype=torch.float64, device=dev)

@@ -76,6 +76,26 @@ class FieldTransformation:
 
     _batch_hmc = hmc
 
+    def run(self, x=None, nprint=25, num_trajs=1024, out=None, **unused):
+        """fthmc/ft_hmc.py:272-346 without its plots / TensorBoard: `num_trajs` latent-space trajectories of the batch x,
+        after each one the physical-space metrics of the flowed field; returns the reference's `history` dict (lists with
+        one entry per trajectory: traj, dt, acc, dh, exp_mdh, plaq, q, dq).  `out`: file-like for the status lines."""
+        x = self.initializer() if x is None else x
+        if torch.cuda.is_available():
+            x = x.cuda()
+        history = {}
+        q = api.topo_charge(x)
+        for i in range(num_trajs):
+            x, metrics = self.hmc(x, step=i)
+            qold = history["q"][i - 1] if "q" in history else q
+            x_phys, _ = self.flow_forward(x)
+            metrics.update(self.lattice_metrics(x_phys, qold))
+            for key, val in metrics.items():
+                history.setdefault(key, []).append(val)
+            if out is not None and i % nprint == 0:
+                out.write(", ".join(f"{k}: {float(torch.as_tensor(v).double().mean()):.5g}" for k, v in metrics.items()) + "\n")
+        return history
+
     def initializer(self, rand=True):
         x = torch.zeros([self.config.nd] + list(self.config.lat), dtype=torch.float64)
         if rand:

@@ -75,20 +75,26 @@ def raw_weights_of(flow_module):
     return np.stack(rows)
 
 
-_cache = {}
+_packed = weakref.WeakKeyDictionary()           # module -> {(device, convention): (digest, PackedFlow)}; dies with the module
 
 
 def pack(flow, convention=0, device=None):
-    """PackedFlow for `flow`: a PackedFlow (returned as is) or a reference-style ModuleList.  Cached by
-    object identity + parameter versions, so repeated ft_hmc calls do not re-upload."""
+    """PackedFlow for `flow`: a PackedFlow (returned as is) or a reference-style ModuleList.  The packed copy is held in a
+    WeakKeyDictionary keyed by the module (so it lives and dies with it) and is validated by a digest of the raw weights on every call: in-place edits
+    through `.data` -- which do not bump a tensor's version counter, and which the reference's own set_weights uses -- are
+    seen, and a recycled id() can never alias another flow."""
     if isinstance(flow, PackedFlow):
         return flow
+    import hashlib
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    params = [p for layer in flow for p in layer.plaq_coupling.net.parameters()]
-    key = (id(flow), dev.index, convention)
-    ver = tuple((p.data_ptr(), p._version) for p in params)
-    hit = _cache.get(key)
-    if hit is not None and hit[0] == ver:
+    raw = raw_weights_of(flow)
+    digest = hashlib.blake2b(raw.tobytes(), digest_size=16).digest()
+    try:
+        slot = _packed.setdefault(flow, {})
+    except TypeError:                          # not weak-referenceable / hashable: pack without caching
+        slot = {}
+    hit = slot.get((dev.index, convention))
+    if hit is not None and hit[0] == digest:
         return hit[1]
     layers = list(flow)
     mu, off = [], []
@@ -103,9 +109,9 @@ def pack(flow, convention=0, device=None):
         mu.append(m)
         off.append(o)
     pc = layers[0].plaq_coupling
-    pf = PackedFlow(raw_weights_of(flow), mu=mu, off=off, activation=_activation_of(pc.net), convention=convention,
+    pf = PackedFlow(raw, mu=mu, off=off, activation=_activation_of(pc.net), convention=convention,
                     inv_prec=getattr(pc, "inv_prec", 1e-6), inv_max_iter=getattr(pc, "inv_max_iter", 1000), device=dev)
-    _cache[key] = (ver, pf)
+    slot[(dev.index, convention)] = (digest, pf)
     return pf
 
 

@@ -236,6 +236,64 @@ def gen_copyB(refroot, out):
     print("copyB_L8 done; roundtrip err", np.abs(wrap(torch.from_numpy(np.stack(invs)) - x)).max().item())
 
 
+def gen_copyB_physics(refroot, out):
+    """Copy B's physics helpers, fthmc/utils/qed_helpers.py: BatchAction (:166-186), batch_charges / topo_charge (:73-77,
+    :108-116), ft_flow / ft_flow_inv / ft_action / ft_force on (B,2,L,L) (:191-242) through a copy-B flow
+    (fthmc/utils/layers.py: [-pi,pi) convention), and the plain action / force / leapfrog / hmc (:261-311)."""
+    st = io.StringIO()
+    with contextlib.redirect_stdout(st), contextlib.redirect_stderr(st):
+        import fthmc.utils.layers as LB
+        import fthmc.utils.qed_helpers as Q
+    torch.set_default_dtype(torch.float64)
+    torch.set_default_tensor_type(torch.DoubleTensor)
+    L, B = 8, 3
+    torch.manual_seed(4243)
+    flow = LB.make_u1_equiv_layers(lattice_shape=(L, L), n_layers=8, n_mixture_comps=2, hidden_sizes=[8, 8], kernel_size=3)
+    flow.eval()
+    flow = flow.double()
+    for layer in flow:
+        layer.active_mask = layer.active_mask.double()
+    with torch.no_grad():
+        for prm in flow.parameters():
+            prm.mul_(2.0)
+    for prm in flow.parameters():
+        prm.requires_grad_(False)
+    P = types.SimpleNamespace(beta=2.5, dt=0.1, nstep=5, volume=L * L)
+    torch.manual_seed(1332)
+    x = torch.empty((B, 2, L, L)).uniform_(-np.pi, np.pi)
+    rec = dict(L=L, n_layers=8, weights=flat_weights(flow), activation="silu", convention=1, beta=P.beta, dt=P.dt, nstep=P.nstep,
+               x=x.numpy().copy())
+    rec["batch_action"] = Q.BatchAction(P.beta)(x).numpy().copy()
+    rec["batch_charges"] = Q.batch_charges(x).numpy().copy()
+    rec["topo_charge"] = Q.topo_charge(x).numpy().copy()
+    rec["ft_flow"] = Q.ft_flow(flow, x.clone()).numpy().copy()
+    rec["ft_action"] = Q.ft_action(P, flow, x.clone()).detach().numpy().copy()
+    rec["ft_force"] = Q.ft_force(P, flow, x.clone()).numpy().copy()
+    inv = [Q.ft_flow_inv(flow, torch.from_numpy(rec["ft_flow"][b:b + 1]).clone()).numpy()[0].copy() for b in range(B)]
+    rec["ft_flow_inv_of_fwd"] = np.stack(inv)
+    # plain single-chain functions
+    x1 = x[0].clone()
+    rec["action"] = float(Q.action(P, x1))
+    rec["force"] = Q.force(P, x1.clone()).numpy().copy()
+    p1 = torch.randn_like(x1)
+    lx, lp = Q.leapfrog(P, x1.clone(), p1, verbose=False)
+    rec.update(lf_p=p1.numpy().copy(), lf_x_out=lx.numpy().copy(), lf_p_out=lp.numpy().copy())
+    xs, ps, us, dHs, accs, outs = [], [], [], [], [], []
+    cur = x1.clone()
+    for n in range(8):
+        seed = 9100 + n
+        p, u = replay_p_u(seed, cur.shape)
+        torch.manual_seed(seed)
+        dH, e, acc, new = Q.hmc(P, cur.clone(), verbose=False)
+        xs.append(cur.numpy().copy()); ps.append(p.numpy().copy()); us.append(float(u))
+        dHs.append(float(dH)); accs.append(bool(acc)); outs.append(new.numpy().copy())
+        cur = new.detach().clone()
+    rec.update(traj_x=np.stack(xs), traj_p=np.stack(ps), traj_u=np.array(us), traj_dH=np.array(dHs), traj_acc=np.array(accs),
+               traj_out=np.stack(outs))
+    np.savez_compressed(os.path.join(out, "copyB_physics_L8.npz"), **rec)
+    print("copyB_physics_L8: ft_action", rec["ft_action"], "hmc acc", accs, "dH", dHs[:3])
+
+
 def thousand_inputs(L, n=1000, seed=20261018):
     """Deterministic inputs for the 1000-trajectory parity runs; regenerated (not stored) by the tests.
     torch's CPU generator is bit-reproducible across machines."""
@@ -426,6 +484,9 @@ def main():
     if a.only == "c3":
         gen_many(ftlib, ref, "ft_L32_b4_many", a.out, L=32, beta=4.0, legs=[(40, 200), (20, 20), (10, 40)], seed=20261032)
         return
+    if a.only == "copyB":
+        gen_copyB_physics(a.ref, a.out)
+        return
     if a.only == "c4":
         gen_c4(ftlib, ref, a.out)
         return
@@ -442,6 +503,7 @@ def main():
     gen_many(ftlib, ref, "ft_L32_b4_many", a.out, L=32, beta=4.0, legs=[(40, 200), (20, 20), (10, 40)], seed=20261032)
     gen_c4(ftlib, ref, a.out)
     try:
+        gen_copyB_physics(a.ref, a.out)
         gen_copyB(a.ref, a.out)
     except Exception as e:  # copy B is optional (it drags in the package's logger/config)
         print("copyB generation failed:", repr(e))

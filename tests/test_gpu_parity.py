@@ -591,6 +591,42 @@ def test_field_transformation_class(golden):
     assert lm["plaq"].shape == (x.shape[0],) and float(lm["plaq"].abs().max()) <= 1.0
 
 
+def test_copyB_physics_golden(golden):
+    """Reference-generated goldens of the package copy's physics helpers (fthmc/utils/qed_helpers.py:73-116 batch_charges /
+    topo_charge, :166-186 BatchAction, :191-242 ft_flow / ft_flow_inv / ft_action / ft_force on (B,2,L,L), :261-311 action /
+    force / leapfrog / hmc) against the CUDA entry points and the FieldTransformation class, [-pi,pi) convention."""
+    import types
+    g = golden("copyB_physics_L8")
+    pf = packed(g)
+    assert pf.convention == 1
+    beta, x = float(g["beta"]), T(g["x"])
+    assert relerr(ft.u1_action(beta, x).numpy(), g["batch_action"]) < REL
+    assert np.max(np.abs(ft.topo_charge(x).numpy() - g["batch_charges"])) < 1e-11
+    cfg = types.SimpleNamespace(beta=beta, volume=64, lat=[8, 8], nd=2)
+    lf = types.SimpleNamespace(dt=float(g["dt"]), tau=float(g["dt"]) * int(g["nstep"]), nstep=int(g["nstep"]))
+    FT = ft.FieldTransformation(pf, cfg, lf)
+    assert relerr(FT.action(x).numpy(), g["ft_action"]) < REL
+    assert relerr(FT.force(x).numpy(), g["ft_force"]) < REL
+    y, _ = FT.flow_forward(x)
+    assert np.max(np.abs(y.numpy() - g["ft_flow"])) < 1e-12
+    for b in range(x.shape[0]):
+        xi, _ = FT.flow_backward(T(g["ft_flow"][b:b + 1]))
+        assert np.max(np.abs(xi.numpy()[0] - g["ft_flow_inv_of_fwd"][b])) < 1e-10
+    lm = FT.lattice_metrics(x, torch.zeros(x.shape[0]))
+    assert relerr(lm["plaq"].numpy(), -g["batch_action"] / (beta * 64)) < REL
+    assert np.max(np.abs(lm["q"].numpy() - g["batch_charges"])) < 1e-11
+    # plain single-chain helpers
+    P = ft.Param(beta=beta, lat=(8, 8), tau=lf.tau, nstep=lf.nstep)
+    assert abs(float(ft.action(P, x[0])) - float(g["action"])) < 1e-10 * abs(float(g["action"]))
+    assert relerr(ft.force(P, x[0], order=0).numpy(), g["force"]) < REL
+    lx, lp = ft.leapfrog(P, x[0], T(g["lf_p"]))
+    assert np.max(np.abs(lx.numpy() - g["lf_x_out"])) < 1e-11 and np.max(np.abs(lp.numpy() - g["lf_p_out"])) < 1e-11
+    r = ft.hmc_batch(P, T(g["traj_x"]), T(g["traj_p"]), T(g["traj_u"]))
+    assert np.max(np.abs(r["dH"].numpy() - g["traj_dH"])) < 1e-8
+    assert np.array_equal(r["acc"].numpy(), g["traj_acc"])
+    assert np.max(np.abs(r["field"].numpy() - g["traj_out"])) < 1e-9
+
+
 def test_statistical_known_answers():
     """The reference's recorded physics: <cos P> = I1(beta)/I0(beta) (PLAQ_EXACT, fthmc/config.py:37-47:
     0.69777 at beta=2) and <Q^2> = 1.23 +- 0.02 at L=8, beta=2 (hmc_2dU1.py:661), from 2048 device-RNG chains of plain HMC

@@ -39,9 +39,11 @@ def test_block_statistics_match_reference(golden):
     g = golden("run_L8")
     hist = list(g["stat_hist"][100:])
     got = np.array(stats.change_sqr_vs_dt(hist, 10), dtype=np.float64)
-    assert np.array_equal(got, g["stat_change_sqr_vs_dt"])
+    assert np.allclose(got, g["stat_change_sqr_vs_dt"], rtol=1e-13, atol=0)     # (numpy's pairwise sums vs the reference's sequential ones)
     assert [len(b) for b in stats.block_list(list(range(37)))] == list(g["stat_block_sizes"])
-    assert np.array_equal(np.array(stats.topo_change_sqr(list(g["stat_hist"]), 10)), g["stat_change_sqr_vs_dt"])
+    assert np.allclose(np.array(stats.topo_change_sqr(list(g["stat_hist"]), 10)), g["stat_change_sqr_vs_dt"], rtol=1e-13, atol=0)
+    m2, e2 = stats.mean_and_error(stats.block_means(np.arange(64.0)), standard_error=True)
+    assert abs(m2 - 31.5) < 1e-12 and e2 > 0
     q = np.stack([g["stat_hist"], g["stat_hist"][::-1]], axis=1)
     m, e = stats.batched_topo_change_sqr(q, dt=1)
     assert m > 0 and e >= 0

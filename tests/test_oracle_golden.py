@@ -177,3 +177,31 @@ def test_headline_configs_sample(golden, name, picks):
         assert dH == g["dH"][i] and bool(acc) == bool(g["acc"][i])
         assert float(O.topocharge(new[0])) == g["topo"][i]
         assert float(new.sum()) == g["field_sum"][i]
+
+
+def test_copyB_physics(golden):
+    """Copy B's helpers (fthmc/utils/qed_helpers.py) against the oracle in the package conventions: the oracle is a
+    restatement of copy A, so agreement here is to rounding (different term order in the plaquette), not bit for bit."""
+    g = golden("copyB_physics_L8")
+    flow = oracle_flow_from_golden(g)
+    assert flow.convention == 1
+    beta, x = float(g["beta"]), T(g["x"])
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(np.asarray(b))))
+    assert rel(O.u1_action(beta, x).numpy(), g["batch_action"]) < 1e-13
+    assert np.max(np.abs(O.topo_charge(x).numpy() - g["batch_charges"])) < 1e-12
+    assert np.max(np.abs(O.topo_charge(x).numpy() - g["topo_charge"])) < 1e-12      # (the two differ in their last ulp: term order)
+    assert np.max(np.abs(O.ft_flow(flow, x).numpy() - g["ft_flow"])) < 1e-12
+    assert rel(O.ft_action(beta, flow, x).numpy(), g["ft_action"]) < 1e-12
+    assert rel(O.ft_force(beta, flow, x).numpy(), g["ft_force"]) < 1e-12
+    for b in range(x.shape[0]):
+        xi = O.ft_flow_inv(flow, T(g["ft_flow"][b:b + 1]))
+        assert np.max(np.abs(xi.numpy()[0] - g["ft_flow_inv_of_fwd"][b])) < 1e-11
+    dt, nstep = float(g["dt"]), int(g["nstep"])
+    assert abs(float(O.action(beta, x[0])) - float(g["action"])) < 1e-12
+    assert np.max(np.abs(O.force(beta, x[0]).numpy() - g["force"])) < 1e-13
+    lx, lp = O.leapfrog(beta, dt, nstep, x[0], T(g["lf_p"]))
+    assert np.max(np.abs(lx.numpy() - g["lf_x_out"])) < 1e-13 and np.max(np.abs(lp.numpy() - g["lf_p_out"])) < 1e-13
+    for n in range(len(g["traj_u"])):
+        dH, e, acc, new = O.hmc(beta, dt, nstep, T(g["traj_x"][n]), p=T(g["traj_p"][n]), u=torch.tensor(g["traj_u"][n]))
+        assert abs(float(dH) - g["traj_dH"][n]) < 1e-11 and bool(acc) == bool(g["traj_acc"][n])
+        assert np.max(np.abs(new.numpy() - g["traj_out"][n])) < 1e-12
