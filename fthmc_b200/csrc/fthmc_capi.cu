@@ -720,6 +720,8 @@ static DevInfo& devinfo() {
     return d;
 }
 
+static int nsm() { const int n = devinfo().sm; return n > 0 ? n : 148; }
+
 // one thread per task (a task = one row of one stripe group; plain HMC: one site)
 static int chain_threads_narrow(int L0, int L1, bool flow, int nr) {
     int tasks = (flow ? (L0 * L1) / 4 : L0 * L1) / nr;
@@ -823,7 +825,7 @@ static long long resident_bound(int L0, int L1, bool flow, int nr, int B) {
         const int r = chain_resident(L0, L1, flow, nr, B);
         if (r > 0) return r;
     }
-    return nr == 1 ? (long long)(d.sm > 0 ? d.sm : 148) * 32 : (long long)(d.sm > 0 ? d.sm : 148) / nr;
+    return nr == 1 ? (long long)nsm() * 32 : (long long)nsm() / nr;
 }
 
 extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
@@ -904,7 +906,7 @@ static int launch_chain(ChainArgs& a, fthmc_flow_t flow, int L0, int L1, void* w
 template <typename T, int WHAT, int ORDER>
 static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta, int rounded, void* out, cudaStream_t st) {
     int nc = 1;
-    while (nc < 16 && (long long)B * nc < 4 * 148 && 2 * nc <= L0 && (long long)(L0 / (2 * nc)) * L1 >= 1024) nc *= 2;
+    while (nc < 16 && (long long)B * nc < 4 * nsm() && 2 * nc <= L0 && (long long)(L0 / (2 * nc)) * L1 >= 1024) nc *= 2;
     const int rows = (L0 + nc - 1) / nc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -914,12 +916,12 @@ static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta
     // 16-byte vector path: whole vectors per row, 16-byte aligned rows
     const bool vec = L1 % Vec<T>::N == 0 && ((uintptr_t)links & 15) == 0;
     const size_t chain_bytes = (size_t)2 * L0 * L1 * sizeof(T);
-    if (FT_STENCIL_TMA && nc == 1 && vec && chain_bytes <= 32 * 1024 && chain_bytes % 16 == 0 && L0 * (L1 / Vec<T>::N) >= 64 && B >= 16 * 148) {
+    if (FT_STENCIL_TMA && nc == 1 && vec && chain_bytes <= 32 * 1024 && chain_bytes % 16 == 0 && L0 * (L1 / Vec<T>::N) >= 64 && B >= 16 * nsm()) {
         constexpr int NSTAGE = FT_TMA_STAGES;
         const int stage_elems = (int)(((chain_bytes + 127) / 128) * 128 / sizeof(T));
         const size_t smem = (size_t)NSTAGE * stage_elems * sizeof(T) + NSTAGE * 8 + 16 * 8;
         int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
-        int grid = 148 * per_sm; if (grid > B) grid = B;
+        int grid = nsm() * per_sm; if (grid > B) grid = B;
         auto kern = k_action_topo_tma<T, NSTAGE, WHAT, ORDER>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 256, smem, st>>>((const T*)links, B, L0, L1, stage_elems, beta, rounded, (T*)out);
@@ -927,7 +929,7 @@ static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta
         CK(cudaGetLastError());
         return 0;
     }
-    if (nc == 1 && vec && (long long)L0 * L1 <= 4096 && L0 * (L1 / Vec<T>::N) >= 32 && B >= 16 * 148) {
+    if (nc == 1 && vec && (long long)L0 * L1 <= 4096 && L0 * (L1 / Vec<T>::N) >= 32 && B >= 16 * nsm()) {
         k_action_topo_warp<T, WHAT, ORDER><<<(B + 7) / 8, 256, 0, st>>>((const T*)links, B, L0, L1, beta, rounded, (T*)out);
         g_launches += 1;
         CK(cudaGetLastError());
@@ -952,24 +954,41 @@ static int reduce_launch(const void* links, int B, int L0, int L1, int what, int
 static int check_stencil(const void* in, const void* out, int B, int L0, int L1, int dtype) {
     if (!in || !out) return fail(FTHMC_E_ARG, "null pointer");
     if (B <= 0 || L0 <= 0 || L1 <= 0) return fail(FTHMC_E_ARG, "B, L0, L1 must be positive");
-    if (B > 65535) return fail(FTHMC_E_ARG, "B > 65535: split the batch");
     if (dtype != FTHMC_F64 && dtype != FTHMC_F32) return fail(FTHMC_E_DTYPE, "dtype must be FTHMC_F64 or FTHMC_F32");
+    return 0;
+}
+
+// the chain-per-CTA stencils carry the batch in grid.y (<= 65535): larger batches go in consecutive launches
+constexpr int STENCIL_MAX_B = 65535;
+template <class F> static int for_batch_chunks(int B, F launch) {
+    for (int b0 = 0; b0 < B; b0 += STENCIL_MAX_B) {
+        const int rc = launch(b0, B - b0 < STENCIL_MAX_B ? B - b0 : STENCIL_MAX_B);
+        if (rc) return rc;
+    }
     return 0;
 }
 
 extern "C" int fthmc_action(const void* links, int B, int L0, int L1, double beta, int order, void* out, int dtype, void* stream) {
     int rc = check_stencil(links, out, B, L0, L1, dtype); if (rc) return rc;
     if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
-    return dtype == FTHMC_F64 ? reduce_launch<double>(links, B, L0, L1, 0, order, beta, 0, out, (cudaStream_t)stream)
-                              : reduce_launch<float>(links, B, L0, L1, 0, order, beta, 0, out, (cudaStream_t)stream);
+    const size_t es = dtype == FTHMC_F64 ? 8 : 4, cs = (size_t)2 * L0 * L1 * es;
+    return for_batch_chunks(B, [&](int b0, int nb) {
+        const void* in = (const char*)links + b0 * cs; void* o = (char*)out + b0 * es;
+        return dtype == FTHMC_F64 ? reduce_launch<double>(in, nb, L0, L1, 0, order, beta, 0, o, (cudaStream_t)stream)
+                                  : reduce_launch<float>(in, nb, L0, L1, 0, order, beta, 0, o, (cudaStream_t)stream);
+    });
 }
 
 extern "C" int fthmc_topo_charge(const void* links, int B, int L0, int L1, int rounded, void* out, int dtype, void* stream) {
     int rc = check_stencil(links, out, B, L0, L1, dtype); if (rc) return rc;
     // rounded: hmc_2dU1.topocharge (plaqphase order, regularize); else field_transformation.topo_charge (u1_plaq order, torch_wrap)
     const int what = rounded ? 1 : 2, order = rounded ? 1 : 0;
-    return dtype == FTHMC_F64 ? reduce_launch<double>(links, B, L0, L1, what, order, 0.0, rounded, out, (cudaStream_t)stream)
-                              : reduce_launch<float>(links, B, L0, L1, what, order, 0.0, rounded, out, (cudaStream_t)stream);
+    const size_t es = dtype == FTHMC_F64 ? 8 : 4, cs = (size_t)2 * L0 * L1 * es;
+    return for_batch_chunks(B, [&](int b0, int nb) {
+        const void* in = (const char*)links + b0 * cs; void* o = (char*)out + b0 * es;
+        return dtype == FTHMC_F64 ? reduce_launch<double>(in, nb, L0, L1, what, order, 0.0, rounded, o, (cudaStream_t)stream)
+                                  : reduce_launch<float>(in, nb, L0, L1, what, order, 0.0, rounded, o, (cudaStream_t)stream);
+    });
 }
 
 extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta, int order, void* force_out, int dtype, void* stream) {
@@ -985,29 +1004,33 @@ extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta
     if (rows > L0) rows = L0;
     rows = (L0 + (L0 + rows - 1) / rows - 1) / ((L0 + rows - 1) / rows);          // equal tiles
     // small batches of large lattices: shorter tiles until the grid fills the device
-    while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) < 4 * 148) rows = (rows + 1) / 2;
+    while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) < 4 * nsm()) rows = (rows + 1) / 2;
     const int nchunk = (L0 + rows - 1) / rows;
     const size_t smem = (size_t)(rows + 1) * L1 * es;
     const int vw = dtype == FTHMC_F64 ? Vec<double>::N : Vec<float>::N;
     const bool vec = L1 % vw == 0 && ((uintptr_t)links & 15) == 0 && ((uintptr_t)force_out & 15) == 0;
-    if (dtype == FTHMC_F64) {
-        auto kern = vec ? k_force<double, true> : k_force<double, false>;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        kern<<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const double*)links, L0, L1, rows, beta, order, (double*)force_out);
-    } else {
-        auto kern = vec ? k_force<float, true> : k_force<float, false>;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        kern<<<dim3(nchunk, B), 256, smem, (cudaStream_t)stream>>>((const float*)links, L0, L1, rows, (float)beta, order, (float*)force_out);
-    }
-    g_launches++;
-    CK(cudaGetLastError());
-    return 0;
+    const size_t cs = (size_t)2 * L0 * L1 * es;
+    return for_batch_chunks(B, [&](int b0, int nb) -> int {
+        const char* in = (const char*)links + b0 * cs; char* fo = (char*)force_out + b0 * cs;
+        if (dtype == FTHMC_F64) {
+            auto kern = vec ? k_force<double, true> : k_force<double, false>;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const double*)in, L0, L1, rows, beta, order, (double*)fo);
+        } else {
+            auto kern = vec ? k_force<float, true> : k_force<float, false>;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const float*)in, L0, L1, rows, (float)beta, order, (float*)fo);
+        }
+        g_launches++;
+        CK(cudaGetLastError());
+        return 0;
+    });
 }
 
 extern "C" int fthmc_regularize(const void* in, void* out, long long n, int dtype, void* stream) {
     if (!in || !out || n <= 0) return fail(FTHMC_E_ARG, "null pointer or n <= 0");
     const int vec = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
-    long long blocks = (n / 2 + 255) / 256; if (blocks < 1) blocks = 1; if (blocks > 148 * 32) blocks = 148 * 32;
+    long long blocks = (n / 2 + 255) / 256; if (blocks < 1) blocks = 1; if (blocks > nsm() * 32) blocks = nsm() * 32;
     if (dtype == FTHMC_F64) k_regularize<double><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, n, vec);
     else if (dtype == FTHMC_F32) k_regularize<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)in, (float*)out, n, vec);
     else return fail(FTHMC_E_DTYPE, "dtype must be FTHMC_F64 or FTHMC_F32");

@@ -591,6 +591,21 @@ def test_field_transformation_class(golden):
     assert lm["plaq"].shape == (x.shape[0],) and float(lm["plaq"].abs().max()) <= 1.0
 
 
+def test_stencils_beyond_grid_y_limit():
+    """BASELINE config 5 asks for 65 536 chains: the stencil entry points take batches beyond the 65 535 a CUDA grid.y holds."""
+    B, L = 65536 + 300, 8
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi
+    P = ft.Param(beta=4.0, lat=(L, L))
+    xd = x.cuda()
+    sel = torch.tensor([0, 1, 65534, 65535, 65536, B - 1])
+    assert relerr(ft.u1_action(4.0, xd).cpu()[sel].numpy(), O.u1_action(4.0, x[sel]).numpy()) < REL
+    assert np.array_equal(ft.topocharge(xd).cpu()[sel].numpy(), np.array([float(O.topocharge(x[i])) for i in sel]))
+    f = ft.force(P, xd).cpu()
+    for i in sel:
+        assert relerr(f[i].numpy(), O.force_closed_form(4.0, x[i]).numpy()) < REL
+
+
 def test_copyB_physics_golden(golden):
     """Reference-generated goldens of the package copy's physics helpers (fthmc/utils/qed_helpers.py:73-116 batch_charges /
     topo_charge, :166-186 BatchAction, :191-242 ft_flow / ft_flow_inv / ft_action / ft_force on (B,2,L,L), :261-311 action /
