@@ -429,6 +429,48 @@ def run_ours(a):
     h2d = B * 2 * L * L * 8
     d2h = B * 2 * L * L * 8 + B * (5 * 8 + 4)
 
+    # ---- BASELINE config 5 as quoted (N > 1 only): 8192 chains per GPU (65 536 at N = 8), the observables all-reduce after
+    # every trajectory batch, and one flow-training step whose 24 x 955-double gradient is all-reduced over NCCL ----
+    c5 = None
+    if world > 1:
+        B5 = 8192
+        gen5 = torch.Generator().manual_seed(4331 + rank)
+        x5 = torch.empty(B5, 2, L, L, dtype=torch.float64).uniform_(-np.pi, np.pi, generator=gen5).to(dev)
+        c05, _ = shard.chain_partition(world * B5, rank, world)
+        r5 = ft.ft_hmc_batch(P, pf, x5, seed=20261018, traj=0, chain0=c05)          # warm-up
+        sync_all()
+        n5 = 2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n5):
+            r5 = ft.ft_hmc_batch(P, pf, r5["field"], seed=20261018, traj=1 + k, chain0=c05)
+            obs5 = shard.allreduce_observables(shard.local_observable_sums(r5))
+        e1.record()
+        sync_all()
+        t5 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        del x5, r5
+        tr = ft.FlowTrainer(ft.default_init_raw(a.layers, 3647), (L, L), beta=a.beta, lr=1e-4, seed=100 + rank)
+        Bt = 4 * torch.cuda.get_device_properties(dev).multi_processor_count                 # four device waves of prior samples per rank
+        tr.train_step(Bt)                                                                   # warm-up (packs, allocates)
+        sync_all()
+        nt = 3
+        t0 = time.perf_counter()
+        for _ in range(nt):
+            m5 = tr.train_step(Bt)
+        torch.cuda.synchronize()
+        tt = torch.tensor([(time.perf_counter() - t0) / nt * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wsum = torch.tensor([float(tr.raw.detach().sum()), float(tr.raw.detach().abs().sum())], dtype=torch.float64, device=dev)
+        wmin, wmax = wsum.clone(), wsum.clone()
+        dist.all_reduce(wmin, op=dist.ReduceOp.MIN); dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        c5 = {"chains_total": world * B5, "chains_per_gpu": B5, "steps": n5, "ms_per_step": float(t5) / n5,
+              "value": world * B5 * n5 / (float(t5) * 1e-3), "unit": UNIT, "observables_allreduce": "7 doubles per step, NCCL",
+              "train_step": {"samples_per_gpu": Bt, "ms_per_step": float(tt), "samples_per_s": world * Bt / (float(tt) * 1e-3),
+                             "gradient_allreduce_doubles": int(tr.raw.numel()) + 2, "backend": dist.get_backend(),
+                             "identical_weights_on_all_ranks": bool(torch.equal(wmin, wmax)), "dkl": m5["dkl"]}}
+        del tr
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -450,8 +492,8 @@ def run_ours(a):
             e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         return flop.value / (best * 1e-3) / 1e12, best
-    dfma_peak, dfma_ms = probe(lib.fthmc_diag_dfma_probe, 1500000)
-    dmma_peak, dmma_ms = probe(lib.fthmc_diag_dmma_probe, 190000)
+    dfma_peak, dfma_ms = probe(lib.fthmc_diag_dfma_probe, 300000)
+    dmma_peak, dmma_ms = probe(lib.fthmc_diag_dmma_probe, 40000)
     fp64_peak = max(dfma_peak, dmma_peak)
     kms = float(np.mean(kern_ms))
     alg_flop = alg_flop_per_chain_traj(a) * B
@@ -501,6 +543,8 @@ def run_ours(a):
             "gpu_launches": int(launches), "clocks": clk,
             "observables": {"plaq": float(obs_h[0] / obs_h[6]), "acc_rate": float(obs_h[3] / obs_h[6]),
                             "mean_dH": float(obs_h[4] / obs_h[6]), "Q2": float(obs_h[2] / obs_h[6])}}
+    if c5 is not None:
+        line["c5"] = c5
     line["stencils"] = stencil_rooflines(ft, P, hbm_peak, dev)
     # supplementary: tau=1 / nstep=10 from a hot start has dH ~ 11 and accepts nothing; the same
     # workload at an nstep that accepts (40) shows the sampler doing physics.  One untimed warm-up, one timed launch.
