@@ -407,9 +407,13 @@ def ft_action(param, flow, f):
 
 
 def ft_force(param, flow, field, create_graph=False):
-    """ipynb/ft_hmc.py:240 -- d/dfield sum(ft_action): hand-written adjoint kernel, no autograd."""
+    """ipynb/ft_hmc.py:240 -- d/dfield sum(ft_action): hand-written adjoint kernel, no autograd.  The reference's
+    create_graph=True exists for one purpose, the force-norm training loss (ipynb/ft_hmc.py:266-269: loss = sum(force^2),
+    loss.backward()); a kernel cannot hand back an autograd graph, so that use is served by `ft_force_norm_grad`, which
+    returns the loss and its gradient with respect to the weights directly."""
     if create_graph:
-        raise NotImplementedError("create_graph=True (second-order training path) is outside the trajectory path")
+        raise NotImplementedError("no autograd graph comes out of a CUDA kernel: use ft_force_norm_grad(param, flow, field) for the "
+                                  "force-norm loss and its weight gradient (FlowTrainer.train_step(with_force=True) does)")
     return _flow_call("force", flow, field, beta=param.beta)
 
 
@@ -620,3 +624,40 @@ def ft_action_grad(param, flow, x, want_force=False):
     _lib.check(L.fthmc_grad_unpack(gch.ctypes.data, pf.n_layers, pf.mu.ctypes.data, raw.ctypes.data))
     out = (_back(act, x), torch.from_numpy(raw))
     return out + (_back(frc, x),) if want_force else out
+
+
+# 6th-order central difference: f'(0) = [3/4 (f1 - f-1) - 3/20 (f2 - f-2) + 1/60 (f3 - f-3)] / h + O(h^6)
+_FD6 = ((1, 3.0 / 4.0), (2, -3.0 / 20.0), (3, 1.0 / 60.0))
+
+
+def ft_force_norm_grad(param, flow, xi, step=1e-3):
+    """The second training loss of the reference (ipynb/ft_hmc.py:266-269, used at :367): loss = sum_b |ft_force(xi_b)|^2, and
+    its gradient with respect to the CNN weights, which the reference gets from `ft_force(..., create_graph=True)` +
+    `loss.backward()`.  With F = d S_FT / d xi and xi held fixed,
+
+        d/dw sum_i F_i^2 = 2 sum_i F_i d^2 S_FT / (d xi_i dw) = d/d eps [ dS_FT/dw (xi + eps v) ] at eps = 0,   v = 2 F,
+
+    i.e. the directional derivative, along the field direction v, of the weight gradient that fthmc_ft_action_grad already
+    computes (summed over the batch: the batch direction field (v_b) gives the batch-summed loss gradient in one go).  S_FT
+    is analytic in xi (every ingredient is a smooth 2 pi-periodic function of the links), so the derivative is taken by a
+    6th-order central difference of six gradient launches at xi +- k h v, max|h v| = `step` radians: truncation ~ step^6,
+    rounding ~ 1e-16 / step -- about 1e-12 relative at the default (tests/test_gpu_parity.py holds it to 1e-8 against
+    torch.autograd with create_graph=True on the oracle).
+    Returns (loss 0-d, grad (n_layers, 955) float64 CPU in the reference's parameter order, force (B,2,L0,L1))."""
+    dev = _device(xi)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+        xd = _dev_in(xi, dev, torch.float64)
+        F = _flow_call("force", pf, xd, beta=param.beta)
+        v = 2.0 * F
+        vmax = float(v.abs().max())
+        if not vmax > 0.0:
+            return _back((F * F).sum(), xi), torch.zeros((pf.n_layers, 955), dtype=torch.float64), _back(F, xi)
+        h = step / vmax
+        acc = None
+        for k, c in _FD6:
+            _, gp = ft_action_grad(param, pf, xd + (k * h) * v)
+            _, gm = ft_action_grad(param, pf, xd - (k * h) * v)
+            term = c * (gp - gm)
+            acc = term if acc is None else acc + term
+    return _back((F * F).sum(), xi), acc / h, _back(F, xi)

@@ -1,4 +1,5 @@
-"""Reverse-KL flow training on top of the weight-gradient kernel (ipynb/ft_hmc.py:253-346, fthmc/train.py:162-228).
+"""Flow training on top of the weight-gradient kernel (ipynb/ft_hmc.py:253-346, fthmc/train.py:162-228): the reverse-KL step
+and the force-norm step of the reference's second training stage.
 
 The reference's train_step draws a batch from the uniform prior, flows it, forms loss = mean(logq - logp) and calls
 loss.backward() / optimizer.step().  With logq = log prior - sum logJ and logp = -S the loss is mean_b ft_action(xi_b) +
@@ -25,7 +26,7 @@ class FlowTrainer:
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(int(seed) if seed is not None else torch.seed())
-        self.history = {"loss": [], "dkl": [], "ess": []}
+        self.history = {"loss": [], "force": [], "dkl": [], "ess": []}
         self._pf, self._stale = None, True
 
     # ---- model pieces -------------------------------------------------------------------------------
@@ -47,27 +48,47 @@ class FlowTrainer:
         return -2 * self.lattice[0] * self.lattice[1] * math.log(2 * math.pi)
 
     # ---- one optimizer step -------------------------------------------------------------------------
-    def train_step(self, batch_size, xi=None, group=None):
-        """train_step(model, action, optimizer, metrics, batch_size, param) (ipynb/ft_hmc.py:253) without its force-norm
-        option: loss = dkl = mean(logq - logp) with logq = log prior - sum logJ, logp = -S, i.e. mean ft_action + log prior.
-        Returns the metrics of this step (also appended to self.history)."""
-        class _P:                                   # ft_action_grad reads only beta
+    def train_step(self, batch_size, xi=None, group=None, with_force=False, pre_model=None):
+        """train_step(model, action, optimizer, metrics, batch_size, param, with_force, pre_model) (ipynb/ft_hmc.py:253-295).
+
+        with_force=False: loss = dkl = mean(logq - logp) with logq = log prior - sum logJ, logp = -S, i.e. mean ft_action +
+        log prior.  pre_model (a FlowTrainer or a packed / reference flow): the latent batch is not drawn from the prior but
+        pulled back from the pre-trained flow's samples, xi = F^-1(F_pre(xi_pre)) (:258-262), held fixed for the step.
+        with_force=True (needs pre_model, as in the reference): loss = sum_b |ft_force(xi_b)|^2 (:266-269), its weight
+        gradient from ft_force_norm_grad.  Returns the metrics of this step (also appended to self.history)."""
+        from .api import ft_flow, ft_flow_inv, ft_force_norm_grad
+
+        class _P:                                   # the entry points read only beta
             beta = self.beta
+        if pre_model is not None and xi is None:
+            pre = pre_model.packed() if isinstance(pre_model, FlowTrainer) else pre_model
+            xi = ft_flow_inv(self.packed(), ft_flow(pre, self.sample_prior(batch_size)))
+        if with_force:
+            assert pre_model is not None or xi is not None, "the force-norm step samples through a pre-trained flow (ipynb/ft_hmc.py:267)"
         if xi is None:
             xi = self.sample_prior(batch_size)
-        act, grad = ft_action_grad(_P, self.packed(), xi.to(self.dev))
-        act = act.cpu()
-        sums = torch.stack([act.sum(), torch.tensor(float(act.numel()), dtype=torch.float64)])
+        xi = xi.to(self.dev)
+        if with_force:
+            from .api import ft_action
+            fsize, grad, _ = ft_force_norm_grad(_P, self.packed(), xi)
+            act = ft_action(_P, self.packed(), xi).cpu()
+            fs = fsize.detach().cpu().reshape(1).double()
+        else:
+            act, grad = ft_action_grad(_P, self.packed(), xi)
+            act = act.cpu()
+            fs = torch.zeros(1, dtype=torch.float64)
+        sums = torch.cat([act.sum().reshape(1), torch.tensor([float(act.numel())], dtype=torch.float64), fs])
         grad, sums = shard.allreduce_gradient(grad, sums, group=group)      # all ranks: same gradient, same step
         nb = float(sums[1])
         dkl = float(sums[0]) / nb + self.log_prior()
+        force_size = float(sums[2])
         self.opt.zero_grad()
-        self.raw.grad = (grad / nb).to(torch.float64)
+        self.raw.grad = (grad if with_force else grad / nb).to(torch.float64)      # sum over the batch / mean over the batch
         self.opt.step()
         self._stale = True                           # weights changed: re-upload lazily
         logw = -(act + self.log_prior())             # logp - logq of this rank's batch
         ess = float(torch.exp(2 * torch.logsumexp(logw, 0) - torch.logsumexp(2 * logw, 0)) / act.numel())   # compute_ess
-        m = {"loss": dkl, "dkl": dkl, "ess": ess}
+        m = {"loss": force_size if with_force else dkl, "force": force_size, "dkl": dkl, "ess": ess}
         for k, v in m.items():
-            self.history[k].append(v)
+            self.history.setdefault(k, []).append(v)
         return m

@@ -522,6 +522,70 @@ def test_train_step_follows_autograd_adam():
     assert np.mean(tr.history["dkl"][-5:]) < first and 0 < m["ess"] <= 1.0
 
 
+def _force_norm_autograd(beta, flow, xi):
+    """loss = sum |ft_force(xi)|^2 and d loss / d weights the reference's way: ft_force(..., create_graph=True), backward."""
+    leaves = [t.requires_grad_(True) for lw in flow.layers for pair in zip(lw.w, lw.b) for t in pair]
+    x = xi.clone().requires_grad_(True)
+    f, = torch.autograd.grad(O.ft_action(beta, flow, x).sum(), x, create_graph=True)
+    loss = (f * f).sum()
+    g = torch.autograd.grad(loss, leaves)
+    per = len(leaves) // len(flow.layers)
+    rows = [torch.cat([t.reshape(-1) for t in g[i * per:(i + 1) * per]]) for i in range(len(flow.layers))]
+    for t in leaves:
+        t.requires_grad_(False)
+    return float(loss.detach()), torch.stack(rows)
+
+
+@pytest.mark.parametrize("L,layers,B,scale", [(8, 8, 4, 2.0), (16, 24, 2, 1.0)])
+def test_force_norm_gradient_vs_autograd(L, layers, B, scale):
+    """ft_force_norm_grad (the reference's second-stage loss, ipynb/ft_hmc.py:266-269, 367) against
+    torch.autograd.grad(..., create_graph=True) on the oracle: loss and d loss / d weights to 1e-8."""
+    flow = O.random_flow(n_layers=layers, seed=3647 + L, scale=scale)
+    pf = ft.PackedFlow(_raw_of(flow))
+    gen = torch.Generator().manual_seed(L)
+    xi = torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 * np.pi
+    P = ft.Param(beta=2.0, lat=(L, L))
+    loss_ref, g_ref = _force_norm_autograd(2.0, flow, xi)
+    loss, g, F = ft.ft_force_norm_grad(P, pf, xi)
+    assert abs(float(loss) - loss_ref) < 1e-10 * loss_ref
+    assert relerr(g.numpy(), g_ref.numpy()) < 1e-8
+    for l in range(layers):
+        assert relerr(g[l].numpy(), g_ref[l].numpy()) < 1e-7, l          # (layer by layer: small-gradient layers included)
+    with pytest.raises(NotImplementedError, match="ft_force_norm_grad"):
+        ft.ft_force(P, pf, xi, create_graph=True)
+
+
+def test_train_step_with_force_and_pre_model():
+    """train_step(with_force=True, pre_model=...) (ipynb/ft_hmc.py:253-276): xi = F^-1(F_pre(xi_pre)) held fixed, loss =
+    sum |ft_force(xi)|^2, Adam step -- against the same step done with autograd on the oracle from the same latent batch."""
+    L, layers = 8, 4
+    raw_pre, raw0 = ft.default_init_raw(layers, 21), ft.default_init_raw(layers, 11)
+    pre = ft.FlowTrainer(raw_pre, (L, L), beta=2.0, seed=1)
+    tr = ft.FlowTrainer(raw0, (L, L), beta=2.0, lr=1e-5, seed=5)
+    xi = ft.ft_flow_inv(tr.packed(), ft.ft_flow(pre.packed(), tr.sample_prior(8))).cpu()
+    flow = oracle_flow_from_golden(dict(weights=raw0, activation="silu", convention=0))
+    loss_ref, g_ref = _force_norm_autograd(2.0, flow, xi)
+    params = [t.requires_grad_(True) for lw in flow.layers for pair in zip(lw.w, lw.b) for t in pair]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    opt.zero_grad()
+    pos = 0
+    for lw, row in zip(flow.layers, g_ref):
+        for w, b in zip(lw.w, lw.b):
+            for t in (w, b):
+                t.grad = row[pos:pos + t.numel()].reshape(t.shape).clone(); pos += t.numel()
+        pos = 0
+    opt.step()
+    m = tr.train_step(8, xi=xi, with_force=True)
+    assert abs(m["force"] - loss_ref) < 1e-9 * loss_ref and m["loss"] == m["force"]
+    twin = np.stack([np.concatenate([np.concatenate([w.detach().numpy().ravel(), b.detach().numpy().ravel()])
+                                     for w, b in zip(lw.w, lw.b)]) for lw in flow.layers])
+    assert np.max(np.abs(tr.raw.detach().numpy() - twin)) < 1e-9
+    # the sampling path through a pre-trained flow, both losses
+    m1 = tr.train_step(16, pre_model=pre)
+    m2 = tr.train_step(16, pre_model=pre, with_force=True)
+    assert np.isfinite(m1["dkl"]) and m2["force"] > 0 and len(tr.history["force"]) == 3
+
+
 def test_flow_independence_sampler():
     """apply_flow_to_prior / make_mcmc_ensemble (ipynb/field_transformation.py:37-83) on the forward-flow kernel: logq
     and logp of the proposals against the oracle, and the accept/reject chain against a replay of the reference's loop."""
