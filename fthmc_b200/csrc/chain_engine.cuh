@@ -128,7 +128,7 @@ FT_HD double regularize1(double f) {
 // The scalar constants sit in constant memory on the device (a DFMA takes a constant-bank operand directly).
 //
 // CONTRACT with the kernels: the dynamic shared memory starts with FT_SMEM_PREFIX doubles of scratch -- [0, 64) the
-// executors' reduction slots and transaction barriers, [64, 128) FT_EXP_TABLE (the chain kernels copy it there before
+// executors' reduction slots, [48, 56) atan2x2_fast's theta_1..theta_8, [56, 64) transaction barriers, [64, 128) FT_EXP_TABLE (the chain kernels copy it there before
 // any phase runs, see fthmc_capi.cu); the engine's arena follows.
 constexpr int FT_SMEM_PREFIX = 128;
 constexpr int FT_EXP_TAB_OFF = 64;
@@ -235,6 +235,116 @@ FT_HD double sincos_kernel(double x, int quadrant_shift) {
 FT_HD double sin_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 0) : sin(x); }
 FT_HD double cos_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 1) : cos(x); }
 
+// sin(x) and cos(x) together: one Cody-Waite reduction (as in sincos_kernel), fdlibm's sine and cosine kernels on the
+// remainder, quadrant swap / signs by selects.  Branch-free for |x| < 2^19 (~24 fp64 operations; ~1 ulp), so that the
+// compiler interleaves it with the neighbouring exp / atan chains of a site; the library sincos() beyond.
+// constants: FT_TRIG_CONSTS, then [17..22] the cosine kernel C6..C1
+#define FT_COS_CONSTS { -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, \
+                        2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02 }
+#ifdef __CUDACC__
+__constant__ double c_cosk[6] = FT_COS_CONSTS;
+#endif
+FT_HD void sincos_fast(double x, double& sn, double& cs) {
+    if (!(fabs(x) < 524288.0)) { sn = sin(x); cs = cos(x); return; }
+#ifdef __CUDA_ARCH__
+    const double* K = c_trig; const double* C = c_cosk;
+#else
+    const double K[17] = FT_TRIG_CONSTS; const double C[6] = FT_COS_CONSTS;
+#endif
+    const double t = fma(x, K[0], K[1]);
+    const double n = t - K[1];
+    int q;
+#ifdef __CUDA_ARCH__
+    q = __double2loint(t);
+#else
+    q = (int)(long long)n;
+#endif
+    double r = fma(n, K[2], x);
+    r = fma(n, K[3], r);
+    r = fma(n, K[4], r);
+    const double r2 = r * r;
+    double ps = K[5], pc = C[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) { ps = fma(ps, r2, K[5 + i]); pc = fma(pc, r2, C[i]); }
+    const double s0 = fma(r * r2, ps, r);                                      // sin r
+    const double c0 = fma(r2 * r2, pc, fma(-0.5, r2, 1.0));                    // cos r
+    const bool odd = q & 1;
+    const double sv = odd ? c0 : s0, cv = odd ? s0 : c0;
+    sn = (q & 2) ? -sv : sv;
+    cs = ((q + 1) & 2) ? -cv : cv;
+}
+
+// n / d for a normal d away from over/underflow: hardware reciprocal seed, one cubic Newton step, one residual correction
+// (error < 1 ulp).  7 fp64 operations and no branch, where the compiler's division is a call with a slow path.
+FT_HD double div_fast(double n, double d) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    y = fma(y, fma(e, e, e), y);
+    const double q = n * y;
+    return fma(fma(-d, q, n), y, q);
+#else
+    return n / d;
+#endif
+}
+
+// 2 atan2(y, x) in [-2pi, 2pi] for (x, y) != (0, 0), branch-free (~30 fp64 operations, ~2 ulp): with mx = max(|x|,|y|),
+// mn = min(|x|,|y|), the octant angle atan(mn/mx) = theta_j + atan((mn - mx j/8) / (mx + mn j/8)), theta_j = atan(j/8),
+// j = rint(8 mn/mx) from a single-precision estimate: ONE division, its quotient below 1/15, a six-term odd polynomial.
+// The mixture transform needs exactly this: mod(2 atan(e^s tan(u/2))) = mod(2 atan2(e^s sin(u/2), cos(u/2))) -- no
+// tangent, no pole at u = pi.
+#define FT_ATAN_TAB { 0.0, 0.12435499454676144, 0.24497866312686414, 0.35877067027057225, 0.46364760900080615, \
+                      0.5585993153435624, 0.6435011087932844, 0.7188299996216245, 0.7853981633974483 }
+#define FT_ATAN_COEFS { 1.0 / 13.0, -1.0 / 11.0, 1.0 / 9.0, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0 }
+constexpr int FT_ATAN_TAB_OFF = 47;     // theta_1..theta_8 sit in slots [48, 56) of the shared scratch prefix (see FT_SMEM_PREFIX)
+#ifdef __CUDACC__
+__constant__ double c_atan[6] = FT_ATAN_COEFS;
+__constant__ double c_atan_tab[9] = FT_ATAN_TAB;
+#endif
+FT_HD double atan2x2_fast(double y, double x) {
+#ifdef __CUDA_ARCH__
+    const double* A = c_atan;
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    const double* TAB = fthmc_dyn_smem + FT_ATAN_TAB_OFF;
+#else
+    const double A[6] = FT_ATAN_COEFS;
+    static const double TAB[9] = FT_ATAN_TAB;
+#endif
+    const double ay = fabs(y), ax = fabs(x);
+    const bool steep = ay > ax;
+    const double mx = steep ? ay : ax, mn = steep ? ax : ay;
+    int j;
+#ifdef __CUDA_ARCH__
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(mx)));
+    j = __float2int_rn(8.0f * __double2float_rn(mn) * rf);
+#else
+    j = (int)lrint(8.0 * mn / mx);
+#endif
+    j = j < 0 ? 0 : (j > 8 ? 8 : j);
+    const double jf = 0.125 * (double)j;
+    const double t = div_fast(fma(-mx, jf, mn), fma(mn, jf, mx));
+    const double t2 = t * t;
+    double p = A[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) p = fma(p, t2, A[i]);
+    double a = fma(t * t2, p, t) + (j ? TAB[j] : 0.0);
+    if (steep) a = 1.5707963267948966 - a;
+    if (x < 0.0) a = PI_D - a;
+    a = a + a;
+    return y < 0.0 ? -a : a;
+}
+// torch_mod of a value already within [-2pi, 2pi]
+FT_HD double mod_2pi_near(double g, int conv) {
+    if (conv == 0) {
+        double r = g < 0.0 ? g + TWO_PI_D : g;
+        return r >= TWO_PI_D ? r - TWO_PI_D : r;
+    }
+    double r = g < -PI_D ? g + TWO_PI_D : g;
+    return r >= PI_D ? r - TWO_PI_D : r;
+}
+
 // 1/d for d >= 1 (one cubic Newton step on the hardware seed: three DFMA); host: plain division
 FT_HD double rcp_ge1(double d) {
 #ifdef __CUDA_ARCH__
@@ -306,6 +416,12 @@ struct alignas(16) dbl2 { double x, y; };
 FT_HD dbl2 ld2(const double* p) { return *reinterpret_cast<const dbl2*>(p); }
 FT_HD void st2(double* p, double x, double y) { dbl2 v; v.x = x; v.y = y; *reinterpret_cast<dbl2*>(p) = v; }
 
+// the same map from sh = sin(x/2), ch = cos(x/2) through atan2 (see atan2x2_fast): what the hot paths evaluate
+FT_HD double mixture_fwd_sc(double sh, double ch, double es0, double es1, int conv) {
+    const double g0 = mod_2pi_near(atan2x2_fast(es0 * sh, ch), conv);
+    const double g1 = mod_2pi_near(atan2x2_fast(es1 * sh, ch), conv);
+    return (g0 + g1) / 2;
+}
 // mean_k mod(2 atan(e^{s_k} tan(x/2)))   (ipynb/field_transformation.py:249-257), es_k = e^{s_k}
 FT_HD double mixture_fwd(double x, double es0, double es1, int conv) {
     double th = tan(x / 2);
@@ -613,7 +729,7 @@ struct Engine {
                 if (kind == 0) UA[tt] = p;
                 else {
                     double sp, cp;
-                    sincos(p, &sp, &cp);
+                    sincos_fast(p, sp, cp);
                     const int i = (2 * gi + kind - 1) * g.R + r;
                     CS[i] = cp; CS[V / 2 + i] = sp;
                     if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
@@ -630,7 +746,7 @@ struct Engine {
                 site(g, r, 4 * gi + 1 + k, n0, n1);
                 double p = plaq(oX, n0, n1, order);
                 double sp, cp;
-                sincos(p, &sp, &cp);
+                sincos_fast(p, sp, cp);
                 const int i = (2 * gi + k) * g.R + r;
                 CS[i] = cp; CS[V / 2 + i] = sp;
                 if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
@@ -1100,23 +1216,27 @@ struct Engine {
 #ifdef FT_PROFILE
         ex.prof_add(PF_C3_CONV, ex.clock() - tc0);
 #endif
+        // one site per thread: everything below is branch-free (exp_fast, sincos_fast, atan2x2_fast), so the independent
+        // chains of a site -- two exponentials and the half-angle sine/cosine, then the two arctangents -- interleave
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / R, r = t - gi * R;
             const double out[NOUT] = { OUT[t], OUT[T + t], OUT[2 * T + t] };
-            double u = UA[t];
-            double es0 = exp(out[0]), es1 = exp(out[1]);
-            double fx1 = mixture_fwd(u, es0, es1, conv);
-            double newp = mod_2pi(fx1 + out[2], conv);
-            double delta = newp - u;
+            const double u = UA[t];
+            const double es0 = exp_fast(out[0]), es1 = exp_fast(out[1]);
+            double sh, ch;
+            sincos_fast(0.5 * u, sh, ch);
+            const double fx1 = mixture_fwd_sc(sh, ch, es0, es1, conv);
+            const double newp = mod_2pi(fx1 + out[2], conv);
+            const double delta = newp - u;
             int n0, n1; site(g, r, 4 * gi, n0, n1);
             double* xl = xat(oX, g.mu, n0, n1);
-            double xo = *xl;
+            const double xo = *xl;
             if (sv) { sv[t] = xo; so[t] = out[0]; so[T + t] = out[1]; }
             *xl = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
             if (want_logJ) {
-                double c = cos(u / 2), s = sin(u / 2);
-                double l0 = -log(exp(-out[0]) * (c * c) + es0 * (s * s));
-                double l1 = -log(exp(-out[1]) * (c * c) + es1 * (s * s));
+                const double c2 = ch * ch, s2 = sh * sh;
+                double l0 = -log(exp_fast(-out[0]) * c2 + es0 * s2);
+                double l1 = -log(exp_fast(-out[1]) * c2 + es1 * s2);
                 double m = l0 > l1 ? l0 : l1;
                 lj += (m + log(exp(l0 - m) + exp(l1 - m))) - 0.6931471805599453;
             }
@@ -1159,7 +1279,7 @@ struct Engine {
         const double lo0 = conv == 0 ? 0.0 : -PI_D, hi0 = conv == 0 ? TWO_PI_D : PI_D;
         conv3_all(g);
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            ES0[t] = exp(OUT[t]); ES1[t] = exp(OUT[T + t]);
+            ES0[t] = exp_fast(OUT[t]); ES1[t] = exp_fast(OUT[T + t]);
             Y[t] = mod_2pi(UA[t] - OUT[2 * T + t], conv);
             LO[t] = lo0; HI[t] = hi0;
         }
@@ -1182,14 +1302,16 @@ struct Engine {
             if (!(x > a && x < b)) x = 0.5 * (a + b);
 #pragma unroll 1
             for (int k = 0; k < 12; ++k) {
-                // f as in mixture_fwd (same operations), f' = mean_k e^s_k (1 + th^2) / (1 + e^2s_k th^2) from the same tangent
-                const double th = tan(x / 2), t2 = th * th;
-                const double fx = (mod_2pi(2 * atan(es0 * th), conv) + mod_2pi(2 * atan(es1 * th), conv)) / 2, r = fx - y;
-                const double n0 = fma(es0 * es0, t2, 1.0), n1 = fma(es1 * es1, t2, 1.0);
-                fp = 0.5 * (1.0 + t2) * (es0 * n1 + es1 * n0) / (n0 * n1);
+                // f through the half-angle sine / cosine (mixture_fwd_sc), f' = mean_k e^s_k / (cos^2 + e^2s_k sin^2) from the same pair
+                double sh, ch;
+                sincos_fast(0.5 * x, sh, ch);
+                const double fx = mixture_fwd_sc(sh, ch, es0, es1, conv), r = fx - y;
+                const double c2 = ch * ch, s2 = sh * sh;
+                const double n0 = fma(es0 * es0, s2, c2), n1 = fma(es1 * es1, s2, c2);
+                fp = 0.5 * div_fast(es0 * n1 + es1 * n0, n0 * n1);
                 if (fabs(r) <= 2e-13) { rho = fabs(r); break; }
                 if (r > 0.0) b = x; else a = x;
-                double xn = x - r / fp;
+                double xn = x - div_fast(r, fp);
                 if (!(xn > a && xn < b)) xn = 0.5 * (a + b);
                 x = xn;
             }
@@ -1321,12 +1443,13 @@ struct Engine {
             double u = plaq(oX, n0, n1, order);
             double s0 = OUT[t], s1 = OUT[T + t];
             double c, s;
-            sincos(u / 2, &s, &c);
-            double su = sin(u);
+            sincos_fast(0.5 * u, s, c);
+            const double su = 2.0 * s * c;                                                  // sin u
             double c2 = c * c, s2 = s * s;
             double ep0 = exp_fast(s0), em0 = exp_fast(-s0), ep1 = exp_fast(s1), em1 = exp_fast(-s1);
-            double e0 = 1.0 / (em0 * c2 + ep0 * s2), e1 = 1.0 / (em1 * c2 + ep1 * s2);   // e^{l_k}
-            double sg0 = e0 / (e0 + e1), sg1 = e1 / (e0 + e1);                             // softmax_k l_k
+            double e0 = div_fast(1.0, em0 * c2 + ep0 * s2), e1 = div_fast(1.0, em1 * c2 + ep1 * s2);   // e^{l_k}
+            const double ise = div_fast(1.0, e0 + e1);
+            double sg0 = e0 * ise, sg1 = e1 * ise;                                           // softmax_k l_k
             // w = -1 multiplies the logJ terms (ft_action = S - sum logJ)
             double ub = -db + db * (0.5 * (e0 + e1))
                       + (sg0 * (0.5 * (ep0 - em0)) * su * e0 + sg1 * (0.5 * (ep1 - em1)) * su * e1);

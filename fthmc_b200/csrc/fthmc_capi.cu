@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
         en->gW = nullptr;                                    // (the training mode runs on the single-CTA path)
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) fthmc_dyn_smem[FT_EXP_TAB_OFF + i] = c_exp_tab[i];   // exp_fast's 2^(j/64) table (blocks may be one warp)
+    if (threadIdx.x < 8) fthmc_dyn_smem[FT_ATAN_TAB_OFF + 1 + threadIdx.x] = c_atan_tab[1 + threadIdx.x];   // atan2x2_fast's theta_j
     __syncthreads();
     en->ex.bar_init(Engine<ClusterExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
         en->gW = a.gbuf ? a.gbuf + (size_t)blockIdx.x * a.gbuf_stride : nullptr;
     }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) fthmc_dyn_smem[FT_EXP_TAB_OFF + i] = c_exp_tab[i];   // exp_fast's 2^(j/64) table (blocks may be one warp)
+    if (threadIdx.x < 8) fthmc_dyn_smem[FT_ATAN_TAB_OFF + 1 + threadIdx.x] = c_atan_tab[1 + threadIdx.x];   // atan2x2_fast's theta_j
     __syncthreads();
     en->ex.bar_init(Engine<CtaExec>::NBAR);
     if (a.pr.nlayers > 0) en->load_geom_table();

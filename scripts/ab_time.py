@@ -10,6 +10,11 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import fthmc_b200._lib as L
 L.LIB_PATH = os.path.abspath(sys.argv[1])
+import ctypes
+_h = ctypes.CDLL(L.LIB_PATH)
+for _n in list(L.SIGNATURES):               # older builds lack the newer diagnostic exports
+    if not hasattr(_h, _n):
+        del L.SIGNATURES[_n]
 import fthmc_b200 as ft
 pf = ft.PackedFlow(ft.default_init_raw(24, 3647))
 P = ft.Param(beta=4.0, lat=(32, 32), tau=1.0, nstep=10)
