@@ -336,6 +336,31 @@ def stencil_rooflines(ft, P, hbm_peak, dev):
     return out
 
 
+def lattice_sizes(ft, pf, dev):
+    """Supplementary: the other BASELINE configurations through the same entry point, one warm-up and the best of three timed
+    launches each.  C2: L=16, beta=6, 64 chains (single-CTA path, the whole batch resident at once: a latency figure);
+    C4: L=128, beta=6, the same 24-layer flow re-masked for the larger lattice (flow_resize), one 16-CTA thread-block
+    cluster per chain with DSMEM halos, as many chains as clusters fit twice; L=64 (4-CTA clusters) for the trend."""
+    out = {}
+    # (66 / 14 chains: two waves of the 33 four-CTA / 7 sixteen-CTA clusters a 148-SM B200 co-schedules, profiles/r1_cluster_probe.txt)
+    for name, L, beta, B in (("C2_L16_b6_64chains", 16, 6.0, 64), ("L64_b6", 64, 6.0, 66), ("C4_L128_b6", 128, 6.0, 14)):
+        P = ft.Param(beta=beta, lat=(L, L), tau=1.0, nstep=10)
+        gen = torch.Generator().manual_seed(L)
+        x = torch.empty(B, 2, L, L, dtype=torch.float64).uniform_(-np.pi, np.pi, generator=gen).to(dev)
+        ft.ft_hmc_batch(P, pf, x, seed=3, traj=0)
+        ts = []
+        for k in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = ft.ft_hmc_batch(P, pf, x, seed=3, traj=1 + k)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = min(ts)
+        out[name] = {"lattice": [L, L], "beta": beta, "chains": B, "nstep": 10, "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT,
+                     "msite_traj_per_s": B * L * L / (ms * 1e-3) / 1e6, "mean_dH": float(r["dH"].mean())}
+    return out
+
+
 def run_ours(a):
     import torch.distributed as dist
     import fthmc_b200 as ft
@@ -556,6 +581,8 @@ def run_ours(a):
     e1.record(); torch.cuda.synchronize()
     line["nstep40"] = {"nstep": 40, "value": B / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "acc_rate": float(r40["acc"].double().mean()),
                        "mean_dH": float(r40["dH"].mean()), "mean_exp_mdH": float(r40["exp_mdH"].mean())}
+    if world == 1:
+        line["lattice_sizes"] = lattice_sizes(ft, pf, dev)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     sys.stdout.flush()
