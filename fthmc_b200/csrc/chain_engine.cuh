@@ -715,6 +715,15 @@ struct Engine {
     // =============================================================================================
     // coupling-layer phases (canonical stripe geometry)
     // =============================================================================================
+    // (cluster mode) scratch behind the conv halos AH / ZH (NH * 2 * R doubles) in arena C: the Pbar transpose of ph_scatter
+    FT_HD int oStage() const { return oC + 2 * NH * (L0 > L1 ? L0 : L1); }
+    FT_HD static int log2_or_neg(int v) { if (v <= 0 || (v & (v - 1))) return -1; int sh = 0; while ((1 << sh) < v) ++sh; return sh; }
+    // plaquette of the canonical site (r, c) of this rank
+    FT_HD double plaq_canon(const LayerGeom& g, int r, int c, int order) const {
+        int n0, n1; site(g, r, c, n0, n1);
+        return plaq(oX, n0, n1, order);
+    }
+
     // cos/sin of the frozen plaquettes and the raw active plaquette; cs_save: global copy of CS
     FT_PHASE void ph_planes(const LayerGeom g, double* cs_save) {
         double* CS = sm(oCS); double* UA = sm(oUA);
@@ -723,9 +732,7 @@ struct Engine {
             for (int t = ex.tid(); t < 3 * T; t += ex.nt()) {
                 const int kind = t / T, tt = t - kind * T;
                 const int gi = tt / g.R, r = tt - gi * g.R;
-                int n0, n1;
-                site(g, r, 4 * gi + kind, n0, n1);
-                const double p = plaq(oX, n0, n1, order);
+                const double p = plaq_canon(g, r, 4 * gi + kind, order);
                 if (kind == 0) UA[tt] = p;
                 else {
                     double sp, cp;
@@ -738,13 +745,11 @@ struct Engine {
             return;
         }
         for (int t = ex.tid(); t < T; t += ex.nt()) {
-            int gi = t / g.R, r = t - gi * g.R, n0, n1;
-            site(g, r, 4 * gi, n0, n1);
-            UA[t] = plaq(oX, n0, n1, order);
+            int gi = t / g.R, r = t - gi * g.R;
+            UA[t] = plaq_canon(g, r, 4 * gi, order);
 #pragma unroll 1
             for (int k = 0; k < 2; ++k) {
-                site(g, r, 4 * gi + 1 + k, n0, n1);
-                double p = plaq(oX, n0, n1, order);
+                double p = plaq_canon(g, r, 4 * gi + 1 + k, order);
                 double sp, cp;
                 sincos_fast(p, sp, cp);
                 const int i = (2 * gi + k) * g.R + r;
@@ -1222,15 +1227,15 @@ struct Engine {
             int gi = t / R, r = t - gi * R;
             const double out[NOUT] = { OUT[t], OUT[T + t], OUT[2 * T + t] };
             const double u = UA[t];
+            int n0, n1; site(g, r, 4 * gi, n0, n1);
+            double* xl = xat(oX, g.mu, n0, n1);
+            const double xo = *xl;                            // (cluster mode: possibly a remote load -- in flight under the arithmetic)
             const double es0 = exp_fast(out[0]), es1 = exp_fast(out[1]);
             double sh, ch;
             sincos_fast(0.5 * u, sh, ch);
             const double fx1 = mixture_fwd_sc(sh, ch, es0, es1, conv);
             const double newp = mod_2pi(fx1 + out[2], conv);
             const double delta = newp - u;
-            int n0, n1; site(g, r, 4 * gi, n0, n1);
-            double* xl = xat(oX, g.mu, n0, n1);
-            const double xo = *xl;
             if (sv) { sv[t] = xo; so[t] = out[0]; so[T + t] = out[1]; }
             *xl = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
             if (want_logJ) {
@@ -1799,7 +1804,40 @@ struct Engine {
     }
 
     // GR += plaquette^T(Pbar); threads run along the stripe direction r (conflict-free on PB and on the padded GR)
+    // Cluster mode: Pbar lives in canonical column blocks, GR in lattice row blocks.  Instead of read-modify-writing GR
+    // through distributed shared memory (two dependent round trips per site), every rank sends its V values of Pbar to the
+    // rank that owns the lattice row (remote stores into ST[H + 1][L1] in arena C, row 0 = the row above the block), and
+    // after one cluster barrier each rank updates its own GR from its own shared memory: a quarter of the remote bytes, none
+    // of them on a dependent path.  Same operands, same operations: bit-identical to the direct form.
     FT_PHASE void ph_scatter(const LayerGeom g) {
+        if constexpr (CL) {
+            const double* PB = sm(oW);
+            const int R = g.R, oST = oStage();
+            const int dcol = ex.nt() / R, drow = ex.nt() - dcol * R;
+            int c = ex.tid() / R, r = ex.tid() - c * R;
+            const int shH = log2_or_neg(H);
+            for (int i = ex.tid(); i < V; i += ex.nt(), c += dcol, r += drow) {
+                if (r >= R) { r -= R; ++c; }
+                int n0, n1; site(g, r, c, n0, n1);
+                const int j = shH >= 0 ? (n0 >> shH) : n0 / H, lr = n0 - j * H;
+                const double pb = PB[i];
+                ex.peer(sm(oST), j)[(lr + 1) * L1 + n1] = pb;
+                if (lr == H - 1) ex.peer(sm(oST), j + 1 == nr ? 0 : j + 1)[n1] = pb;
+            }
+            ex.sync();
+            const double* ST = sm(oST);
+            double* GR = sm(oGR);
+            const int e0 = ex.nt() / L1, e1 = ex.nt() - e0 * L1;
+            int lr = ex.tid() / L1, n1 = ex.tid() - lr * L1;
+            for (int i = ex.tid(); i < V; i += ex.nt(), lr += e0, n1 += e1) {
+                if (n1 >= L1) { n1 -= L1; ++lr; }
+                const int n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+                const double pb = ST[(lr + 1) * L1 + n1], pm1 = ST[(lr + 1) * L1 + n1m], pm0 = ST[lr * L1 + n1];
+                GR[lr * LP + n1] += pb - pm1;
+                GR[(H + lr) * LP + n1] += pm0 - pb;
+            }
+            return;
+        }
         const double* PB = sm(oW);
         const int R = g.R, Cn = g.Cn;
         // (column, row) of the sites this thread visits advance without divisions: i += nt  <=>  c += nt / R, r += nt % R

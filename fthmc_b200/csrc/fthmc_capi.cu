@@ -766,6 +766,8 @@ static int chain_ranks(int L0, int L1, bool flow) {
     for (int nr = 1; nr <= 16; ++nr) {
         if ((L0 / 4) % nr || (L1 / 4) % nr) continue;
         if (flow && (size_t)L0 * L1 / nr > (size_t)OFF_W3T) continue;     // Pbar plane aliases the forward weights
+        // cluster mode: the link / Pbar staging areas sit in arena C behind the conv halos (chain_engine.cuh: oStage)
+        if (flow && nr > 1 && 17 * (size_t)(L0 > L1 ? L0 : L1) > 4 * ((size_t)L0 * L1 / nr) + 32) continue;
         if (chain_smem_bytes(L0, L1, flow, nr) + chain_static_smem(nr > 1) > (size_t)d.smem_optin) continue;
         return nr;
     }
