@@ -706,6 +706,31 @@ def test_copyB_physics_golden(golden):
     assert np.max(np.abs(r["field"].numpy() - g["traj_out"])) < 1e-9
 
 
+def test_run_history_mirrors(golden):
+    """run_hmc (fthmc/hmc.py:57-175) and FieldTransformation.run (fthmc/ft_hmc.py:272-346) without their plots and dumps:
+    the history dicts carry the reference's keys, one entry per trajectory, and run_hmc seeded like the reference's loop
+    follows the reference's free-running chain (the run_L8 golden)."""
+    import io, types
+    g = golden("run_L8")
+    n = int(g["ntraj"])
+    P = ft.Param(beta=float(g["plain_beta"]), lat=(8, 8), tau=float(g["plain_tau"]), nstep=int(g["plain_nstep"]), ntraj=n, nrun=1)
+    torch.manual_seed(int(g["seed"]))
+    out = io.StringIO()
+    fields, hist = ft.run_hmc(P, T(g["x0"]), out=out)
+    h = hist[0]
+    assert set(h) == {"traj", "dt", "acc", "dH", "plaq", "q", "dq"} and len(h["dH"]) == n and out.getvalue().count("Traj:") == n
+    assert np.max(np.abs(np.array(h["dH"]) - g["plain_dH"])) < 1e-8
+    assert [bool(a) for a in h["acc"]] == [bool(a) for a in g["plain_acc"]]
+    assert np.max(np.abs(fields[0][0].numpy() - g["plain_final"])) < 1e-8
+    gb = golden("copyB_L8")
+    cfg = types.SimpleNamespace(beta=2.0, volume=64, lat=[8, 8], nd=2)
+    lf = types.SimpleNamespace(dt=0.05, tau=0.2, nstep=4)
+    FT = ft.FieldTransformation(ft.PackedFlow(gb["weights"], activation=str(gb["activation"]), convention=1), cfg, lf)
+    hist = FT.run(T(gb["x"]), num_trajs=5, nprint=2, out=out)
+    assert {"traj", "dt", "acc", "dh", "exp_mdh", "plaq", "q", "dq"} <= set(hist) and all(len(v) == 5 for v in hist.values())
+    assert float(hist["plaq"][-1].abs().max()) <= 1.0
+
+
 def test_statistical_known_answers():
     """The reference's recorded physics: <cos P> = I1(beta)/I0(beta) (PLAQ_EXACT, fthmc/config.py:37-47:
     0.69777 at beta=2) and <Q^2> = 1.23 +- 0.02 at L=8, beta=2 (hmc_2dU1.py:661), from 2048 device-RNG chains of plain HMC
