@@ -731,6 +731,49 @@ def test_run_history_mirrors(golden):
     assert float(hist["plaq"][-1].abs().max()) <= 1.0
 
 
+def test_two_streams_do_not_share_scratch(golden):
+    """The kernels keep per-CTA state (momenta, layer blocks of the adjoint) in the workspace the Python mirror hands them:
+    calls in flight on two CUDA streams must get different workspaces.  Two different batches run concurrently on two
+    streams, repeatedly; each must reproduce its single-stream result bit for bit."""
+    g = golden("ft_L16_b6")
+    pf = packed(g)
+    P = ft.Param(beta=6.0, lat=(16, 16), tau=1.0, nstep=10)
+    gen = torch.Generator().manual_seed(77)
+    xa = ((torch.rand(300, 2, 16, 16, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+    xb = ((torch.rand(300, 2, 16, 16, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi).cuda()
+    ra = ft.ft_hmc_batch(P, pf, xa, seed=5)
+    rb = ft.ft_hmc_batch(P, pf, xb, seed=6)
+    fa, fb = ft.ft_force(P, pf, xa), ft.ft_force(P, pf, xb)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ra2 = ft.ft_hmc_batch(P, pf, xa, seed=5)
+            fa2 = ft.ft_force(P, pf, xa)
+        with torch.cuda.stream(s2):
+            rb2 = ft.ft_hmc_batch(P, pf, xb, seed=6)
+            fb2 = ft.ft_force(P, pf, xb)
+        torch.cuda.synchronize()
+        assert torch.equal(ra2["field"], ra["field"]) and torch.equal(rb2["field"], rb["field"])
+        assert torch.equal(ra2["dH"], ra["dH"]) and torch.equal(rb2["dH"], rb["dH"])
+        assert torch.equal(fa2, fa) and torch.equal(fb2, fb)
+
+
+def test_pack_sees_inplace_weight_edits(golden):
+    """pack(flow) validates its cached device copy with a digest of the weights: an in-place `.data` edit (which does not
+    bump the tensor version; the reference's set_weights uses one) must be seen by the next call."""
+    g = golden("ft_L8_n8")
+    flow = module_like(g)
+    x = T(g["x"])
+    P = ft.Param(beta=float(g["beta"]), lat=(8, 8))
+    a0 = ft.ft_action(P, flow, x)
+    assert relerr(a0.numpy(), g["ft_action"]) < REL
+    assert ft.pack(flow) is ft.pack(flow)
+    flow[0].plaq_coupling.net[0].bias.data.fill_(0.25)
+    a1 = ft.ft_action(P, flow, x)
+    assert float((a1 - a0).abs().max()) > 1e-6
+
+
 def test_statistical_known_answers():
     """The reference's recorded physics: <cos P> = I1(beta)/I0(beta) (PLAQ_EXACT, fthmc/config.py:37-47:
     0.69777 at beta=2) and <Q^2> = 1.23 +- 0.02 at L=8, beta=2 (hmc_2dU1.py:661), from 2048 device-RNG chains of plain HMC
