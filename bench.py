@@ -57,6 +57,12 @@ def workload_name(a):
             f"(seed 3647), tau={a.tau} nstep={a.nstep}, fp64")
 
 
+def common_config(a, world):
+    """`config` of the JSON line: the workload only, identical for both arms (arm-specific notes go under `run`)."""
+    return {"workload": workload_name(a), "chains_total": world * a.chains, "lattice": [a.L, a.L], "beta": a.beta,
+            "n_layers": a.layers, "tau": a.tau, "nstep": a.nstep, "parallelism": f"chains sharded over {world} GPU(s)"}
+
+
 def alg_flop_per_chain_traj(a):
     return a.layers * a.L * a.L * (a.nstep * FLOP_PER_SITE_FORCE + 4 * FLOP_PER_SITE_FWD)
 
@@ -209,7 +215,8 @@ def run_reference(a):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(a), "step": "one chain-trajectory on the host CPU (bounded sample)"},
+            "config": common_config(a, a.gpus),
+            "run": {"step": "one chain-trajectory on the host CPU (a bounded sample of the workload `config` names)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": best, "kind": arm.kind,
                              "sample": f"{a.steps} single-chain ft_hmc trajectories: {arm.what}; {best} pinned threads, the best of "
                                        f"the sweep", "threads_sweep": {str(k): v for k, v in sw.items()},
@@ -556,13 +563,11 @@ def run_ours(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": tot_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "chains_total": world * B, "lattice": [L, L], "beta": a.beta,
-                       "n_layers": a.layers, "tau": a.tau, "nstep": a.nstep, "parallelism": f"chains sharded over {world} GPU(s)",
-                       "momenta": "device Philox4x32-10", "l2": "256 MiB flush between timed steps",
-                       "acceptance_note": "BASELINE's stated tau=1 / nstep=10 from a hot start has dH ~ 11: every timed trajectory "
-                                          "takes the reject branch (see observables.acc_rate); the `nstep40` leg is the same "
-                                          "workload at an nstep that accepts about half",
-                       "observables_allreduce": world > 1},
+            "config": common_config(a, world),
+            "run": {"momenta": "device Philox4x32-10", "l2": "256 MiB flush between timed steps", "observables_allreduce": world > 1,
+                    "acceptance_note": "BASELINE's stated tau=1 / nstep=10 from a hot start has dH ~ 11: every timed trajectory "
+                                       "takes the reject branch (see observables.acc_rate); the `nstep40` leg is the same "
+                                       "workload at an nstep that accepts about half"},
             "roofline": roof,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clk,

@@ -29,9 +29,9 @@ def local_observable_sums(result):
     """(7,) fp64 sums over this rank's chains of a `ft_hmc_batch` / `hmc_batch` result dict, on the
     device the result lives on: [sum plaq, sum Q, sum Q^2, sum acc, sum dH, sum exp(-dH), count]."""
     q = result["topo"].double()
-    n = torch.tensor(float(q.numel()), dtype=torch.float64, device=q.device)
-    return torch.stack([result["plaq"].double().sum(), q.sum(), (q * q).sum(), result["acc"].double().sum(),
-                        result["dH"].double().sum(), result["exp_mdH"].double().sum(), n])
+    rows = torch.stack([result["plaq"].double(), q, q * q, result["acc"].double(), result["dH"].double(),
+                        result["exp_mdH"].double(), torch.ones_like(q)])          # (7, B): one reduction instead of six
+    return rows.sum(dim=1)
 
 
 def allreduce_observables(sums, group=None):
