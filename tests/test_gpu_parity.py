@@ -472,6 +472,49 @@ def test_checkpoint_load_and_lattice_transfer(golden, tmp_path):
     assert float(torch.max(torch.abs(torch.remainder(xi - x + np.pi, 2 * np.pi) - np.pi))) < 5e-5 and abs(float(lj + lji)) < 1e-2
 
 
+def test_load_flow_pickled_modulelist(golden, tmp_path):
+    """The reference's own way of keeping a trained flow, `torch.save(flow, "flow_b{beta}_l{L}x{L}.dat")` (a pickled
+    ModuleList, ipynb/ft_hmc.py:356-373): load_flow unpickles it (its classes importable, as for the reference) and packs it."""
+    import importlib, sys, textwrap
+    (tmp_path / "ref_like_layers.py").write_text(textwrap.dedent("""
+        import torch.nn as nn
+        class PlaqCoupling(nn.Module):
+            def __init__(self, net):
+                super().__init__()
+                self.net, self.inv_prec, self.inv_max_iter = net, 1e-6, 1000
+        class Layer(nn.Module):
+            def __init__(self, net):
+                super().__init__()
+                self.plaq_coupling = PlaqCoupling(net)
+        def make(weights):
+            import torch
+            shapes = [(8, 2, 3, 3), (8,), (8, 8, 3, 3), (8,), (3, 8, 3, 3), (3,)]
+            layers = []
+            for row in weights:
+                convs = [nn.Conv2d(2, 8, 3, padding=1, padding_mode="circular"), nn.Conv2d(8, 8, 3, padding=1, padding_mode="circular"),
+                         nn.Conv2d(8, 3, 3, padding=1, padding_mode="circular")]
+                pos = 0
+                for c in convs:
+                    for prm in (c.weight, c.bias):
+                        n = prm.numel()
+                        prm.data = torch.from_numpy(row[pos:pos + n].reshape(tuple(prm.shape)).copy()); pos += n
+                layers.append(Layer(nn.Sequential(convs[0], nn.SiLU(), convs[1], nn.SiLU(), convs[2])))
+            return nn.ModuleList(layers)
+    """))
+    sys.path.insert(0, str(tmp_path))
+    try:
+        mod = importlib.import_module("ref_like_layers")
+        g = golden("ft_L8_n8")
+        fn = tmp_path / "flow_b2.0_l8x8.dat"
+        torch.save(mod.make(g["weights"]), fn)
+        pf = ft.load_flow(str(fn))
+        assert pf.n_layers == int(g["n_layers"])
+        assert np.max(np.abs(ft.ft_flow(pf, T(g["x"])).numpy() - g["flow_fwd"])) < 1e-12
+    finally:
+        sys.path.remove(str(tmp_path))
+        sys.modules.pop("ref_like_layers", None)
+
+
 # ---------------------------------------------------------------- flow training gradient
 @pytest.mark.parametrize("L,layers,B", [(8, 6, 5), (16, 8, 3), (32, 24, 2)])
 def test_weight_gradient_vs_autograd(L, layers, B):
