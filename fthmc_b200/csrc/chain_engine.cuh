@@ -53,6 +53,11 @@
 #ifndef FT_WINOGRAD
 #define FT_WINOGRAD 1
 #endif
+// act'(z2) of the adjoint sweep single-buffered in plane B, fetched one layer ahead (measured: no slower than the round-1
+// double buffer B / C, profiles/r2_microopt_ab.txt) -- which leaves plane C free for the trajectory state: momenta, x0, y0.
+#ifndef FT_D2_SINGLE
+#define FT_D2_SINGLE 1
+#endif
 
 // loop over the lanes a "thread" carries: exactly one iteration (its own lane) on the device, 32 in the serial emulation
 #define FT_LANES(ln, ls) for (int ls = 0, ln = ex.lane0(); ls < E::kLanes; ++ls, ++ln)
@@ -570,6 +575,11 @@ struct Engine {
         oW = o;   o += PACK_DOUBLES;
         oTab = o; o += 32;                             // per-layer (mu, off) bytes, MAX_LAYERS = 128
         oS = oUA;                                      // Wilson-force scratch plane = UA+OUT (V doubles, contiguous)
+        // Single-CTA trajectories keep the momenta and the two saved fields (x0: start of the MD evolution, y0 = F(x0): the
+        // field returned on reject) ON CHIP, in plane C (6 V + 32 doubles; free now that act'(z2) is single-buffered): between
+        // the load and the store of the field a trajectory touches global memory only for the layer blocks of the adjoint.
+        // (Cluster mode keeps its halos and the Pbar transpose in C, the training mode h2: both stay with the global workspace.)
+        if (!CL && FT_D2_SINGLE && !p.train) { wsP = ex.smem() + oC; wsX0 = wsP + 2 * Vg; wsY0 = wsP + 4 * Vg; }
     }
     // copy the per-layer mask parameters into shared memory once per kernel (global-latency off the layer loop)
     FT_HD void load_geom_table() {
@@ -1862,7 +1872,7 @@ struct Engine {
     // buffered, two layers ahead), act'(z1) -> A, frozen cos/sin -> CS, transposed weights -> W.  The waits sit
     // right before the first use (d1 / cs: after the MAC loops of ph_conv2T / ph_conv1T).
     // cluster mode: act'(z2) is single-buffered in B, one layer ahead; arena C holds the halos
-    FT_HD int zbuf(int l) const { return CL ? oB : ((l & 1) ? oB : oC); }
+    FT_HD int zbuf(int l) const { return (CL || FT_D2_SINGLE) ? oB : ((l & 1) ? oB : oC); }
     FT_HD int zbar(int l) const { return zbuf(l) == oB ? BAR_D2B : BAR_D2C; }
     FT_HD void issue_d2(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(zbar(l), sm(zbuf(l)), wsD2(l), NH * sB); }
     FT_HD void issue_d1(int l) { if (l >= 0 && ex.tid() == 0) ex.bulk_load(BAR_D1, sm(oA), wsD1(l), NH * sA); }
@@ -1922,7 +1932,7 @@ struct Engine {
         FT_T(PF_CONV2T, ph_conv2T(g, zbuf(l));     // waits for d1(l) after its MAC loop
              ex.lsync();
              advance_bar(BAR_D1));
-        FT_T(PF_ISSUE, issue_d2(CL ? l - 1 : l - 2));   // zbuf(l) is free again
+        FT_T(PF_ISSUE, issue_d2((CL || FT_D2_SINGLE) ? l - 1 : l - 2));   // zbuf(l) is free again
         FT_T(PF_CONV1T, ph_conv1T(g);              // waits for cs(l) after its MAC loop
              ex.lsync();
              advance_bar(BAR_CS));
@@ -1977,7 +1987,7 @@ struct Engine {
             issue_cs(last);
         } else {
             FT_T(PF_ISSUE, issue_d2(last);
-                 issue_d2(CL ? -1 : last - 1);
+                 issue_d2((CL || FT_D2_SINGLE) ? -1 : last - 1);
                  issue_weights(last, true);
                  issue_d1(last);
                  issue_cs(last));
