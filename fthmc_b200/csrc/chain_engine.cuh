@@ -541,7 +541,8 @@ struct Engine {
     int Vg, nr, rk, H;              // whole-lattice volume, ranks in the cluster, own rank, lattice rows per rank
     int sA, sB;                     // channel strides of plane A and of planes B, C (padded, see PLANE_PAD)
     int oX, oGR, oCS, oUA, oOUT, oA, oB, oC, oW, oS, oTab;   // arena offsets (doubles)
-    double *wsP, *wsX0, *wsY0, *wsLay;                 // global per-CTA workspace
+    double *wsP, *wsX0, *wsY0;                         // momenta, x0, y0: plane C (single-CTA flow chains) or the global workspace
+    double* wsLay;                                     // layer blocks of the adjoint: global per-CTA workspace
     size_t layStride;
     double* gW;                                        // training: this CTA's gradient accumulators [warp][layer][GRAD_DOUBLES]
     int* iters_out;                                    // optional global: bisection iterations per layer
@@ -1868,8 +1869,8 @@ struct Engine {
 
     // ---- bulk (TMA) prefetch of the layer blocks for the adjoint sweep ----
     // Every block is contiguous in the workspace and lands at the same layout in shared memory, so each is ONE
-    // cp.async.bulk issued by thread 0 and completed on its own transaction barrier: act'(z2) -> B or C (double
-    // buffered, two layers ahead), act'(z1) -> A, frozen cos/sin -> CS, transposed weights -> W.  The waits sit
+    // cp.async.bulk issued by thread 0 and completed on its own transaction barrier: act'(z2) -> B (one layer ahead; with
+    // -DFT_D2_SINGLE=0: B or C alternately, two layers ahead), act'(z1) -> A, frozen cos/sin -> CS, transposed weights -> W.  The waits sit
     // right before the first use (d1 / cs: after the MAC loops of ph_conv2T / ph_conv1T).
     // cluster mode: act'(z2) is single-buffered in B, one layer ahead; arena C holds the halos
     FT_HD int zbuf(int l) const { return (CL || FT_D2_SINGLE) ? oB : ((l & 1) ? oB : oC); }
@@ -2138,7 +2139,8 @@ struct Engine {
 };
 
 // ------------------------------------------------------------------------------------------------
-// trajectory programs (one chain).  Momenta live in the per-CTA global workspace (L2 resident).
+// trajectory programs (one chain).  en.wsP / wsX0 / wsY0 (momenta, x0, y0) point into shared memory (plane C) for single-CTA
+// flow chains and into the per-CTA global workspace otherwise (see the Engine constructor).
 // ------------------------------------------------------------------------------------------------
 struct TrajIO {
     const double* field_in;    // (2,L0,L1)
