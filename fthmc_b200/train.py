@@ -92,3 +92,54 @@ class FlowTrainer:
         for k, v in m.items():
             self.history.setdefault(k, []).append(v)
         return m
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's training / evaluation drivers around train_step
+# ------------------------------------------------------------------------------------------------
+def flow_train(lattice, beta, n_layers=24, n_era=10, n_epoch=30, batch_size=64, base_lr=1e-4, with_force=False, pre_model=None,
+               raw_weights=None, seed=None, out=None):
+    """flow_train(param, with_force, pre_model) (ipynb/ft_hmc.py:297-346): a 24-layer flow from PyTorch's default Conv2d init
+    (the reference's set_weights is a no-op on a ModuleList), Adam at base_lr for the reverse-KL step and, with
+    `with_force`, a second Adam at base_lr / 100 for a force-norm step after every reverse-KL step, n_era x n_epoch steps of
+    each.  Returns the FlowTrainer (its `.packed()` flow drives every entry point; `.history` has loss / force / dkl / ess)."""
+    from .flow import default_init_raw
+    raw = default_init_raw(n_layers, 3647 if seed is None else seed) if raw_weights is None else raw_weights
+    tr = FlowTrainer(raw, lattice, beta, lr=base_lr, seed=seed)
+    opt_kl, opt_wf = tr.opt, torch.optim.Adam([tr.raw], lr=base_lr / 100.0)
+    for era in range(n_era):
+        for epoch in range(n_epoch):
+            tr.opt = opt_kl
+            tr.train_step(batch_size)
+            if with_force:
+                assert pre_model is not None, "the force-norm stage samples through a pre-trained flow (ipynb/ft_hmc.py:267)"
+                tr.opt = opt_wf
+                tr.train_step(batch_size, with_force=True, pre_model=pre_model)
+        if out is not None:
+            n = n_epoch * (2 if with_force else 1)
+            out.write(f"== Era {era} ==  " + "  ".join(f"{k} {np.mean(v[-n:]):g}" for k, v in tr.history.items()) + "\n")
+    tr.opt = opt_kl
+    return tr
+
+
+def blocked_bootstrap(x, n_boot=100, binsize=16, rng=None):
+    """(mean, error) of the mean of x by resampling whole bins of `binsize` consecutive samples with replacement (what the
+    reference's bootstrap(x, Nboot=, binsize=) estimates, ipynb/field_transformation.py:28-33)."""
+    x = np.asarray(x, dtype=np.float64)
+    nb = x.shape[0] // binsize
+    bins = x[:nb * binsize].reshape(nb, binsize).mean(axis=1)
+    rng = np.random.default_rng() if rng is None else rng
+    means = bins[rng.integers(nb, size=(n_boot, nb))].mean(axis=1)
+    return float(means.mean()), float(means.std())
+
+
+def flow_eval(flow, beta, lattice, ensemble_size=1024, batch_size=64, generator=None, rng=None):
+    """flow_eval(model, action) (ipynb/ft_hmc.py:348-354): an independence-Metropolis ensemble from the flow, its accept rate
+    and the topological susceptibility <Q^2> with a blocked bootstrap error."""
+    from . import sampler
+    from .api import topo_charge
+    flow = flow.packed() if isinstance(flow, FlowTrainer) else flow
+    ens = sampler.make_mcmc_ensemble(flow, beta, tuple(lattice), batch_size, ensemble_size, generator=generator)
+    q = topo_charge(torch.stack(ens["x"], dim=0)).cpu().numpy()
+    chi, err = blocked_bootstrap(q ** 2, n_boot=100, binsize=16, rng=rng)
+    return {"accept_rate": float(np.mean(ens["accepted"])), "Q2": chi, "Q2_err": err, "ensemble": ens}

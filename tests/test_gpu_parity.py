@@ -629,6 +629,22 @@ def test_train_step_with_force_and_pre_model():
     assert np.isfinite(m1["dkl"]) and m2["force"] > 0 and len(tr.history["force"]) == 3
 
 
+def test_flow_train_and_eval_drivers():
+    """flow_train / flow_eval (ipynb/ft_hmc.py:297-354) on the CUDA entry points: a short two-stage training run at L=8
+    (reverse-KL, then reverse-KL + force-norm steps through the first stage's flow) lowers the loss, and the
+    independence-Metropolis evaluation of the trained flow returns an accept rate and <Q^2> with an error."""
+    import io
+    out = io.StringIO()
+    pre = ft.flow_train((8, 8), 2.0, n_layers=4, n_era=2, n_epoch=20, batch_size=64, base_lr=1e-3, seed=11, out=out)
+    assert np.mean(pre.history["dkl"][-5:]) < np.mean(pre.history["dkl"][:5]) and out.getvalue().count("== Era") == 2
+    tr = ft.flow_train((8, 8), 2.0, n_layers=4, n_era=1, n_epoch=3, batch_size=16, base_lr=1e-3, with_force=True, pre_model=pre,
+                       raw_weights=pre.raw.detach().numpy(), seed=12)
+    assert len(tr.history["loss"]) == 6 and sum(f > 0 for f in tr.history["force"]) == 3
+    torch.manual_seed(3)
+    ev = ft.flow_eval(pre, 2.0, (8, 8), ensemble_size=128, batch_size=32, rng=np.random.default_rng(1))
+    assert 0 < ev["accept_rate"] <= 1 and ev["Q2"] >= 0 and ev["Q2_err"] >= 0 and len(ev["ensemble"]["x"]) == 128
+
+
 def test_flow_independence_sampler():
     """apply_flow_to_prior / make_mcmc_ensemble (ipynb/field_transformation.py:37-83) on the forward-flow kernel: logq
     and logp of the proposals against the oracle, and the accept/reject chain against a replay of the reference's loop."""
