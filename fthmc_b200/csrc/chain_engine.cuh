@@ -53,6 +53,12 @@
 #ifndef FT_WINOGRAD
 #define FT_WINOGRAD 1
 #endif
+#ifndef FT_CONV1T_PAIR
+#define FT_CONV1T_PAIR 1
+#endif
+#ifndef FT_CONV3T_PAIR
+#define FT_CONV3T_PAIR 1
+#endif
 // act'(z2) of the adjoint sweep single-buffered in plane B, fetched one layer ahead (measured: no slower than the round-1
 // double buffer B / C, profiles/r2_microopt_ab.txt) -- which leaves plane C free for the trajectory state: momenta, x0, y0.
 #ifndef FT_D2_SINGLE
@@ -1478,7 +1484,53 @@ struct Engine {
 
     // zbar2 = conv3^T(OUT) * act'(z2)  (in place in C, which holds act'(z2))
     FT_HD void ph_conv3T(const LayerGeom g, int oZ) {
+#if FT_CONV3T_PAIR
+        if (!fine_tasks() && (g.R & 1) == 0) { ph_conv3T_pair(g, oZ); return; }
+#endif
         if (fine_tasks()) ph_conv3T_t<4>(g, oZ); else ph_conv3T_t<8>(g, oZ);
+    }
+    // two rows (r, r+1), r even, per thread: the 108 warp-uniform weight vectors of a task -- the bulk of the phase's
+    // shared-memory wavefronts -- are loaded once for both rows (see ph_conv1T_pair)
+    FT_PHASE void ph_conv3T_pair(const LayerGeom g, int oZ) {
+        const double* OUT = sm(oOUT); const double* W = sm(oW);
+        double* C = sm(oZ);
+        const int T = g.G * g.R, R = g.R, hR = R >> 1;
+        for (int t2 = ex.tid(); t2 < (T >> 1); t2 += ex.nt()) {
+            const int gi = t2 / hR, r = 2 * (t2 - gi * hR);
+            const int rm = r == 0 ? R - 1 : r - 1, rp = r + 2 == R ? 0 : r + 2;
+            double ob[NOUT][4];                              // out-gradient rows r-1 .. r+2; output row r + d reads row r + d - a + 1 = ob[.][d - a + 2]
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+                const double* p = OUT + o * T + gi * R;
+                const dbl2 m = ld2(p + r);
+                ob[o][0] = p[rm]; ob[o][1] = m.x; ob[o][2] = m.y; ob[o][3] = p[rp];
+            }
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                double acc[2][NH];
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci) { acc[0][ci] = 0.0; acc[1][ci] = 0.0; }
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        double w[NH];
+#pragma unroll
+                        for (int ci = 0; ci < NH; ci += 2) { const dbl2 wv = ld2(W + OFF_W3T + ((o * 3 + a) * 3 + k) * NH + ci); w[ci] = wv.x; w[ci + 1] = wv.y; }
+#pragma unroll
+                        for (int ci = 0; ci < NH; ++ci) {
+                            acc[0][ci] = fma(w[ci], ob[o][2 - a], acc[0][ci]);
+                            acc[1][ci] = fma(w[ci], ob[o][3 - a], acc[1][ci]);
+                        }
+                    }
+#pragma unroll
+                for (int ci = 0; ci < NH; ++ci) {
+                    double* p = C + ci * sB + (3 * gi + k) * R + r;
+                    const dbl2 d = ld2(p);                   // act'(z2) of the two rows
+                    st2(p, acc[0][ci] * d.x, acc[1][ci] * d.y);
+                }
+            }
+        }
     }
     template <int CH> FT_PHASE void ph_conv3T_t(const LayerGeom g, int oZ) {
         const double* OUT = sm(oOUT); const double* W = sm(oW);
@@ -1765,7 +1817,64 @@ struct Engine {
     // (cos,sin)-gradients at the frozen sites = conv1^T(zbar1); assemble Pbar in the canonical layout
     // PB[c][r] (the unused forward-weight slots of W: V <= OFF_W3T doubles)
     FT_HD void ph_conv1T(const LayerGeom g) {
+#if FT_CONV1T_PAIR
+        if (!fine_tasks() && (g.R & 1) == 0) { ph_conv1T_pair(g); return; }
+#endif
         if (fine_tasks()) ph_conv1T_t<1>(g); else ph_conv1T_t<2>(g);
+    }
+    // The same for the two rows (r, r+1), r even, of a stripe group per thread: every weight vector is loaded once for both
+    // rows and the four input rows r-1 .. r+2 of a column are shared (as in conv3_pair) -- the phase is bound by shared-memory
+    // wavefronts, and this form needs 41 of them per (channel, 2 rows) where the row-per-thread form needs 2 x 33.
+    FT_PHASE void ph_conv1T_pair(const LayerGeom g) {
+        const double* A = sm(oA); const double* W = sm(oW); const double* CS = sm(oCS); const double* UA = sm(oUA);
+        double* PB = sm(oW);
+        const int T = g.G * g.R, R = g.R, hR = R >> 1;
+        for (int t2 = ex.tid(); t2 < (T >> 1); t2 += ex.nt()) {
+            const int gi = t2 / hR, r = 2 * (t2 - gi * hR);
+            const int rm = r == 0 ? R - 1 : r - 1, rp = r + 2 == R ? 0 : r + 2;
+            // output row r + d reads source row r + d - a + 1: with v[j] = row r - 1 + j, that is v[d - a + 2]
+            double gc[2][3][2], gs[2][3][2];                                      // [row d][kernel row a][frozen column k]
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) { gc[d][a][k] = 0.0; gs[d][a][k] = 0.0; }
+#pragma unroll 2
+            for (int o = 0; o < NH; ++o) {
+                double v[4][4];                                                   // [row r-1 .. r+2][column 4g .. 4g+3]
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double* col = A + o * sA + (4 * gi + q) * R;
+                    const dbl2 m = ld2(col + r);
+                    v[0][q] = col[rm]; v[1][q] = m.x; v[2][q] = m.y; v[3][q] = col[rp];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const dbl2 w = ld2(W + OFF_W1T + ((o * 3 + a) * 3 + b) * 2);
+#pragma unroll
+                        for (int d = 0; d < 2; ++d)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {                         // frozen column 4g+1+k reads column 4g+1+k-b+1
+                                gc[d][a][k] = fma(w.x, v[d - a + 2][k + 2 - b], gc[d][a][k]);
+                                gs[d][a][k] = fma(w.y, v[d - a + 2][k + 2 - b], gs[d][a][k]);
+                            }
+                    }
+            }
+            const dbl2 ua = ld2(UA + gi * R + r);
+            st2(PB + (4 * gi) * R + r, ua.x, ua.y);
+            st2(PB + (4 * gi + 3) * R + r, 0.0, 0.0);
+            wait_bar(BAR_CS);                     // the frozen cos/sin have landed in CS
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const dbl2 cp = ld2(CS + (2 * gi + k) * R + r), sp = ld2(CS + V / 2 + (2 * gi + k) * R + r);
+                const double c0 = (gc[0][0][k] + gc[0][1][k]) + gc[0][2][k], s0 = (gs[0][0][k] + gs[0][1][k]) + gs[0][2][k];
+                const double c1 = (gc[1][0][k] + gc[1][1][k]) + gc[1][2][k], s1 = (gs[1][0][k] + gs[1][1][k]) + gs[1][2][k];
+                st2(PB + (4 * gi + 1 + k) * R + r, -sp.x * c0 + cp.x * s0, -sp.y * c1 + cp.y * s1);
+            }
+        }
     }
     // KN = frozen columns per task: 2 (one task per (group, row)) or 1 (two tasks, wide blocks)
     template <int KN> FT_PHASE void ph_conv1T_t(const LayerGeom g) {
