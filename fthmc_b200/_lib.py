@@ -44,6 +44,7 @@ SIGNATURES = {
                                  c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp]),
     "fthmc_grad_workspace_bytes": (c_sz, [c_dp, c_int, c_int, c_int]),
     "fthmc_ft_action_grad": (c_int, [c_dp, c_dp, c_dbl, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_sz, c_dp]),
+    "fthmc_flow_vjp": (c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_sz, c_dp]),
     "fthmc_grad_doubles": (c_int, []),
     "fthmc_grad_unpack": (c_int, [c_dp, c_int, c_dp, c_dp]),
 }

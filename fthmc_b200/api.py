@@ -661,3 +661,96 @@ def ft_force_norm_grad(param, flow, xi, step=1e-3):
             term = c * (gp - gm)
             acc = term if acc is None else acc + term
     return _back((F * F).sum(), xi), acc / h, _back(F, xi)
+
+
+# ------------------------------------------------------------------------------------------------
+# the flow as a differentiable torch operation
+# ------------------------------------------------------------------------------------------------
+def flow_vjp(flow, x, gy, glj, want_grad_x=True):
+    """Vector-Jacobian product of the flow map (x, weights) -> (y = F(x), logJ): (grad_weights (n_layers, 955) float64 CPU in
+    the reference's parameter order, grad_x (B,2,L0,L1) or None) of  sum_b [<gy_b, y_b> + glj_b logJ_b]  in ONE launch."""
+    import numpy as np
+    dev = _device(x)
+    with torch.cuda.device(dev):
+        pf = pack(flow, device=dev)
+        xd = _dev_in(x, dev, torch.float64)
+        gyd = _dev_in(gy, dev, torch.float64)
+        gld = _dev_in(glj.reshape(-1), dev, torch.float64)
+        if xd.dim() != 4 or gyd.shape != xd.shape or gld.numel() != xd.shape[0]:
+            raise _lib.FthmcError(-1, "x, gy must be (B,2,L0,L1) and glj (B,)")
+        B, _, L0, L1 = xd.shape
+        L = _lib.lib()
+        ws = _workspace(pf.handle, B, L0, L1, dev, need=L.fthmc_grad_workspace_bytes(pf.handle, B, L0, L1), kind="grad")
+        gc = torch.empty((pf.n_layers, L.fthmc_grad_doubles()), dtype=torch.float64, device=dev)
+        gx = torch.empty_like(xd) if want_grad_x else None
+        _lib.check(L.fthmc_flow_vjp(pf.handle, xd.data_ptr(), gyd.data_ptr(), gld.data_ptr(), gc.data_ptr(), _ptr(gx),
+                                    B, L0, L1, ws.data_ptr(), ws.numel(), _stream()))
+        gch = np.ascontiguousarray(gc.cpu().numpy())
+    raw = np.zeros((pf.n_layers, 955), dtype=np.float64)
+    _lib.check(L.fthmc_grad_unpack(gch.ctypes.data, pf.n_layers, pf.mu.ctypes.data, raw.ctypes.data))
+    return torch.from_numpy(raw), gx
+
+
+class _FlowFunction(torch.autograd.Function):
+    """(raw weights (n_layers, 955), xi (B,2,L0,L1)) -> (F(xi), sum_layers logJ): forward = fthmc_flow_fwd, backward = fthmc_flow_vjp."""
+
+    @staticmethod
+    def forward(ctx, raw, xi, activation, convention):
+        pf = PackedFlow(raw.detach().double().cpu().numpy(), activation=activation, convention=convention, device=_device(xi))
+        y, lj = _flow_call("fwd", pf, xi.detach(), want_logJ=True)
+        ctx.pf, ctx.raw_meta = pf, (raw.device, raw.dtype)
+        ctx.save_for_backward(xi.detach())
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, gy, glj):
+        (xi,) = ctx.saved_tensors
+        gy = torch.zeros_like(xi) if gy is None else gy
+        glj = torch.zeros(xi.shape[0], dtype=xi.dtype, device=xi.device) if glj is None else glj
+        graw, gx = flow_vjp(ctx.pf, xi, gy.contiguous(), glj.contiguous(), want_grad_x=ctx.needs_input_grad[1])
+        dev, dt = ctx.raw_meta
+        return (graw.to(device=dev, dtype=dt) if ctx.needs_input_grad[0] else None), (None if gx is None else _back(gx, xi)), None, None
+
+
+def differentiable_flow(flow, xi, activation="silu", convention=0):
+    """x, logJ = differentiable_flow(flow, xi): the forward flow as ONE differentiable torch operation, so that the reference's
+    training code -- `apply_flow_to_prior` + any loss + `loss.backward()` (ipynb/ft_hmc.py:253-295,
+    ipynb/field_transformation.py:107-115) -- runs on the kernels unchanged: forward is one launch of fthmc_flow_fwd, backward
+    one launch of fthmc_flow_vjp.  `flow`: a reference-style ModuleList (gradients reach its Conv2d parameters) or a
+    (n_layers, 955) tensor of raw weights in the reference's parameter order.  First-order only (no double backward)."""
+    if isinstance(flow, torch.Tensor):
+        raw = flow
+    else:
+        rows = []
+        for layer in flow:
+            convs = [m for m in layer.plaq_coupling.net if hasattr(m, "weight")]
+            rows.append(torch.cat([t.reshape(-1) for c in convs for t in (c.weight, c.bias)]))
+        raw = torch.stack(rows)
+        from .flow import _activation_of
+        activation = _activation_of(flow[0].plaq_coupling.net)
+    return _FlowFunction.apply(raw, xi, activation, convention)
+
+
+class _ActionFunction(torch.autograd.Function):
+    """U1GaugeAction(beta)(cfgs) with its gradient from the force stencil."""
+
+    @staticmethod
+    def forward(ctx, cfgs, beta):
+        ctx.beta = float(beta)
+        ctx.save_for_backward(cfgs.detach())
+        return _reduce_call("action", cfgs.detach(), 0, beta)
+
+    @staticmethod
+    def backward(ctx, gs):
+        (cfgs,) = ctx.saved_tensors
+
+        class _P:
+            beta = ctx.beta
+        f = force(_P, cfgs, order=0)
+        return f * gs.to(f.device).reshape(-1, 1, 1, 1), None
+
+
+def differentiable_u1_action(beta, cfgs):
+    """U1GaugeAction(beta)(cfgs) (ipynb/field_transformation.py:120-137) as a differentiable torch operation: forward the action
+    stencil, backward the force stencil scaled by the upstream gradient."""
+    return _ActionFunction.apply(cfgs, beta)

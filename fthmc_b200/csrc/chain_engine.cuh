@@ -556,6 +556,10 @@ struct Engine {
     // waited with parity k & 1.  Thread 0 advances a counter only after a block barrier that follows every thread's wait.
     enum { BAR_W = 0, BAR_D2B, BAR_D2C, BAR_D1, BAR_CS, BAR_SO, BAR_H1, NBAR };
     int barcnt[NBAR];
+    // vector-Jacobian mode of the adjoint sweep (fthmc_flow_vjp): an external gradient d/dy of this chain seeds the sweep
+    // instead of the Wilson force, and the log-Jacobian terms are weighted by -mw (ft_action = S - sum logJ: mw = 1)
+    const double* vjp_seed;
+    double mw;
 
     FT_HD Engine(const E& e, const EngineParams& p, double* ws) : ex(e), pr(p) {
         L0 = p.L0; L1 = p.L1; LP = L1 + 1; Vg = L0 * L1;
@@ -570,6 +574,7 @@ struct Engine {
         wsP = ws; wsX0 = ws + 2 * Vg; wsY0 = ws + 4 * Vg;
         wsLay = ws + 6 * (size_t)Vg + (size_t)rk * p.nlayers * layStride;
         iters_out = nullptr;
+        vjp_seed = nullptr; mw = 1.0;
         oCS = oUA = oOUT = oA = oB = oC = oW = oTab = 0;
         if (p.nlayers == 0) { oS = o; return; }        // plain HMC: only a scratch plane
         oCS = o;  o += V;
@@ -1454,6 +1459,7 @@ struct Engine {
     FT_PHASE void ph_outgrad(const LayerGeom g) {
         double* OUT = sm(oOUT); double* UA = sm(oUA);
         const int T = g.G * g.R, R = g.R, order = pr.conv;
+        const double mwl = mw;
         wait_bar(BAR_SO);
         // the active plaquette only involves its own active link, so restore + plaquette fuse per task
         for (int t = ex.tid(); t < T; t += ex.nt()) {
@@ -1472,11 +1478,11 @@ struct Engine {
             double e0 = div_fast(1.0, em0 * c2 + ep0 * s2), e1 = div_fast(1.0, em1 * c2 + ep1 * s2);   // e^{l_k}
             const double ise = div_fast(1.0, e0 + e1);
             double sg0 = e0 * ise, sg1 = e1 * ise;                                           // softmax_k l_k
-            // w = -1 multiplies the logJ terms (ft_action = S - sum logJ)
+            // the logJ terms carry the weight w = -mw (ft_action = S - sum logJ: w = -1, mw = 1; a product with 1.0 is exact)
             double ub = -db + db * (0.5 * (e0 + e1))
-                      + (sg0 * (0.5 * (ep0 - em0)) * su * e0 + sg1 * (0.5 * (ep1 - em1)) * su * e1);
-            double sb0 = db * su * e0 * 0.5 - sg0 * (em0 * c2 - ep0 * s2) * e0;
-            double sb1 = db * su * e1 * 0.5 - sg1 * (em1 * c2 - ep1 * s2) * e1;
+                      + mwl * (sg0 * (0.5 * (ep0 - em0)) * su * e0 + sg1 * (0.5 * (ep1 - em1)) * su * e1);
+            double sb0 = db * su * e0 * 0.5 - mwl * (sg0 * (em0 * c2 - ep0 * s2) * e0);
+            double sb1 = db * su * e1 * 0.5 - mwl * (sg1 * (em1 * c2 - ep1 * s2) * e1);
             OUT[t] = sb0; OUT[T + t] = sb1; OUT[2 * T + t] = db;
             UA[t] = ub;
         }
@@ -2102,6 +2108,12 @@ struct Engine {
                  issue_d1(last);
                  issue_cs(last));
         }
+        if (TRAIN && vjp_seed != nullptr) {                // vector-Jacobian mode: the caller's d/dy seeds the sweep
+            double* GRs = sm(oGR);
+            const double* sd = vjp_seed;
+            for_links([&](int si, int gi) { GRs[si] = sd[gi]; });
+            ex.sync();
+        } else
         FT_T(PF_WFORCE, wilson_force(beta, pr.conv));      // scratch plane = UA+OUT
         FT_T(PF_ISSUE, issue_so(last));
         for (int l = last; l >= 0; --l) layer_adjoint<TRAIN>(l);

@@ -35,6 +35,8 @@ struct ChainArgs {
     int* iters;               // (B,nlayers) or null (bisection iteration counts)
     double* expmdH; int* acc; double* plaq; double* topo; double* h0; double* h1;   // (B) each, trajectory modes
     uint64_t seed, traj, chain0;
+    const double* vjp_seed;   // MODE_FT_GRAD, optional (B,2,L0,L1): external d/dy seeding the adjoint sweep instead of the Wilson force
+    const double* vjp_wlj;    // MODE_FT_GRAD, optional (B): weight of sum logJ per chain (-1 for ft_action)
     double* gbuf;             // MODE_FT_GRAD: gradient accumulators, one slice of gbuf_stride doubles per CTA
     size_t gbuf_stride;
     double* ws;               // per-CTA workspace base
@@ -81,6 +83,10 @@ FT_HD void run_chain(Engine<E>& en, const ChainArgs& a, int b) {
         ex.sync();
     } break;
     case MODE_FT_GRAD: {
+        if (ex.tid() == 0) {
+            en.vjp_seed = a.vjp_seed ? a.vjp_seed + (size_t)b * fs : nullptr;
+            en.mw = a.vjp_wlj ? -a.vjp_wlj[b] : 1.0;
+        }
         en.load_field(en.oX, fin); ex.sync();
         double s = en.template ft_force<true>(a.beta, true); // weight gradients accumulate into en.gW along the adjoint sweep
         if (a.s_out && ex.tid() == 0) a.s_out[b] = s;

@@ -263,9 +263,17 @@ struct ClusterExec : CtaExec {
 #endif
 };
 
+// The engine object sits in STATIC shared memory, padded to a multiple of 128 bytes.  The padding is load-bearing: the
+// dynamic shared memory (fthmc_dyn_smem) starts behind the static part, rounded up to the alignment of the extern array --
+// and this translation unit declares extern __shared__ arrays with 16-byte (the chain kernels, the engine's helpers) and
+// 128-byte alignment (the TMA stencil).  With a static size that is not a multiple of 128 the kernel body and its noinline
+// device functions resolved the dynamic base differently (observed: 112 bytes apart at sizeof(Engine) = 272: the exp / atan
+// tables written by the kernel prologue were read 14 slots off by the phases).  A multiple of 128 makes every view agree.
+#define ENGINE_BUF_BYTES(EXEC) ((sizeof(Engine<EXEC>) + 127) / 128 * 128)
+
 __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
-    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<ClusterExec>)];
+    __shared__ __align__(128) unsigned char en_buf[ENGINE_BUF_BYTES(ClusterExec)];
     Engine<ClusterExec>* en = reinterpret_cast<Engine<ClusterExec>*>(en_buf);
     auto cl = cooperative_groups::this_cluster();
     const int nr = (int)cl.num_blocks(), cid = blockIdx.x / nr, ncl = gridDim.x / nr;
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs
 // plain HMC / leapfrog only: no flow phases in the kernel, a quarter of the registers, four CTAs per SM
 __global__ void __launch_bounds__(256, 4) k_chain_plain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
-    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<CtaExec>)];
+    __shared__ __align__(128) unsigned char en_buf[ENGINE_BUF_BYTES(CtaExec)];
     Engine<CtaExec>* en = reinterpret_cast<Engine<CtaExec>*>(en_buf);
     if (threadIdx.x == 0) {
         CtaExec ex{ fthmc_dyn_smem };
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(256, 4) k_chain_plain(const ChainArgs a) {
 __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
     // the engine object lives in (static) shared memory: its members are read by every noinline phase
-    __shared__ __align__(16) unsigned char en_buf[sizeof(Engine<CtaExec>)];
+    __shared__ __align__(128) unsigned char en_buf[ENGINE_BUF_BYTES(CtaExec)];
     Engine<CtaExec>* en = reinterpret_cast<Engine<CtaExec>*>(en_buf);
     if (threadIdx.x == 0) {
         CtaExec ex{ fthmc_dyn_smem };
@@ -1223,6 +1231,23 @@ extern "C" int fthmc_ft_action_grad(fthmc_flow_t flow, const double* x, double b
                                     int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
     if (!flow || !x || !grad_canon) return fail(FTHMC_E_ARG, "null pointer");
     ChainArgs a{}; a.mode = MODE_FT_GRAD; a.B = B; a.field_in = x; a.field_out = force_out; a.s_out = action_out; a.beta = beta;
+    int rc = launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
+    if (rc) return rc;
+    const int n = flow->n_layers * GRAD_DOUBLES;
+    const int chains = (int)(((char*)a.gbuf - (char*)a.ws) / (a.ws_stride * sizeof(double)));
+    const int nslices = chains * (int)(a.gbuf_stride / ((size_t)flow->n_layers * GRAD_DOUBLES));
+    k_grad_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.gbuf, nslices, n, grad_canon);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// vector-Jacobian product of the flow (x, weights) -> (y, logJ):  d/dx and d/dweights of  sum_b [ <gy_b, y_b> + glj_b logJ_b ]
+extern "C" int fthmc_flow_vjp(fthmc_flow_t flow, const double* x, const double* gy, const double* glj, double* grad_canon, double* grad_x,
+                              int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream) {
+    if (!flow || !x || !gy || !glj || !grad_canon) return fail(FTHMC_E_ARG, "null pointer");
+    ChainArgs a{}; a.mode = MODE_FT_GRAD; a.B = B; a.field_in = x; a.field_out = grad_x; a.s_out = nullptr; a.beta = 0.0;
+    a.vjp_seed = gy; a.vjp_wlj = glj;
     int rc = launch_chain(a, flow, L0, L1, ws, ws_bytes, stream);
     if (rc) return rc;
     const int n = flow->n_layers * GRAD_DOUBLES;

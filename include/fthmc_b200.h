@@ -138,6 +138,13 @@ int fthmc_ft_hmc_run(fthmc_flow_t flow, const double* field_in, double* field_ou
 size_t fthmc_grad_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1);
 int fthmc_ft_action_grad(fthmc_flow_t flow, const double* x, double beta, double* action_out, double* grad_canon, double* force_out,
                          int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream);
+/* Vector-Jacobian product of the flow map (x, weights) -> (y = F(x), logJ), i.e. what loss.backward() propagates through
+ * `layer.forward` of every coupling layer (ipynb/field_transformation.py:160-166, 300-317) in the reference's train_step
+ * (ipynb/ft_hmc.py:253-295) for ANY loss built on (y, logJ): grad_canon / grad_x receive d/dweights (canonical layout, see
+ * fthmc_grad_unpack) and d/dx of  sum_b [ <gy_b, y_b> + glj_b * logJ_b ].  gy (B,2,L0,L1), glj (B); grad_x may be null.
+ * fthmc_ft_action_grad is the special case gy = dS/dy, glj = -1.  Workspace: fthmc_grad_workspace_bytes. */
+int fthmc_flow_vjp(fthmc_flow_t flow, const double* x, const double* gy, const double* glj, double* grad_canon, double* grad_x,
+                   int B, int L0, int L1, void* ws, size_t ws_bytes, void* stream);
 int fthmc_grad_doubles(void);
 int fthmc_grad_unpack(const double* grad_canon_host, int n_layers, const int* mu_host, double* raw_host);
 

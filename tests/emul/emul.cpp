@@ -79,6 +79,10 @@ extern "C" int emul_run(int mode, int B, int L0, int L1, int nlayers, const doub
 
 // Training gradient (MODE_FT_GRAD): action (B) and d/d(raw weights) of sum_b ft_action(x_b), (nlayers, 955).
 // Needs the tensor-core code path (FT_EMUL_MMA) and L0, L1 multiples of 8.
+static const double* g_vjp_seed = nullptr;       // set by emul_set_vjp: the next emul_grad call runs the vector-Jacobian mode
+static const double* g_vjp_wlj = nullptr;
+extern "C" void emul_set_vjp(const double* seed, const double* wlj) { g_vjp_seed = seed; g_vjp_wlj = wlj; }
+
 extern "C" int emul_grad(int B, int L0, int L1, int nlayers, const double* raw, const int* mu, const int* off,
                          int act, int conv, double beta, const double* field_in, double* action_out, double* grad_raw, double* force_out) {
     using namespace fthmc;
@@ -92,6 +96,8 @@ extern "C" int emul_grad(int B, int L0, int L1, int nlayers, const double* raw, 
     a.pr.L0 = L0; a.pr.L1 = L1; a.pr.nlayers = nlayers; a.pr.act = act; a.pr.conv = conv;
     a.pr.inv_tol = 1e-6; a.pr.inv_max_iter = 1000; a.pr.wpack = pack.data(); a.pr.lmu = mu; a.pr.loff = off; a.pr.train = 1;
     a.beta = beta; a.field_in = field_in; a.field_out = force_out; a.s_out = action_out;
+    a.vjp_seed = g_vjp_seed; a.vjp_wlj = g_vjp_wlj;
+    g_vjp_seed = nullptr; g_vjp_wlj = nullptr;
     SerialExec ex{ smem.data() };
     if (!ex.use_mma()) return -3;
     Engine<SerialExec> en(ex, a.pr, ws.data());

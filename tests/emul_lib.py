@@ -70,8 +70,10 @@ def run(mode, raw_weights, field, *, beta=1.0, dt=0.1, nstep=1, p=None, u=None, 
     return out
 
 
-def grad(raw_weights, field, *, beta=1.0, act="silu", conv=0, mu=None, off=None):
-    """MODE_FT_GRAD on the CPU build: ft_action (B,), d/d(raw weights) of its sum (n_layers, 955), force (B,2,L0,L1)."""
+def grad(raw_weights, field, *, beta=1.0, act="silu", conv=0, mu=None, off=None, vjp_seed=None, vjp_wlj=None):
+    """MODE_FT_GRAD on the CPU build: ft_action (B,), d/d(raw weights) of its sum (n_layers, 955), force (B,2,L0,L1).
+    vjp_seed (B,2,L0,L1) + vjp_wlj (B): the vector-Jacobian mode (fthmc_flow_vjp) -- `grad` / `force` are then d/dweights
+    and d/dx of sum_b [<seed_b, F(x_b)> + wlj_b logJ_b]."""
     os.environ["FT_EMUL_MMA"] = "1"
     field = np.ascontiguousarray(field, dtype=np.float64)
     B, _, L0, L1 = field.shape
@@ -80,6 +82,10 @@ def grad(raw_weights, field, *, beta=1.0, act="silu", conv=0, mu=None, off=None)
     mu = np.array([i % 2 for i in range(n)] if mu is None else mu, dtype=np.int32)
     off = np.array([(i // 2) % 4 for i in range(n)] if off is None else off, dtype=np.int32)
     action, g, force = np.zeros(B), np.zeros((n, 955)), np.zeros_like(field)
+    if vjp_seed is not None:
+        vjp_seed = np.ascontiguousarray(vjp_seed, dtype=np.float64)
+        vjp_wlj = np.ascontiguousarray(vjp_wlj, dtype=np.float64)
+        lib().emul_set_vjp(_p(vjp_seed), _p(vjp_wlj))
     try:
         rc = lib().emul_grad(B, L0, L1, n, _p(raw), _p(mu, ctypes.c_int), _p(off, ctypes.c_int), ACTS[act], conv,
                              ctypes.c_double(beta), _p(field), _p(action), _p(g), _p(force))

@@ -645,6 +645,38 @@ def test_flow_train_and_eval_drivers():
     assert 0 < ev["accept_rate"] <= 1 and ev["Q2"] >= 0 and ev["Q2_err"] >= 0 and len(ev["ensemble"]["x"]) == 128
 
 
+def test_flow_vjp_and_differentiable_flow():
+    """fthmc_flow_vjp against torch.autograd on the oracle (random d/dy and per-chain logJ weights), and the flow as a
+    differentiable torch operation: the reference's reverse-KL training loss written with ordinary torch code on
+    differentiable_flow / differentiable_u1_action gives, through loss.backward(), the gradients autograd gives on the oracle
+    -- in the Conv2d parameters of a reference-style ModuleList and in the latent field."""
+    from test_engine_emul import _vjp_reference
+    L, layers, B = 16, 8, 3
+    flow = O.random_flow(n_layers=layers, seed=41, scale=1.5)
+    raw = _raw_of(flow)
+    gen = torch.Generator().manual_seed(12)
+    x = torch.rand(B, 2, L, L, generator=gen, dtype=torch.float64) * 2 * np.pi
+    gy = torch.randn(B, 2, L, L, generator=gen, dtype=torch.float64)
+    glj = torch.randn(B, generator=gen, dtype=torch.float64)
+    gx_ref, gw_ref = _vjp_reference(flow, x, gy, glj)
+    gw, gx = ft.flow_vjp(ft.PackedFlow(raw), x.cuda(), gy.cuda(), glj.cuda())
+    assert relerr(gx.cpu().numpy(), gx_ref.numpy()) < REL
+    assert relerr(gw.numpy(), gw_ref.numpy()) < 1e-9
+    # reverse-KL loss through autograd on the kernels: mean(logq - logp), logq = const - logJ, logp = -S(x)
+    beta = 2.0
+    mod = module_like(dict(weights=raw))
+    xi = x.cuda().requires_grad_(True)
+    y, lj = ft.differentiable_flow(mod, xi)
+    loss = torch.mean(-lj + ft.differentiable_u1_action(beta, y))
+    loss.backward()
+    a_ref, g_ref = O.ft_action_weight_grad(beta, flow, x)
+    assert abs(float(loss.detach()) - float(a_ref.mean())) < 1e-10 * abs(float(a_ref.mean()))
+    got = np.stack([np.concatenate([np.concatenate([c.weight.grad.numpy().ravel(), c.bias.grad.numpy().ravel()])
+                                    for c in layer.plaq_coupling.net if hasattr(c, "weight")]) for layer in mod])
+    assert relerr(got, (g_ref / B).numpy()) < 1e-9
+    assert relerr(xi.grad.cpu().numpy(), (O.ft_force(beta, flow, x) / B).numpy()) < REL
+
+
 def test_flow_independence_sampler():
     """apply_flow_to_prior / make_mcmc_ensemble (ipynb/field_transformation.py:37-83) on the forward-flow kernel: logq
     and logp of the proposals against the oracle, and the accept/reject chain against a replay of the reference's loop."""
