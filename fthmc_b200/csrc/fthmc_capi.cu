@@ -270,6 +270,10 @@ struct ClusterExec : CtaExec {
 // device functions resolved the dynamic base differently (observed: 112 bytes apart at sizeof(Engine) = 272: the exp / atan
 // tables written by the kernel prologue were read 14 slots off by the phases).  A multiple of 128 makes every view agree.
 #define ENGINE_BUF_BYTES(EXEC) ((sizeof(Engine<EXEC>) + 127) / 128 * 128)
+// L = 32 (BASELINE config 3) fits ONE SM with 64 bytes to spare: 232 000 B of arena + 384 B of engine object of the 232 448 B
+// a block may opt into.  One more 128-byte step of the engine object would silently push L = 32 onto the 2-CTA cluster path.
+static_assert(ENGINE_BUF_BYTES(CtaExec) <= 384 && ENGINE_BUF_BYTES(ClusterExec) <= 384,
+              "Engine grew past 384 bytes: L=32 no longer fits a single SM's shared memory -- shrink the engine object or the arena");
 
 __global__ void __launch_bounds__(FT_THREADS, 1) k_chain_cluster(const ChainArgs a) {
     extern __shared__ __align__(16) double fthmc_dyn_smem[];
