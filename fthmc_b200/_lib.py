@@ -22,6 +22,7 @@ SIGNATURES = {
     "fthmc_force": (c_int, [c_dp, c_int, c_int, c_int, c_dbl, c_int, c_dp, c_int, c_dp]),
     "fthmc_topo_charge": (c_int, [c_dp, c_int, c_int, c_int, c_int, c_dp, c_int, c_dp]),
     "fthmc_regularize": (c_int, [c_dp, c_dp, c_ll, c_int, c_dp]),
+    "fthmc_chain_ranks": (c_int, [c_int, c_int, c_int]),
     "fthmc_workspace_bytes": (c_sz, [c_dp, c_int, c_int, c_int]),
     "fthmc_leapfrog": (c_int, [c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_dp, c_sz, c_dp]),
     "fthmc_hmc_traj": (c_int, [c_dp, c_dp, c_dp, c_dp, c_ull, c_ull, c_ull, c_int, c_int, c_int, c_dbl, c_dbl, c_int,

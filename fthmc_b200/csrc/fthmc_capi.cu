@@ -844,6 +844,11 @@ static long long resident_bound(int L0, int L1, bool flow, int nr, int B) {
     return nr == 1 ? (long long)nsm() * 32 : (long long)nsm() / nr;
 }
 
+extern "C" int fthmc_chain_ranks(int L0, int L1, int with_flow) {
+    if (L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4 || !devinfo().ok) return 0;
+    return chain_ranks(L0, L1, with_flow != 0);
+}
+
 extern "C" size_t fthmc_workspace_bytes(fthmc_flow_t flow, int B, int L0, int L1) {
     if (B <= 0 || L0 <= 0 || L1 <= 0 || L0 % 4 || L1 % 4) return 0;
     int nr = chain_ranks(L0, L1, flow != nullptr);

@@ -154,6 +154,10 @@ int fthmc_diag_dfma_probe(void* scratch, int iters, int blocks, void* stream, do
 /* the same on the fp64 tensor path: 8 independent DMMA.8x8x4 accumulator tiles per warp (512 flop per DMMA per warp) */
 int fthmc_diag_dmma_probe(void* scratch, int iters, int blocks, void* stream, double* flop_out_host);
 
+/* diagnostic: CTAs a chain of this lattice is spread over on the current device -- 1 = the whole chain resident in one SM's
+ * shared memory (L0*L1 <= 1024 with a flow), 2..16 = one thread-block cluster per chain, 0 = does not fit / no device */
+int fthmc_chain_ranks(int L0, int L1, int with_flow);
+
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 unsigned long long fthmc_launch_count(void);
 

@@ -761,6 +761,15 @@ def test_stencils_beyond_grid_y_limit():
         assert relerr(f[i].numpy(), O.force_closed_form(4.0, x[i]).numpy()) < REL
 
 
+def test_resident_path_selection():
+    """Which lattices run with the whole chain in ONE SM's shared memory and which on a thread-block cluster: a guard for the
+    L=32 shared-memory budget (232 384 of 232 448 bytes; one more 128-byte step of the engine object would silently move the
+    headline configuration onto the 2-CTA cluster path)."""
+    L = ft.lib()
+    assert [L.fthmc_chain_ranks(n, n, 1) for n in (8, 16, 32, 48, 64, 128)] == [1, 1, 1, 3, 4, 16]
+    assert L.fthmc_chain_ranks(32, 32, 0) == 1 and L.fthmc_chain_ranks(256, 256, 1) == 0
+
+
 def test_copyB_physics_golden(golden):
     """Reference-generated goldens of the package copy's physics helpers (fthmc/utils/qed_helpers.py:73-116 batch_charges /
     topo_charge, :166-186 BatchAction, :191-242 ft_flow / ft_flow_inv / ft_action / ft_force on (B,2,L,L), :261-311 action /
