@@ -194,62 +194,55 @@ FT_HD double exp_fast(double x) {
     return fma(sc, q, sc);
 }
 
-// sin / cos for the Wilson stencils: one branch-free evaluation with ~1 ulp error for |x| < 2^19 (beyond that, and for
-// non-finite arguments, the library function).  x = n pi/2 + r by a three-term Cody-Waite reduction (pi/2 in 33-bit
-// pieces, fdlibm's pio2_1 / pio2_2 / pio2_2t: n * piece is exact), then ONE degree-5 polynomial in r^2 whose coefficients
-// are selected per lane between fdlibm's sine and cosine kernels: 15 fp64 operations where the library's sin / cos
-// spends ~25 plus its slow-path bookkeeping -- the reduction scans are issue bound, not HBM bound, with the latter.
-// constants: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -pi/2 in three pieces, [5..10] sine kernel S6..S1, [11..16] C - S for C6..C1.
-// On the device they sit in constant memory (a DFMA takes a constant-bank operand directly; as 64-bit immediates every
-// use costs two extra moves, which made the scans issue bound).
+// cos for the Wilson action stencil: x = n pi + r, |r| <= pi/2, by a three-term Cody-Waite reduction (pi in 34-bit pieces,
+// twice fdlibm's pio2_1 / pio2_2 / pio2_2t), then cos x = (-1)^n cos r with ONE even polynomial (Taylor to r^22: truncation
+// < 1e-19 on the interval) -- 17 fp64 operations, every Horner step with a single constant-bank operand, the sign through
+// the parity bit of n: no per-lane coefficient selects, no constant loads into registers.  (The first form reduced to
+// [-pi/4, pi/4] and blended sine / cosine coefficients per lane: 21 fp64 operations, eight LDC.64 and six FSEL per site; the
+// reduction scans are ISSUE bound, not HBM bound.)  Absolute error ~1.5e-16 (the result is not relatively accurate next to
+// its zeros, which a sum of cosines does not need).  |x| < 2^19; beyond that, and for non-finite arguments, the library.
+// constants: [0] 1/pi, [1] 1.5 * 2^52, [2..4] -pi in three pieces, [5..15] -1/22!, 1/20!, ... 1/4!, -1/2
+// (sincos_fast's constants: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -pi/2 in three pieces, [5..10] fdlibm's sine kernel S6..S1)
 #define FT_TRIG_CONSTS { 0.63661977236758134308, 6755399441055744.0, \
     -1.57079632673412561417e+00, -6.07710050630396597660e-11, -2.02226624879595063154e-21, \
     1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, \
-    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01, \
-    -1.13596475577881948265e-11 - 1.58969099521155010221e-10, 2.08757232129817482790e-09 + 2.50507602534068634195e-08, \
-    -2.75573143513906633035e-07 - 2.75573137070700676789e-06, 2.48015872894767294178e-05 + 1.98412698298579493134e-04, \
-    -1.38888888888741095749e-03 - 8.33333333332248946124e-03, 4.16666666666666019037e-02 + 1.66666666666666324348e-01 }
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01 }
+#define FT_COSPI_CONSTS { 0.31830988618379067154, 6755399441055744.0, \
+    -2.0 * 1.57079632673412561417e+00, -2.0 * 6.07710050630396597660e-11, -2.0 * 2.02226624879595063154e-21, \
+    -1.0 / 1124000727777607680000.0, 1.0 / 2432902008176640000.0, -1.0 / 6402373705728000.0, \
+    1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5 }
 #ifdef __CUDACC__
-__constant__ double c_trig[17] = FT_TRIG_CONSTS;
+__constant__ double c_trig[11] = FT_TRIG_CONSTS;
+__constant__ double c_cospi[16] = FT_COSPI_CONSTS;
 #endif
-FT_HD double sincos_kernel(double x, int quadrant_shift) {
+FT_HD double cos_fast(double x) {
+    if (!(fabs(x) < 524288.0)) return cos(x);
 #ifdef __CUDA_ARCH__
-    const double* K = c_trig;
+    const double* K = c_cospi;
 #else
-    const double K[17] = FT_TRIG_CONSTS;
+    const double K[16] = FT_COSPI_CONSTS;
 #endif
-    const double t = fma(x, K[0], K[1]);                                      // n = rint(x * 2/pi) in the low mantissa bits
+    const double t = fma(x, K[0], K[1]);                                      // n = rint(x / pi) in the low mantissa bits
     const double n = t - K[1];
-    int q;
-#ifdef __CUDA_ARCH__
-    q = __double2loint(t);
-#else
-    q = (int)(long long)n;
-#endif
-    q += quadrant_shift;                                                      // sin: 0, cos: +1  (cos x = sin(x + pi/2))
     double r = fma(n, K[2], x);
     r = fma(n, K[3], r);
     r = fma(n, K[4], r);
-    // odd quadrant: cosine kernel.  The coefficients are blended arithmetically, k = S + odd * (C - S) (one DFMA with
-    // constant-bank operands each; exact to ~0.1 ulp of the result) instead of per-lane selects of 64-bit constants.
-    const bool odd = q & 1;
-    const double od = odd ? 1.0 : 0.0;
-    const double r2 = r * r;
-    double p = fma(od, K[11], K[5]);
+    const double s = r * r;
+    double p = K[5];
 #pragma unroll
-    for (int i = 1; i < 6; ++i) p = fma(p, r2, fma(od, K[11 + i], K[5 + i]));
-    const double a = (odd ? r2 : r) * r2;                                     // cos: r^4 P + (1 - r^2/2),  sin: r^3 P + r
-    const double b = odd ? fma(-0.5, r2, 1.0) : r;
-    const double v = fma(a, p, b);
-    return (q & 2) ? -v : v;
+    for (int i = 6; i < 16; ++i) p = fma(p, s, K[i]);
+    p = fma(p, s, 1.0);
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(p) ^ (__double2loint(t) << 31), __double2loint(p));
+#else
+    return (((long long)n) & 1) ? -p : p;
+#endif
 }
-FT_HD double sin_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 0) : sin(x); }
-FT_HD double cos_fast(double x) { return fabs(x) < 524288.0 ? sincos_kernel(x, 1) : cos(x); }
 
-// sin(x) and cos(x) together: one Cody-Waite reduction (as in sincos_kernel), fdlibm's sine and cosine kernels on the
+// sin(x) and cos(x) together: one three-term Cody-Waite reduction x = n pi/2 + r, fdlibm's sine and cosine kernels on the
 // remainder, quadrant swap / signs by selects.  Branch-free for |x| < 2^19 (~24 fp64 operations; ~1 ulp), so that the
 // compiler interleaves it with the neighbouring exp / atan chains of a site; the library sincos() beyond.
-// constants: FT_TRIG_CONSTS, then [17..22] the cosine kernel C6..C1
+// constants: FT_TRIG_CONSTS and the cosine kernel C6..C1
 #define FT_COS_CONSTS { -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, \
                         2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02 }
 #ifdef __CUDACC__
@@ -260,7 +253,7 @@ FT_HD void sincos_fast(double x, double& sn, double& cs) {
 #ifdef __CUDA_ARCH__
     const double* K = c_trig; const double* C = c_cosk;
 #else
-    const double K[17] = FT_TRIG_CONSTS; const double C[6] = FT_COS_CONSTS;
+    const double K[11] = FT_TRIG_CONSTS; const double C[6] = FT_COS_CONSTS;
 #endif
     const double t = fma(x, K[0], K[1]);
     const double n = t - K[1];
@@ -371,14 +364,57 @@ FT_HD double rcp_ge1(double d) {
 
 // activation (and derivative) with the kind as a compile-time parameter: the element loops below are
 // unrolled and must stay branch-free so that several exp chains interleave in one warp
+#ifndef FT_SILU_V2
+#define FT_SILU_V2 1
+#endif
+// 1 + e^x for the SiLU passes (issue bound: every fp64 operation counts): exp_fast with the argument reduction against ONE
+// constant (the fma is exact; the error n * |C - ln2/64| <= 8.7e-19 n stays below 1 ulp of e^x for |x| < 3.5 and grows to
+// ~6 ulp at |x| = 20 -- sigma(z) is then within 2e-9 of 0 or 1), and the "+ 1" folded into the last fma's addend so that it
+// leaves the dependent chain: 10 fp64 operations instead of 12.
+FT_HD double one_plus_exp(double x) {
+#ifdef __CUDA_ARCH__
+    const double* K = c_exp;
+    extern __shared__ __align__(16) double fthmc_dyn_smem[];
+    const double* TAB = fthmc_dyn_smem + FT_EXP_TAB_OFF;
+#else
+    const double K[8] = FT_EXP_COEFS;
+    static const double TAB[64] = FT_EXP_TABLE;
+#endif
+    const double nm = fma(x, K[4], K[5]);
+    const double n = nm - K[5];
+    const double r = fma(n, -0.010830424696249145, x);                        // -ln2/64
+    double w = K[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) w = fma(w, r, K[i]);
+    const double q = r * fma(r, w, 1.0);
+    int ni;
+#ifdef __CUDA_ARCH__
+    ni = __double2loint(nm);
+#else
+    ni = (int)(long long)fmin(fmax(n, -2147483647.0), 2147483647.0);
+#endif
+    const double tj = TAB[ni & 63];
+    int k = ni >> 6;
+    k = k < -1022 ? -1022 : (k > 1021 ? 1021 : k);
+    double sc;
+#ifdef __CUDA_ARCH__
+    sc = __hiloint2double(__double2hiint(tj) + (k << 20), __double2loint(tj));
+#else
+    long long bits;
+    memcpy(&bits, &tj, sizeof(bits));
+    bits += (long long)k << 52;
+    memcpy(&sc, &bits, sizeof(sc));
+#endif
+    return fma(sc, q, sc + 1.0);
+}
 template <int ACT> FT_HD void act_fwd_t(double z, double& h) {
-    if (ACT == ACT_SILU) h = z * rcp_ge1(1.0 + exp_fast(-z));
+    if (ACT == ACT_SILU) h = z * rcp_ge1(FT_SILU_V2 ? one_plus_exp(-z) : 1.0 + exp_fast(-z));
     else if (ACT == ACT_LEAKY) h = z > 0.0 ? z : 0.01 * z;
     else h = z > 0.0 ? z : 0.0;
 }
 template <int ACT> FT_HD void act_fwd_der_t(double z, double& h, double& d) {
     if (ACT == ACT_SILU) {
-        double sg = rcp_ge1(1.0 + exp_fast(-z));
+        double sg = rcp_ge1(FT_SILU_V2 ? one_plus_exp(-z) : 1.0 + exp_fast(-z));
         h = z * sg;
         d = fma(sg, fma(-z, sg, z), sg);          // sg * (1 + z * (1 - sg))
     } else if (ACT == ACT_LEAKY) {

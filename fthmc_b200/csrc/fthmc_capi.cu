@@ -337,8 +337,22 @@ template <> struct M<double> {
     static __device__ double floorv(double x) { return floor(x); }
     static __device__ double modv(double x, double y) { return fmod(x, y); }
 };
+// cosf for the fp32 action scan: x = n pi + r by a two-term reduction (fmaf), cos x = (-1)^n cos r, one even polynomial
+// (Taylor to r^12: truncation 6e-9 on |r| <= pi/2) -- 11 fp32 operations; |x| < 2^15, beyond that the library.
+static __device__ __forceinline__ float cosf_pi(float x) {
+    if (!(fabsf(x) < 32768.0f)) return cosf(x);
+    const float t = fmaf(x, 0.318309886f, 12582912.0f);                        // n = rint(x / pi) in the low mantissa bits
+    const float n = t - 12582912.0f;
+    float r = fmaf(n, -3.14159274101257324f, x);
+    r = fmaf(n, 8.74227765734758577e-8f, r);
+    const float s = r * r;
+    float p = 1.0f / 479001600.0f;
+    p = fmaf(p, s, -1.0f / 3628800.0f); p = fmaf(p, s, 1.0f / 40320.0f); p = fmaf(p, s, -1.0f / 720.0f);
+    p = fmaf(p, s, 1.0f / 24.0f); p = fmaf(p, s, -0.5f); p = fmaf(p, s, 1.0f);
+    return __int_as_float(__float_as_int(p) ^ (__float_as_int(t) << 31));
+}
 template <> struct M<float> {
-    static __device__ float cosv(float x) { return cosf(x); }
+    static __device__ float cosv(float x) { return FT_FAST_TRIG ? cosf_pi(x) : cosf(x); }
     static __device__ float sinv(float x) { return sinf(x); }
     static __device__ float floorv(float x) { return floorf(x); }
     static __device__ float modv(float x, float y) { return fmodf(x, y); }
@@ -488,8 +502,11 @@ __global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ 
 // shared memory, so the HBM stream never waits for the cos / wrap arithmetic.  The scans are issue bound after that
 // (ncu: issue slots 74 % busy), so the ring is kept short (FT_TMA_STAGES = 2: six CTAs of 2 x 16 KB per SM at L = 32).  One block barrier per chain: it publishes the warps' partial sums (thread 0 adds them in warp order:
 // deterministic) and frees the stage for thread 0 to refill.
+#ifndef FT_TMA_MINB
+#define FT_TMA_MINB 1
+#endif
 template <typename T, int NSTAGE, int WHAT, int ORDER>
-__global__ void __launch_bounds__(256) k_action_topo_tma(const T* __restrict__ links, int B, int L0, int L1, int stage_elems,
+__global__ void __launch_bounds__(256, FT_TMA_MINB) k_action_topo_tma(const T* __restrict__ links, int B, int L0, int L1, int stage_elems,
                                                        double beta, int rounded, T* __restrict__ out) {
     constexpr int what = WHAT, order = ORDER;
     extern __shared__ __align__(128) unsigned char tma_raw[];
@@ -517,7 +534,22 @@ __global__ void __launch_bounds__(256) k_action_topo_tma(const T* __restrict__ l
     constexpr int N = Vec<T>::N;
     using VT = typename Vec<T>::type;
     const int W = L1 / N, nvec = L0 * W, dr = 256 / W, dc = 256 - dr * W;
-    const int row0 = tid / W, col0 = tid - row0 * W;
+    // Every chain has the same geometry: the element offsets of this thread's (at most MAXIT: a stage holds <= 32 KB) vectors
+    // are computed once, outside the chain loop -- the scans are issue bound, and the (row, column) stepping with its two
+    // periodic wraps was a quarter of the loop's instructions.
+    constexpr int MAXIT = 4;
+    int o0[MAXIT], o0n[MAXIT], o1[MAXIT], o1p[MAXIT];
+    {
+        int row = tid / W, col = tid - row * W;
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int n1 = col * N, n0p = row + 1 >= L0 ? 0 : row + 1, n1n = n1 + N == L1 ? 0 : n1 + N;
+            o0[it] = row * L1 + n1; o0n[it] = row * L1 + n1n; o1[it] = (L0 + row) * L1 + n1; o1p[it] = (L0 + n0p) * L1 + n1;
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+    }
+    const int nit = tid < nvec ? (nvec - tid + 255) / 256 : 0;
     for (int k = 0; k < nmine; ++k) {
         const int st = k % NSTAGE;
         {
@@ -534,21 +566,20 @@ __global__ void __launch_bounds__(256) k_action_topo_tma(const T* __restrict__ l
         }
         const T* f = buf + (size_t)st * stage_elems;
         double acc = 0.0;
-        int row = row0, col = col0;
-        for (int i = tid; i < nvec; i += 256) {
-            const int n1 = col * N, n0p = row + 1 == L0 ? 0 : row + 1, n1n = n1 + N == L1 ? 0 : n1 + N;
-            __align__(16) T t0[N + 1], t1[N], t1p[N];
-            *reinterpret_cast<VT*>(t0) = *reinterpret_cast<const VT*>(f + row * L1 + n1);
-            t0[N] = f[row * L1 + n1n];
-            *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + (L0 + row) * L1 + n1);
-            *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + (L0 + n0p) * L1 + n1);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
-                acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+        for (int it = 0; it < MAXIT; ++it) {
+            if (it < nit) {
+                __align__(16) T t0[N + 1], t1[N], t1p[N];
+                *reinterpret_cast<VT*>(t0) = *reinterpret_cast<const VT*>(f + o0[it]);
+                t0[N] = f[o0n[it]];
+                *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + o1[it]);
+                *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + o1p[it]);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+                    acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+                }
             }
-            col += dc; row += dr;
-            if (col >= W) { col -= W; ++row; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -941,10 +972,14 @@ static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta
         constexpr int NSTAGE = FT_TMA_STAGES;
         const int stage_elems = (int)(((chain_bytes + 127) / 128) * 128 / sizeof(T));
         const size_t smem = (size_t)NSTAGE * stage_elems * sizeof(T) + NSTAGE * 8 + 16 * 8;
-        int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
-        int grid = nsm() * per_sm; if (grid > B) grid = B;
         auto kern = k_action_topo_tma<T, NSTAGE, WHAT, ORDER>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // persistent CTAs: exactly as many as are resident at once (registers or shared memory, whichever binds)
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        if (per_sm < 1) per_sm = 1;
+        if ((size_t)per_sm * (smem + 1024) > 200 * 1024) per_sm = (int)((200 * 1024) / (smem + 1024));
+        int grid = nsm() * per_sm; if (grid > B) grid = B;
         kern<<<grid, 256, smem, st>>>((const T*)links, B, L0, L1, stage_elems, beta, rounded, (T*)out);
         g_launches += 1;
         CK(cudaGetLastError());
