@@ -90,6 +90,33 @@ def test_reduction_stencils_large_batch(shape, dtype):
         assert np.array_equal(q[:5], small)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("scale", [40.0, 3.0e5, 4.0e6])
+def test_action_on_unwrapped_links(scale, dtype):
+    """HMC never wraps the links between Metropolis steps, so the plaquette angles the action scans see are unbounded: the
+    scans' cosine reduces by multiples of pi up to 2^19 (2^15 in fp32) and hands larger arguments to the library.  Every
+    kernel form (TMA ring, warp per chain, CTA per chain, cluster per chain) against the oracle on links of magnitude
+    `scale`; one chain carries an Inf and must come back NaN, as torch.cos gives."""
+    gen = torch.Generator().manual_seed(int(scale))
+    for B, L0, L1 in [(2400, 32, 32), (2400, 8, 12), (2400, 8, 8), (5, 32, 32), (2, 256, 128)]:
+        x = (torch.rand(B, 2, L0, L1, generator=gen, dtype=torch.float64) * 2 - 1) * scale
+        xd = x.to(dtype).cuda()
+        # the plaquette angle in the caller's precision and the reference's term order (field_transformation.py:118-119),
+        # then an exact cosine of THAT angle summed in fp64: what the scan's cosine is measured against
+        xc = xd.cpu()
+        pl = ((xc[:, 0] + torch.roll(xc[:, 1], -1, 1)) - torch.roll(xc[:, 0], -1, 2)) - xc[:, 1]
+        ref = (-2.5 * torch.cos(pl.double()).sum(dim=(1, 2))).numpy()
+        if dtype == torch.float64:
+            assert relerr(ref, O.u1_action(2.5, xc).numpy()) < 1e-12
+        got = ft.u1_action(2.5, xd).double().cpu().numpy()
+        bar = 2.5 * L0 * L1 * (4e-16 if dtype == torch.float64 else 3e-7)      # beta * V * (error of one cosine)
+        assert np.max(np.abs(got - ref)) < bar, (B, L0, L1, np.max(np.abs(got - ref)))
+    x = torch.zeros(3, 2, 32, 32, dtype=dtype)
+    x[1, 0, 3, 4] = float("inf")
+    a = ft.u1_action(2.5, x.cuda()).cpu()
+    assert bool(torch.isnan(a[1])) and float(a[0]) == -2.5 * 1024 and float(a[2]) == -2.5 * 1024
+
+
 # ---------------------------------------------------------------- plain HMC
 def test_plain_hmc_teacher_forced_golden(golden):
     g = golden("plain_L8")
