@@ -195,13 +195,13 @@ FT_HD double exp_fast(double x) {
 }
 
 // cos for the Wilson action stencil: x = n pi + r, |r| <= pi/2, by a three-term Cody-Waite reduction (pi in 34-bit pieces,
-// twice fdlibm's pio2_1 / pio2_2 / pio2_2t), then cos x = (-1)^n cos r with ONE even polynomial (Taylor to r^22: truncation
-// < 1e-19 on the interval) -- 17 fp64 operations, every Horner step with a single constant-bank operand, the sign through
+// twice fdlibm's pio2_1 / pio2_2 / pio2_2t), then cos x = (-1)^n cos r with ONE even polynomial (Taylor to r^20: truncation
+// < 2e-17 on the interval) -- 16 fp64 operations, every Horner step with a single constant-bank operand, the sign through
 // the parity bit of n: no per-lane coefficient selects, no constant loads into registers.  (The first form reduced to
 // [-pi/4, pi/4] and blended sine / cosine coefficients per lane: 21 fp64 operations, eight LDC.64 and six FSEL per site; the
 // reduction scans are ISSUE bound, not HBM bound.)  Absolute error ~1.5e-16 (the result is not relatively accurate next to
 // its zeros, which a sum of cosines does not need).  |x| < 2^19; beyond that, and for non-finite arguments, the library.
-// constants: [0] 1/pi, [1] 1.5 * 2^52, [2..4] -pi in three pieces, [5..15] -1/22!, 1/20!, ... 1/4!, -1/2
+// constants: [0] 1/pi, [1] 1.5 * 2^52, [2..4] -pi in three pieces, [5..14] 1/20!, -1/18!, ... 1/4!, -1/2
 // (sincos_fast's constants: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -pi/2 in three pieces, [5..10] fdlibm's sine kernel S6..S1)
 #define FT_TRIG_CONSTS { 0.63661977236758134308, 6755399441055744.0, \
     -1.57079632673412561417e+00, -6.07710050630396597660e-11, -2.02226624879595063154e-21, \
@@ -209,18 +209,22 @@ FT_HD double exp_fast(double x) {
     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01 }
 #define FT_COSPI_CONSTS { 0.31830988618379067154, 6755399441055744.0, \
     -2.0 * 1.57079632673412561417e+00, -2.0 * 6.07710050630396597660e-11, -2.0 * 2.02226624879595063154e-21, \
-    -1.0 / 1124000727777607680000.0, 1.0 / 2432902008176640000.0, -1.0 / 6402373705728000.0, \
+    1.0 / 2432902008176640000.0, -1.0 / 6402373705728000.0, \
     1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5 }
+// sin_fast: the same reduction, sin x = (-1)^n sin r, sin r = r + r s Q(s) with the odd Taylor series to r^21 (truncation 1.2e-18)
+#define FT_SINPI_CONSTS { 1.0 / 51090942171709440000.0, -1.0 / 121645100408832000.0, 1.0 / 355687428096000.0, -1.0 / 1307674368000.0, \
+    1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0 }
 #ifdef __CUDACC__
 __constant__ double c_trig[11] = FT_TRIG_CONSTS;
-__constant__ double c_cospi[16] = FT_COSPI_CONSTS;
+__constant__ double c_cospi[15] = FT_COSPI_CONSTS;
+__constant__ double c_sinpi[10] = FT_SINPI_CONSTS;
 #endif
 FT_HD double cos_fast(double x) {
     if (!(fabs(x) < 524288.0)) return cos(x);
 #ifdef __CUDA_ARCH__
     const double* K = c_cospi;
 #else
-    const double K[16] = FT_COSPI_CONSTS;
+    const double K[15] = FT_COSPI_CONSTS;
 #endif
     const double t = fma(x, K[0], K[1]);                                      // n = rint(x / pi) in the low mantissa bits
     const double n = t - K[1];
@@ -230,7 +234,7 @@ FT_HD double cos_fast(double x) {
     const double s = r * r;
     double p = K[5];
 #pragma unroll
-    for (int i = 6; i < 16; ++i) p = fma(p, s, K[i]);
+    for (int i = 6; i < 15; ++i) p = fma(p, s, K[i]);
     p = fma(p, s, 1.0);
 #ifdef __CUDA_ARCH__
     return __hiloint2double(__double2hiint(p) ^ (__double2loint(t) << 31), __double2loint(p));
@@ -238,6 +242,35 @@ FT_HD double cos_fast(double x) {
     return (((long long)n) & 1) ? -p : p;
 #endif
 }
+#ifndef FT_FAST_SIN
+#define FT_FAST_SIN 1
+#endif
+// sin for the Wilson force (k_force, the plain-HMC leapfrog): 18 fp64 operations; absolute error ~2e-16, relative accuracy
+// next to the zeros at multiples of pi as well (the result is r (1 + ...) there).
+FT_HD double sin_fast(double x) {
+    if (!(fabs(x) < 524288.0)) return sin(x);
+#ifdef __CUDA_ARCH__
+    const double* K = c_cospi; const double* S = c_sinpi;
+#else
+    const double K[15] = FT_COSPI_CONSTS; const double S[10] = FT_SINPI_CONSTS;
+#endif
+    const double t = fma(x, K[0], K[1]);
+    const double n = t - K[1];
+    double r = fma(n, K[2], x);
+    r = fma(n, K[3], r);
+    r = fma(n, K[4], r);
+    const double s = r * r;
+    double p = S[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) p = fma(p, s, S[i]);                          // Q(s) = -1/6 + s/120 - ...
+    p = fma(r * s, p, r);
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(p) ^ (__double2loint(t) << 31), __double2loint(p));
+#else
+    return (((long long)n) & 1) ? -p : p;
+#endif
+}
+FT_HD double sin_force(double x) { return FT_FAST_SIN ? sin_fast(x) : sin(x); }   // every Wilson-force site: one definition, so that all paths agree bitwise
 
 // sin(x) and cos(x) together: one three-term Cody-Waite reduction x = n pi/2 + r, fdlibm's sine and cosine kernels on the
 // remainder, quadrant swap / signs by selects.  Branch-free for |x| < 2^19 (~24 fp64 operations; ~1 ulp), so that the
@@ -745,7 +778,7 @@ struct Engine {
             for (int i = ex.tid(); i < V; i += ex.nt()) {
                 int n0, n1; site_map(i, n0, n1);
                 const int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
-                const double s = sin(plaq(oX, n0, n1, order)), s1 = sin(plaq(oX, n0, n1m, order)), s0 = sin(plaq(oX, n0m, n1, order));
+                const double s = sin_force(plaq(oX, n0, n1, order)), s1 = sin_force(plaq(oX, n0, n1m, order)), s0 = sin_force(plaq(oX, n0m, n1, order));
                 *xat(oGR, 0, n0, n1) = beta * (s - s1);
                 *xat(oGR, 1, n0, n1) = beta * (s0 - s);
             }
@@ -757,7 +790,7 @@ struct Engine {
         const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1, s0 = ex.tid() / L1, s1 = ex.tid() - s0 * L1;
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
             if (n1 >= L1) { n1 -= L1; ++n0; }
-            S[i] = sin(plaq(oX, n0, n1, order));
+            S[i] = sin_force(plaq(oX, n0, n1, order));
         }
         ex.sync();
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
@@ -2387,7 +2420,7 @@ FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep
         const double step = st == nstep - 1 ? hdt : dt;
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
             if (n1 >= L1) { n1 -= L1; ++n0; }
-            S[i] = sin(en.plaq(en.oX, n0, n1, 1));
+            S[i] = sin_force(en.plaq(en.oX, n0, n1, 1));
         }
         ex.sync();
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
