@@ -270,7 +270,10 @@ FT_HD double sin_fast(double x) {
     return (((long long)n) & 1) ? -p : p;
 #endif
 }
-FT_HD double sin_force(double x) { return FT_FAST_SIN ? sin_fast(x) : sin(x); }   // every Wilson-force site: one definition, so that all paths agree bitwise
+// the sine of the plain-HMC kernels (k_force, k_chain_plain).  The flow kernels keep the library sine in their Wilson-force
+// seed (0.4 % of a force evaluation): their register allocation is fragile -- the same seed with sin_fast inlined made k_chain
+// 0.9 % slower as a whole, a kernel without the training sweeps 6 % slower (profiles/r2_microopt_ab.txt (16), (17)).
+FT_HD double sin_force(double x) { return FT_FAST_SIN ? sin_fast(x) : sin(x); }
 
 // sin(x) and cos(x) together: one three-term Cody-Waite reduction x = n pi/2 + r, fdlibm's sine and cosine kernels on the
 // remainder, quadrant swap / signs by selects.  Branch-free for |x| < 2^19 (~24 fp64 operations; ~1 ulp), so that the
@@ -778,7 +781,7 @@ struct Engine {
             for (int i = ex.tid(); i < V; i += ex.nt()) {
                 int n0, n1; site_map(i, n0, n1);
                 const int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
-                const double s = sin_force(plaq(oX, n0, n1, order)), s1 = sin_force(plaq(oX, n0, n1m, order)), s0 = sin_force(plaq(oX, n0m, n1, order));
+                const double s = sin(plaq(oX, n0, n1, order)), s1 = sin(plaq(oX, n0, n1m, order)), s0 = sin(plaq(oX, n0m, n1, order));
                 *xat(oGR, 0, n0, n1) = beta * (s - s1);
                 *xat(oGR, 1, n0, n1) = beta * (s0 - s);
             }
@@ -790,7 +793,7 @@ struct Engine {
         const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1, s0 = ex.tid() / L1, s1 = ex.tid() - s0 * L1;
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
             if (n1 >= L1) { n1 -= L1; ++n0; }
-            S[i] = sin_force(plaq(oX, n0, n1, order));
+            S[i] = sin(plaq(oX, n0, n1, order));
         }
         ex.sync();
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
@@ -2399,7 +2402,8 @@ FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, For
 // momentum update and the position update -- with division-free site stepping.  Same operations in the same order as
 // leapfrog_resident + wilson_force (bit-identical results), without the per-step trips of the momenta through L2, the
 // separate gradient plane and a third barrier.  Single-CTA chains only; clusters use the generic path.
-template <class E>
+// FAST: the dedicated sine (k_chain_plain); the flow kernels, which carry this program only for completeness, keep the library's
+template <class E, bool FAST = false>
 FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep, double* Pg) {
     auto& ex = en.ex;
     const int L0 = en.L0, L1 = en.L1, LP = en.LP, V = en.V;
@@ -2420,7 +2424,7 @@ FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep
         const double step = st == nstep - 1 ? hdt : dt;
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
             if (n1 >= L1) { n1 -= L1; ++n0; }
-            S[i] = sin_force(en.plaq(en.oX, n0, n1, 1));
+            S[i] = FAST ? sin_force(en.plaq(en.oX, n0, n1, 1)) : sin(en.plaq(en.oX, n0, n1, 1));
         }
         ex.sync();
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
@@ -2499,7 +2503,7 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
 }
 
 // plain HMC trajectory (hmc_2dU1.py:144-155)
-template <class E>
+template <class E, bool FAST = false>
 FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     auto& ex = en.ex;
     const int V = en.Vg;
@@ -2517,7 +2521,7 @@ FT_HD void hmc_trajectory(Engine<E>& en, const TrajIO& io) {
     double s0 = en.wilson_action(io.beta, 1);
     double h0 = s0 + 0.5 * k0;
     if constexpr (E::kCluster) leapfrog_resident(en, io.dt, io.nstep, P, [&]() { en.wilson_force(io.beta, 1); });
-    else leapfrog_plain_fused(en, io.beta, io.dt, io.nstep, P);
+    else leapfrog_plain_fused<E, FAST>(en, io.beta, io.dt, io.nstep, P);
     en.for_links([&](int si, int gi) { X[si] = regularize1(X[si]); });
     ex.sync();
     double k1 = 0.0;

@@ -150,7 +150,7 @@ FT_HD void run_chain_plain(Engine<E>& en, const ChainArgs& a, int b) {
         en.for_links([&](int, int gi) { en.wsP[gi] = a.p_in[(size_t)b * fs + gi]; });
         ex.sync();
         if constexpr (E::kCluster) leapfrog_resident(en, a.dt, a.nstep, en.wsP, [&]() { en.wilson_force(a.beta, 1); });
-        else leapfrog_plain_fused(en, a.beta, a.dt, a.nstep, en.wsP);
+        else leapfrog_plain_fused<E, true>(en, a.beta, a.dt, a.nstep, en.wsP);
         en.store_field(fout, en.oX);
         en.for_links([&](int, int gi) { a.p_out[(size_t)b * fs + gi] = en.wsP[gi]; });
         ex.sync();
@@ -173,7 +173,7 @@ FT_HD void run_chain_plain(Engine<E>& en, const ChainArgs& a, int b) {
         io.out_Q = a.topo ? a.topo + row : nullptr;
         io.out_h0 = nullptr; io.out_h1 = nullptr;
         io.first = t == 0; io.last = t == nt - 1;
-        hmc_trajectory(en, io);
+        hmc_trajectory<E, true>(en, io);
     }
 }
 
