@@ -403,6 +403,9 @@ FT_HD double rcp_ge1(double d) {
 #ifndef FT_SILU_V2
 #define FT_SILU_V2 1
 #endif
+#ifndef FT_CL_PLANES
+#define FT_CL_PLANES 1
+#endif
 // 1 + e^x for the SiLU passes (issue bound: every fp64 operation counts): exp_fast with the argument reduction against ONE
 // constant (the fma is exact; the error n * |C - ln2/64| <= 8.7e-19 n stays below 1 ulp of e^x for |x| < 3.5 and grows to
 // ~6 ulp at |x| = 20 -- sigma(z) is then within 2e-9 of 0 or 1), and the "+ 1" folded into the last fma's addend so that it
@@ -822,6 +825,42 @@ struct Engine {
     FT_PHASE void ph_planes(const LayerGeom g, double* cs_save) {
         double* CS = sm(oCS); double* UA = sm(oUA);
         const int T = g.G * g.R, order = pr.conv;
+#if FT_CL_PLANES
+        if constexpr (CL) {
+            // Cluster mode, mu = 0 layers: the stripes run along n0, the links are split by blocks of n0, so all but 1 / nr of
+            // the plaquettes of this rank's columns are read through distributed shared memory.  With the lanes of a warp
+            // along the stripe (consecutive n0) every lane's 8 bytes come from a different row, often a different owner;
+            // remote loads are served a sector at a time.  Two steps instead: the plaquette angles with the lanes ACROSS
+            // the stripes (consecutive n1: the rank's Cn columns of a row are contiguous in the owner's memory) into a
+            // scratch plane (plane A is free here; pitch R + 1: conflict-free both ways), then cos / sin with the lanes
+            // along the stripe as everywhere else.  Same operands, same operations: bit-identical to the direct form.
+            if (g.mu == 0 && !fine_tasks()) {
+                double* SCR = sm(oA);
+                const int Cn = g.Cn, R = g.R, RP = R + 1;
+                const int dr = ex.nt() / Cn, dc = ex.nt() - dr * Cn;
+                int r = ex.tid() / Cn, c = ex.tid() - r * Cn;
+                for (int i = ex.tid(); i < V; i += ex.nt(), r += dr, c += dc) {
+                    if (c >= Cn) { c -= Cn; ++r; }
+                    if ((c & 3) != 3) SCR[c * RP + r] = plaq_canon(g, r, c, order);
+                }
+                ex.lsync();
+                for (int t = ex.tid(); t < T; t += ex.nt()) {
+                    const int gi = t / R, rr = t - gi * R;
+                    UA[t] = SCR[(4 * gi) * RP + rr];
+#pragma unroll 1
+                    for (int k = 0; k < 2; ++k) {
+                        const double p = SCR[(4 * gi + 1 + k) * RP + rr];
+                        double sp, cp;
+                        sincos_fast(p, sp, cp);
+                        const int i = (2 * gi + k) * R + rr;
+                        CS[i] = cp; CS[V / 2 + i] = sp;
+                        if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
+                    }
+                }
+                return;
+            }
+        }
+#endif
         if (fine_tasks()) {                                  // one plaquette per task: T active, then 2T frozen
             for (int t = ex.tid(); t < 3 * T; t += ex.nt()) {
                 const int kind = t / T, tt = t - kind * T;
