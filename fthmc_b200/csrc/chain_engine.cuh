@@ -406,6 +406,9 @@ FT_HD double rcp_ge1(double d) {
 #ifndef FT_CL_PLANES
 #define FT_CL_PLANES 1
 #endif
+#ifndef FT_CL_SAVED_U
+#define FT_CL_SAVED_U 1
+#endif
 // 1 + e^x for the SiLU passes (issue bound: every fp64 operation counts): exp_fast with the argument reduction against ONE
 // constant (the fma is exact; the error n * |C - ln2/64| <= 8.7e-19 n stays below 1 ulp of e^x for |x| < 3.5 and grows to
 // ~6 ulp at |x| = 20 -- sigma(z) is then within 2e-9 of 0 or 1), and the "+ 1" folded into the last fma's addend so that it
@@ -601,7 +604,9 @@ FT_HD size_t engine_smem_doubles(int L0, int L1, bool flow = true, int nr = 1) {
 // Training mode (weight gradients) appends the activations themselves: h1 [plane A], h2 [plane B].
 FT_HD size_t engine_layer_ws_doubles(int L0, int L1, int nr = 1, bool train = false) {
     size_t V = (size_t)L0 * L1 / nr;
-    return (train ? 2 : 1) * (plane_a_doubles(V) + plane_b_doubles(V)) + V + 3 * (V / 4);
+    // cluster mode appends the raw active plaquettes [V/4]: the adjoint reads them back instead of re-forming each from four
+    // links, most of which it would have to fetch through distributed shared memory
+    return (train ? 2 : 1) * (plane_a_doubles(V) + plane_b_doubles(V)) + V + 3 * (V / 4) + (nr > 1 ? V / 4 : 0);
 }
 // per-chain global workspace (doubles): momenta, x0, y0 (whole lattice), then for every rank nlayers layer blocks
 FT_HD size_t engine_ws_doubles(int L0, int L1, int nlayers, int nr = 1, bool train = false) {
@@ -1369,7 +1374,10 @@ struct Engine {
             const double fx1 = mixture_fwd_sc(sh, ch, es0, es1, conv);
             const double newp = mod_2pi(fx1 + out[2], conv);
             const double delta = newp - u;
-            if (sv) { sv[t] = xo; so[t] = out[0]; so[T + t] = out[1]; }
+            if (sv) {
+                sv[t] = xo; so[t] = out[0]; so[T + t] = out[1];
+                if constexpr (CL) { if (nr > 1) sv[T + t] = u; }   // (cluster mode) the active plaquette, for ph_outgrad_saved
+            }
             *xl = mod_2pi((g.mu == 0 ? delta : -delta) + xo, conv);
             if (want_logJ) {
                 const double c2 = ch * ch, s2 = sh * sh;
@@ -1567,7 +1575,11 @@ struct Engine {
     // the active sites:  OUT <- (s1bar, s2bar, tbar),  UA <- Pbar(active)
     // On entry OUT holds (s_1, s_2, pre-update active links) of this layer, prefetched from the layer block; every
     // task reads its own three entries before overwriting them.
-    FT_PHASE void ph_outgrad(const LayerGeom g) {
+    FT_PHASE void ph_outgrad(const LayerGeom g) { outgrad_impl<false>(g, nullptr); }
+    // cluster mode: the active plaquette comes from the layer block (ua: V/4 doubles behind the saved links) -- with the
+    // pre-update link restored it is bit for bit the value the forward sweep formed
+    FT_PHASE void ph_outgrad_saved(const LayerGeom g, const double* ua) { outgrad_impl<true>(g, ua); }
+    template <bool SAVED> FT_HD void outgrad_impl(const LayerGeom g, const double* ua) {
         double* OUT = sm(oOUT); double* UA = sm(oUA);
         const int T = g.G * g.R, R = g.R, order = pr.conv;
         const double mwl = mw;
@@ -1579,7 +1591,8 @@ struct Engine {
             *xat(oX, g.mu, n0, n1) = OUT[2 * T + t];
             double gl = *xat(oGR, g.mu, n0, n1);
             double db = g.mu == 0 ? gl : -gl;                 // delta-bar
-            double u = plaq(oX, n0, n1, order);
+            double u;
+            if constexpr (SAVED) u = ua[t]; else u = plaq(oX, n0, n1, order);
             double s0 = OUT[t], s1 = OUT[T + t];
             double c, s;
             sincos_fast(0.5 * u, s, c);
@@ -2149,7 +2162,7 @@ struct Engine {
     template <bool TRAIN = false> FT_HD void layer_adjoint(int l) {
         if (TRAIN) { layer_adjoint_train(l); return; }
         LayerGeom g = geom(l);
-        FT_T(PF_OUTGRAD, ph_outgrad(g);            // waits for so/sv(l)
+        FT_T(PF_OUTGRAD, if (CL && FT_CL_SAVED_U && nr > 1) ph_outgrad_saved(g, wsSV(l) + VQ); else ph_outgrad(g);   // waits for so/sv(l)
              wait_bar(zbar(l)); wait_bar(BAR_W);   // d2(l), Wt(l) have landed
              ex.lsync();                           // (restored links / GR reads cross ranks, but are ordered by the cluster barriers around)
              advance_bar(zbar(l)); advance_bar(BAR_W); advance_bar(BAR_SO));
