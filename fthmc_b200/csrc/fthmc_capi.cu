@@ -405,7 +405,8 @@ __device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1
 // grid (nc, B), thread-block cluster (nc, 1, 1): the nc CTAs of a cluster split the rows of ONE chain, reduce in fp64,
 // hand their partial sums to rank 0 through distributed shared memory, and rank 0 writes the finished per-chain value.
 // One launch, no global scratch, deterministic summation order.  nc == 1 (large batches): a plain one-CTA-per-chain scan.
-template <typename T, bool VEC, int WHAT, int ORDER>
+// PIPE (with VEC): the software-pipelined scan for FEW LARGE chains (clusters; low occupancy), see below
+template <typename T, bool VEC, int WHAT, int ORDER, bool PIPE = false>
 __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links, int L0, int L1, int rows,
                                                    double beta, int rounded, T* __restrict__ out) {
     constexpr int what = WHAT, order = ORDER;                // compile time: a run-time switch evaluates every branch's arithmetic
@@ -422,14 +423,51 @@ __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links
         constexpr int N = Vec<T>::N;
         const int W = L1 / N, dr = (int)blockDim.x / W, dc = (int)blockDim.x - dr * W, nr = r1 - r0;
         int row = (int)threadIdx.x / W, col = (int)threadIdx.x - row * W;
-        while (row < nr) {
-            T p[N];
-            plaq_vec<T>(f, L0, L1, r0 + row, col * N, order, p);
+        if constexpr (PIPE) {
+            // Software pipeline: the link vectors of steps k + 1 and k + 2 are loaded (raw, no arithmetic on them: an add would
+            // stall the in-order warp until they land) BEFORE the cos / wrap of step k.  The compiler does not move loads across
+            // the divergent slow-path branches of those functions on its own, and with one step in flight per warp a scan of a
+            // few large lattices ran at HBM latency (L = 1024, 48 chains: ~2000 cycles per step and warp; pipelined +24 % / +14 %
+            // for action / charge).  64 registers instead of 40: with many chains (one CTA each, full occupancy) the plain loop
+            // below is the faster one (L = 256: -9 % / -15 % pipelined), so the launcher picks this form for clusters only.
+            using VT = typename Vec<T>::type;
+            struct Raw { VT t0, t1, t1p; T t0n; };
+            auto fetch = [&](int rw, int cl, Raw& q) {
+                const int n0 = r0 + rw, n1 = cl * N, n0p = n0 + 1 == L0 ? 0 : n0 + 1, n1n = n1 + N == L1 ? 0 : n1 + N;
+                q.t0 = *reinterpret_cast<const VT*>(f + (size_t)n0 * L1 + n1);
+                q.t0n = f[(size_t)n0 * L1 + n1n];
+                q.t1 = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0) * L1 + n1);
+                q.t1p = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0p) * L1 + n1);
+            };
+            auto step = [&]() { col += dc; row += dr; if (col >= W) { col -= W; ++row; } };
+            Raw qa, qb, qc;
+            bool va = row < nr, vb, vc;
+            if (va) fetch(row, col, qa);
+            step(); vb = row < nr;
+            if (vb) fetch(row, col, qb);
+            while (va) {
+                step(); vc = row < nr;
+                if (vc) fetch(row, col, qc);
+                __align__(16) T t0[N + 1], t1[N], t1p[N];
+                *reinterpret_cast<VT*>(t0) = qa.t0; t0[N] = qa.t0n;
+                *reinterpret_cast<VT*>(t1) = qa.t1; *reinterpret_cast<VT*>(t1p) = qa.t1p;
 #pragma unroll
-            for (int j = 0; j < N; ++j)
-                acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
-            col += dc; row += dr;
-            if (col >= W) { col -= W; ++row; }
+                for (int j = 0; j < N; ++j) {
+                    const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+                    acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+                }
+                qa = qb; qb = qc; va = vb; vb = vc;
+            }
+        } else {
+            while (row < nr) {
+                T p[N];
+                plaq_vec<T>(f, L0, L1, r0 + row, col * N, order, p);
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
+                col += dc; row += dr;
+                if (col >= W) { col -= W; ++row; }
+            }
         }
     } else {
         for (int i = threadIdx.x; i < (r1 - r0) * L1; i += blockDim.x) {
@@ -649,6 +687,57 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
             const T s = S[(rr + 1) * L1 + n1];
             o[(r0 + rr) * L1 + n1] = beta * (s - S[(rr + 1) * L1 + n1m]);
             o[(L0 + r0 + rr) * L1 + n1] = beta * (S[rr * L1 + n1] - s);
+        }
+    }
+}
+
+// grid (row chunks x column chunks, B): the tile rows [r0,r1) x columns [c0,c0+cw) of one chain; sin P of rows r0-1..r1-1 and
+// columns c0-1..c0+cw-1 staged in shared memory (one sine per site, plus the halo row and column).
+// The column-chunked form of k_force's vector path (very wide lattices only: whole rows with the plain pitch are the faster
+// layout wherever they fit, L = 32: 92 % against 84 % of HBM); needs L1 % Vec<T>::N == 0 and cw % Vec<T>::N == 0.  The staged tile has pitch cw + N: an N-wide left pad keeps the vector stores aligned, its last slot
+// holds the halo column c0 - 1.  Very wide lattices are cut into column chunks (cw < L1) so that a tile of ~24 rows still
+// fits ~26 KB and eight CTAs stay on an SM (whole rows of L1 = 1024 allowed 7 rows per 64 KB tile: three CTAs per SM, 62 % of HBM).
+template <typename T>
+__global__ void __launch_bounds__(256) k_force_tiled(const T* __restrict__ links, int L0, int L1, int rows, int cw, T beta, int order, T* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* S = reinterpret_cast<T*>(smem_raw);                  // (rows+1) x pitch, row 0 is r0-1
+    const int b = blockIdx.y, ncol = L1 / cw, cr = (int)blockIdx.x / ncol, c = (int)blockIdx.x - cr * ncol;
+    const T* f = links + (size_t)b * 2 * L0 * L1;
+    T* o = out + (size_t)b * 2 * L0 * L1;
+    const int r0 = cr * rows, r1 = min(L0, r0 + rows), nr = r1 - r0, c0 = c * cw;
+    {
+        constexpr int N = Vec<T>::N;
+        using VT = typename Vec<T>::type;
+        const int W = cw / N, SP = cw + N, dr = (int)blockDim.x / W, dc = (int)blockDim.x - dr * W;
+        const int row0 = (int)threadIdx.x / W, col0 = (int)threadIdx.x - row0 * W;
+        for (int row = row0, col = col0; row < nr + 1;) {
+            int n0 = r0 - 1 + row; if (n0 < 0) n0 += L0;
+            __align__(16) T p[N];
+            plaq_vec<T>(f, L0, L1, n0, c0 + col * N, order, p);
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[j] = M<T>::sinv(p[j]);
+            *reinterpret_cast<VT*>(S + row * SP + N + col * N) = *reinterpret_cast<const VT*>(p);
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
+        }
+        if (cw != L1)                                                            // the halo column c0 - 1 (whole rows: the row's own last column)
+            for (int row = threadIdx.x; row < nr + 1; row += blockDim.x) {
+                int n0 = r0 - 1 + row; if (n0 < 0) n0 += L0;
+                S[row * SP + N - 1] = M<T>::sinv(plaq_g(f, L0, L1, n0, c0 == 0 ? L1 - 1 : c0 - 1, order));
+            }
+        __syncthreads();
+        for (int row = row0, col = col0; row < nr;) {
+            const int n1 = col * N;
+            __align__(16) T s[N], su[N], f0[N], f1[N];
+            *reinterpret_cast<VT*>(s) = *reinterpret_cast<const VT*>(S + (row + 1) * SP + N + n1);
+            *reinterpret_cast<VT*>(su) = *reinterpret_cast<const VT*>(S + row * SP + N + n1);
+            T sl = S[(row + 1) * SP + N + (n1 == 0 && cw == L1 ? L1 - 1 : n1 - 1)];
+#pragma unroll
+            for (int j = 0; j < N; ++j) { f0[j] = beta * (s[j] - sl); f1[j] = beta * (su[j] - s[j]); sl = s[j]; }
+            *reinterpret_cast<VT*>(o + (size_t)(r0 + row) * L1 + c0 + n1) = *reinterpret_cast<const VT*>(f0);
+            *reinterpret_cast<VT*>(o + (size_t)(L0 + r0 + row) * L1 + c0 + n1) = *reinterpret_cast<const VT*>(f1);
+            col += dc; row += dr;
+            if (col >= W) { col -= W; ++row; }
         }
     }
 }
@@ -991,9 +1080,26 @@ static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta
         CK(cudaGetLastError());
         return 0;
     }
-    auto kern = vec ? k_action_topo<T, true, WHAT, ORDER> : k_action_topo<T, false, WHAT, ORDER>;
+    // (fp32 scans measured 5 % slower pipelined: four sites per vector already give their loop twice the bytes in flight)
+    auto kern = vec ? (nc > 1 && sizeof(T) == 8 ? k_action_topo<T, true, WHAT, ORDER, true> : k_action_topo<T, true, WHAT, ORDER>) : k_action_topo<T, false, WHAT, ORDER>;
     if (nc > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, beta, rounded, (T*)out));
+    // all clusters in one wave: a 16-CTA cluster needs 16 free slots inside ONE GPC, and fewer of those exist than the
+    // CTA slots of the device suggest (45 at once on a B200, 104 clusters of 8) -- three stragglers of 48 chains cost more
+    // than the lower occupancy of the next smaller cluster size (L = 1024, 48 chains: +4 %)
+    static int max_active[2][5] = { { 0, 0, 0, 0, 0 }, { 0, 0, 0, 0, 0 } };   // [vec][log2 nc], this instantiation's kernels
+    while (nc > 1) {
+        int lg = 0; while ((1 << lg) < nc) ++lg;
+        int& mc = max_active[vec ? 1 : 0][lg];
+        if (mc == 0) {
+            cfg.gridDim = dim3(nc, B); at[0].val.clusterDim.x = nc;
+            if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc < 1) { mc = 1 << 30; (void)cudaGetLastError(); }
+        }
+        if (B <= mc) break;
+        nc /= 2;
+    }
+    const int rows2 = (L0 + nc - 1) / nc;
+    cfg.gridDim = dim3(nc, B); at[0].val.clusterDim.x = nc;
+    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows2, beta, rounded, (T*)out));
     g_launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -1051,31 +1157,41 @@ extern "C" int fthmc_force(const void* links, int B, int L0, int L1, double beta
     int rc = check_stencil(links, force_out, B, L0, L1, dtype); if (rc) return rc;
     if (order != 0 && order != 1) return fail(FTHMC_E_ARG, "order must be 0 or 1");
     const size_t es = dtype == FTHMC_F64 ? 8 : 4;
-    // tile height: about 24 KB of sin(P) per CTA keeps eight CTAs (all 2048 threads) on an SM, so that the load / sine
-    // half of one tile overlaps the store half of others; very wide rows take what 64 KB hold (>= 1 halo row per 15)
-    const int rows_max = (int)((64 * 1024) / (es * L1)) - 1;
+    const int vw = dtype == FTHMC_F64 ? Vec<double>::N : Vec<float>::N;
+    const bool vec = L1 % vw == 0 && ((uintptr_t)links & 15) == 0 && ((uintptr_t)force_out & 15) == 0;
+    // tile: about 24 KB of sin(P) per CTA keeps eight CTAs (all 2048 threads) on an SM, so that the load / sine half of one
+    // tile overlaps the store half of others.  Rows of 4 KB and more are cut into 1 KB column chunks (vector path), so that
+    // a tile still has ~22 rows per halo row; without the vector path very wide rows take what 64 KB hold.
+    int cw = L1;
+    if (vec && (size_t)L1 * es >= 4096 && L1 % (int)(1024 / es) == 0) cw = (int)(1024 / es);
+    const size_t pitch = (size_t)(cw + (cw != L1 ? vw : 0)) * es;
+    const int rows_max = (int)((64 * 1024) / pitch) - 1;
     if (rows_max < 1) return fail(FTHMC_E_LATTICE, "L1 too large for the force tile");
-    int rows = (int)((24 * 1024) / (es * L1)) - 1;
+    int rows = (int)((24 * 1024) / pitch) - 1;
     if (rows < 15) rows = rows_max < 15 ? rows_max : 15;
     if (rows > L0) rows = L0;
     rows = (L0 + (L0 + rows - 1) / rows - 1) / ((L0 + rows - 1) / rows);          // equal tiles
     // small batches of large lattices: shorter tiles until the grid fills the device
-    while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) < 4 * nsm()) rows = (rows + 1) / 2;
-    const int nchunk = (L0 + rows - 1) / rows;
-    const size_t smem = (size_t)(rows + 1) * L1 * es;
-    const int vw = dtype == FTHMC_F64 ? Vec<double>::N : Vec<float>::N;
-    const bool vec = L1 % vw == 0 && ((uintptr_t)links & 15) == 0 && ((uintptr_t)force_out & 15) == 0;
+    while (rows > 8 && (long long)B * ((L0 + rows - 1) / rows) * (L1 / cw) < 4 * nsm()) rows = (rows + 1) / 2;
+    const int nchunk = ((L0 + rows - 1) / rows) * (L1 / cw);
+    const size_t smem = (size_t)(rows + 1) * pitch;
     const size_t cs = (size_t)2 * L0 * L1 * es;
     return for_batch_chunks(B, [&](int b0, int nb) -> int {
         const char* in = (const char*)links + b0 * cs; char* fo = (char*)force_out + b0 * cs;
         if (dtype == FTHMC_F64) {
-            auto kern = vec ? k_force<double, true> : k_force<double, false>;
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const double*)in, L0, L1, rows, beta, order, (double*)fo);
+            if (cw != L1) k_force_tiled<double><<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const double*)in, L0, L1, rows, cw, beta, order, (double*)fo);
+            else {
+                auto kern = vec ? k_force<double, true> : k_force<double, false>;
+                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const double*)in, L0, L1, rows, beta, order, (double*)fo);
+            }
         } else {
-            auto kern = vec ? k_force<float, true> : k_force<float, false>;
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const float*)in, L0, L1, rows, (float)beta, order, (float*)fo);
+            if (cw != L1) k_force_tiled<float><<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const float*)in, L0, L1, rows, cw, (float)beta, order, (float*)fo);
+            else {
+                auto kern = vec ? k_force<float, true> : k_force<float, false>;
+                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                kern<<<dim3(nchunk, nb), 256, smem, (cudaStream_t)stream>>>((const float*)in, L0, L1, rows, (float)beta, order, (float*)fo);
+            }
         }
         g_launches++;
         CK(cudaGetLastError());
