@@ -44,7 +44,9 @@ def test_plain_pointwise_golden(golden):
     assert float(ft.action(P, z)) / (-P.beta * P.volume) == 1.0 and float(ft.topocharge(z)) == 0.0
 
 
-@pytest.mark.parametrize("shape", [(1, 4, 4), (7, 8, 12), (5, 32, 32), (3, 64, 64), (2, 256, 128)])
+# (the last two shapes have rows of >= 4 KB: the column-chunked force tiles, k_force_tiled; few large chains also take the
+# cluster-per-chain, software-pipelined form of the reduction scans)
+@pytest.mark.parametrize("shape", [(1, 4, 4), (7, 8, 12), (5, 32, 32), (3, 64, 64), (2, 256, 128), (2, 24, 512), (1, 64, 1024)])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_stencils_vs_oracle(shape, dtype):
     B, L0, L1 = shape
