@@ -1048,7 +1048,6 @@ template <typename T, int WHAT, int ORDER>
 static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta, int rounded, void* out, cudaStream_t st) {
     int nc = 1;
     while (nc < 16 && (long long)B * nc < 4 * nsm() && 2 * nc <= L0 && (long long)(L0 / (2 * nc)) * L1 >= 1024) nc *= 2;
-    const int rows = (L0 + nc - 1) / nc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1097,9 +1096,9 @@ static int reduce_launch_t(const void* links, int B, int L0, int L1, double beta
         if (B <= mc) break;
         nc /= 2;
     }
-    const int rows2 = (L0 + nc - 1) / nc;
+    const int rows = (L0 + nc - 1) / nc;
     cfg.gridDim = dim3(nc, B); at[0].val.clusterDim.x = nc;
-    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows2, beta, rounded, (T*)out));
+    CK(cudaLaunchKernelEx(&cfg, kern, (const T*)links, L0, L1, rows, beta, rounded, (T*)out));
     g_launches += 1;
     CK(cudaGetLastError());
     return 0;
