@@ -351,9 +351,22 @@ static __device__ __forceinline__ float cosf_pi(float x) {
     p = fmaf(p, s, 1.0f / 24.0f); p = fmaf(p, s, -0.5f); p = fmaf(p, s, 1.0f);
     return __int_as_float(__float_as_int(p) ^ (__float_as_int(t) << 31));
 }
+// sinf for the fp32 force: the same reduction, sin x = (-1)^n sin r, odd Taylor polynomial to r^11 (truncation 6e-8 at pi/2)
+static __device__ __forceinline__ float sinf_pi(float x) {
+    if (!(fabsf(x) < 32768.0f)) return sinf(x);
+    const float t = fmaf(x, 0.318309886f, 12582912.0f);
+    const float n = t - 12582912.0f;
+    float r = fmaf(n, -3.14159274101257324f, x);
+    r = fmaf(n, 8.74227765734758577e-8f, r);
+    const float s = r * r;
+    float p = -1.0f / 39916800.0f;
+    p = fmaf(p, s, 1.0f / 362880.0f); p = fmaf(p, s, -1.0f / 5040.0f); p = fmaf(p, s, 1.0f / 120.0f); p = fmaf(p, s, -1.0f / 6.0f);
+    p = fmaf(r * s, p, r);
+    return __int_as_float(__float_as_int(p) ^ (__float_as_int(t) << 31));
+}
 template <> struct M<float> {
     static __device__ float cosv(float x) { return FT_FAST_TRIG ? cosf_pi(x) : cosf(x); }
-    static __device__ float sinv(float x) { return sinf(x); }
+    static __device__ float sinv(float x) { return FT_FAST_TRIG ? sinf_pi(x) : sinf(x); }
     static __device__ float floorv(float x) { return floorf(x); }
     static __device__ float modv(float x, float y) { return fmodf(x, y); }
 };

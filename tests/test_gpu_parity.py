@@ -84,6 +84,14 @@ def test_reduction_stencils_large_batch(shape, dtype):
     assert relerr(ft.u1_action(2.5, xd).double().cpu().numpy(), ref) < tol
     # hmc_2dU1's plaquette term order differs from u1_plaq's in the last ulp only
     assert relerr(ft.action(P, xd).double().cpu().numpy(), ref) < (1e-9 if dtype == torch.float64 else 2e-5)
+    # the force of the whole batch (large batches of small fp32 chains go two chains per CTA), against the closed form
+    # hmc_2dU1.py:104-111 differentiates: F0 = beta [sin P(n) - sin P(n - e1)], F1 = beta [sin P(n - e0) - sin P(n)]
+    sp = torch.sin(x64[:, 0] - x64[:, 1] - torch.roll(x64[:, 0], -1, 2) + torch.roll(x64[:, 1], -1, 1))
+    fref = 2.5 * torch.stack([sp - torch.roll(sp, 1, 2), torch.roll(sp, 1, 1) - sp], dim=1)
+    assert relerr(fref[:3].numpy(), torch.stack([O.force_closed_form(2.5, x64[b]) for b in range(3)]).numpy()) < 1e-12
+    assert relerr(ft.force(P, xd).double().cpu().numpy(), fref.numpy()) < (REL if dtype == torch.float64 else 1e-4)
+    odd = ft.force(P, xd[:2501]).double().cpu().numpy()          # an odd number of chains: the last CTA holds one
+    assert relerr(odd, fref[:2501].numpy()) < (REL if dtype == torch.float64 else 1e-4)
     if dtype == torch.float64:
         assert np.max(np.abs(ft.topo_charge(xd).cpu().numpy() - O.topo_charge(x64).numpy())) < 1e-9
         q = ft.topocharge(xd).cpu().numpy()
