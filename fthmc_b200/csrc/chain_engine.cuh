@@ -2449,6 +2449,52 @@ FT_HD void leapfrog_resident(Engine<E>& en, double dt, int nstep, double* P, For
     }
 }
 
+// the MD steps of leapfrog_plain_fused for threads that own at most NS sites each (k_chain_plain): see there
+template <class E, int NS>
+FT_HD void plain_md_steps(Engine<E>& en, double beta, double dt, int nstep) {
+    auto& ex = en.ex;
+    const int L0 = en.L0, L1 = en.L1, LP = en.LP, V = en.V, X1 = L0 * LP;
+    const double hdt = 0.5 * dt;
+    double* X = en.sm(en.oX);
+    double* P = en.sm(en.oGR);
+    double* S = en.sm(en.oS);
+    int xb[NS], sb[NS], dc[NS], dr[NS], sl[NS], su[NS];   // x0 offset, S offset, offsets of the n1+1 / n0+1 / n1-1 / n0-1 neighbours
+    bool ok[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int i = ex.tid() + k * ex.nt();
+        ok[k] = i < V;
+        const int n0 = ok[k] ? i / L1 : 0, n1 = ok[k] ? i - n0 * L1 : 0;
+        xb[k] = n0 * LP + n1; sb[k] = n0 * L1 + n1;
+        dc[k] = n1 + 1 == L1 ? 1 - L1 : 1;
+        dr[k] = n0 + 1 == L0 ? -(L0 - 1) * LP : LP;
+        sl[k] = n1 == 0 ? L1 - 1 : -1;
+        su[k] = n0 == 0 ? V - L1 : -L1;
+    }
+    for (int st = 0; st < nstep; ++st) {
+        const double step = st == nstep - 1 ? hdt : dt;
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (ok[k]) {
+                const double a = X[xb[k]], b = X[X1 + xb[k] + dr[k]], c = X[xb[k] + dc[k]], d = X[X1 + xb[k]];
+                S[sb[k]] = sin_force(((a - d) - c) + b);
+            }
+        ex.sync();
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (ok[k]) {
+                const double sv = S[sb[k]];
+                const double f0 = beta * (sv - S[sb[k] + sl[k]]), f1 = beta * (S[sb[k] + su[k]] - sv);
+                const int i0 = xb[k], i1 = X1 + xb[k];
+                const double p0 = P[i0] + (-dt) * f0, p1 = P[i1] + (-dt) * f1;
+                P[i0] = p0; P[i1] = p1;
+                X[i0] = X[i0] + step * p0;
+                X[i1] = X[i1] + step * p1;
+            }
+        ex.sync();
+    }
+}
+
 // Plain-HMC leapfrog (hmc_2dU1.py:132-141) with everything on chip: the momenta live in the (otherwise unused) gradient
 // plane, and every MD step is two phases -- S = sin(plaquette), then per SITE the force of its two links from S, the
 // momentum update and the position update -- with division-free site stepping.  Same operations in the same order as
@@ -2472,6 +2518,23 @@ FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep
         X[row * LP + n1] = X[row * LP + n1] + hdt * p;
     }
     ex.sync();
+    if constexpr (FAST) {
+        // k_chain_plain, up to four sites per thread (L <= 32 with 256 threads): the kernel is ISSUE bound (ncu: issue slots
+        // 70 % busy, fp64 pipe 25 %) and most of what it issued was the address arithmetic of the sites -- which are the same
+        // in every MD step of every chain.  Offsets and wrap flags of a thread's sites are formed once; a step is then
+        // loads, the plaquette, the sine, and the updates.  Same operands and operations as the loops below: bit-identical.
+        if (V <= 4 * ex.nt()) {
+            if (V <= ex.nt()) plain_md_steps<E, 1>(en, beta, dt, nstep);
+            else if (V <= 2 * ex.nt()) plain_md_steps<E, 2>(en, beta, dt, nstep);
+            else plain_md_steps<E, 4>(en, beta, dt, nstep);
+            for (int i = ex.tid(), row = s0, n1 = s1; i < 2 * V; i += ex.nt(), row += d0, n1 += d1) {
+                if (n1 >= L1) { n1 -= L1; ++row; }
+                Pg[i] = P[row * LP + n1];
+            }
+            ex.sync();
+            return;
+        }
+    }
     for (int st = 0; st < nstep; ++st) {
         const double step = st == nstep - 1 ? hdt : dt;
         for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
