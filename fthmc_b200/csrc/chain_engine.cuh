@@ -130,6 +130,13 @@ FT_HD double regularize1(double f) {
     double g = (f - PI_D) / TWO_PI_D;
     return TWO_PI_D * (g - floor(g) - 0.5);
 }
+// The same value, bit for bit, without the division routine (k_chain_plain): with C = RN(1 / 2pi), q0 = RN(a C) is a faithful
+// quotient, r = a - q0 * 2pi is exact in one fma, and RN(q0 + r C) is the correctly rounded a / 2pi (Markstein's theorem;
+// checked against the division on 4e8 random arguments).  Non-finite arguments give NaN either way.
+FT_HD double regularize1_fast(double f) {
+    const double a = f - PI_D, q0 = a * 0.15915494309189535, r = fma(-q0, TWO_PI_D, a), g = fma(r, 0.15915494309189535, q0);
+    return TWO_PI_D * (g - floor(g) - 0.5);
+}
 
 // e^x with ~1 ulp error for |x| <= 708 (finite and monotone-saturated beyond): x = (64 k + j) ln2/64 + r with |r| <= ln2/128, e^x = 2^k * 2^(j/64) * e^r.
 // 2^(j/64) comes from a 64-entry table (on the device: 512 bytes of shared memory), the power of two goes into its
@@ -2562,6 +2569,43 @@ FT_HD void leapfrog_plain_fused(Engine<E>& en, double beta, double dt, int nstep
     ex.sync();
 }
 
+// The same leapfrog with the momenta already in, and staying in, the gradient plane (hmc_trajectory_plain): no copies
+template <class E>
+FT_HD void leapfrog_plain_resident(Engine<E>& en, double beta, double dt, int nstep) {
+    auto& ex = en.ex;
+    const int L0 = en.L0, L1 = en.L1, LP = en.LP, V = en.V;
+    const double hdt = 0.5 * dt;
+    double* X = en.sm(en.oX);
+    double* P = en.sm(en.oGR);
+    double* S = en.sm(en.oS);
+    en.for_links([&](int si, int) { X[si] = X[si] + hdt * P[si]; });
+    ex.sync();
+    if (V <= ex.nt()) { plain_md_steps<E, 1>(en, beta, dt, nstep); return; }
+    if (V <= 2 * ex.nt()) { plain_md_steps<E, 2>(en, beta, dt, nstep); return; }
+    if (V <= 4 * ex.nt()) { plain_md_steps<E, 4>(en, beta, dt, nstep); return; }
+    const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1, s0 = ex.tid() / L1, s1 = ex.tid() - s0 * L1;
+    for (int st = 0; st < nstep; ++st) {
+        const double step = st == nstep - 1 ? hdt : dt;
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            S[i] = sin_force(en.plaq(en.oX, n0, n1, 1));
+        }
+        ex.sync();
+        for (int i = ex.tid(), n0 = s0, n1 = s1; i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            const int n0m = n0 == 0 ? L0 - 1 : n0 - 1, n1m = n1 == 0 ? L1 - 1 : n1 - 1;
+            const double sv = S[i];
+            const double f0 = beta * (sv - S[n0 * L1 + n1m]), f1 = beta * (S[n0m * L1 + n1] - sv);
+            const int i0 = n0 * LP + n1, i1 = (L0 + n0) * LP + n1;
+            const double p0 = P[i0] + (-dt) * f0, p1 = P[i1] + (-dt) * f1;
+            P[i0] = p0; P[i1] = p1;
+            X[i0] = X[i0] + step * p0;
+            X[i1] = X[i1] + step * p1;
+        }
+        ex.sync();
+    }
+}
+
 // FT-HMC trajectory (ipynb/ft_hmc.py:420-435)
 template <class E>
 FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
@@ -2610,6 +2654,85 @@ FT_HD void ft_hmc_trajectory(Engine<E>& en, const TrajIO& io) {
         if (io.out_expmdH) *io.out_expmdH = e;
         if (io.out_acc) *io.out_acc = acc ? 1 : 0;
         if (io.out_plaq) *io.out_plaq = (acc ? s1_plain : s0_plain) / (-io.beta * V);
+        if (io.out_Q) *io.out_Q = q;
+        if (io.out_h0) *io.out_h0 = h0;
+        if (io.out_h1) *io.out_h1 = h1;
+    }
+    ex.sync();
+}
+
+// Plain HMC trajectory of k_chain_plain (single-CTA chains): the program of hmc_trajectory below with everything that is not
+// the reference's arithmetic taken off the path.  A trajectory at nstep = 10 spent 58 % of its time OUTSIDE the MD steps
+// (profiles/r2_microopt_ab.txt (21)): the momenta made five trips through the global workspace (drawn, summed, copied in,
+// copied out, summed), the Box-Muller angle, the two actions and the wraps went through library routines with slow paths.
+// Here the momenta are drawn into, and stay in, the shared-memory gradient plane; the angle uses sincos_fast, the actions
+// cos_fast, the wraps the division-free regularize1_fast (bit-identical).  Same summation orders as hmc_trajectory.
+template <class E>
+FT_HD void hmc_trajectory_plain(Engine<E>& en, const TrajIO& io) {
+    auto& ex = en.ex;
+    const int V = en.Vg, L1 = en.L1, LP = en.LP;
+    double* X = en.sm(en.oX);
+    double* P = en.sm(en.oGR);
+    auto action = [&]() {
+        double acc = 0.0;
+        const int d0 = ex.nt() / L1, d1 = ex.nt() - d0 * L1;
+        int n0 = ex.tid() / L1, n1 = ex.tid() - n0 * L1;
+        for (int i = ex.tid(); i < V; i += ex.nt(), n0 += d0, n1 += d1) {
+            if (n1 >= L1) { n1 -= L1; ++n0; }
+            acc += cos_fast(en.plaq(en.oX, n0, n1, 1));
+        }
+        return -io.beta * ex.sum(acc);
+    };
+    if (io.first) en.load_field(en.oX, io.field_in);
+    ex.sync();
+    en.for_links([&](int si, int gi) { en.wsX0[gi] = X[si]; });   // the trajectory's start field, restored on reject
+    if (io.p_in) en.for_links([&](int si, int gi) { P[si] = io.p_in[gi]; });
+    else {
+        Philox ph{ (uint32_t)io.seed, (uint32_t)(io.seed >> 32) };
+        for (int j = ex.tid(); j < V; j += ex.nt()) {             // pair j = links 2j, 2j+1 of the (2, L0, L1) layout (same row: L1 is even)
+            const int row = (2 * j) / L1, n1 = 2 * j - row * L1;
+            uint32_t r[4];
+            ph.gen((uint32_t)j, (uint32_t)io.traj, (uint32_t)io.chain, (uint32_t)(io.chain >> 32) ^ 0x5EEDu, r);
+            const double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincos_fast(TWO_PI_D * u2, sn, cs);
+            P[row * LP + n1] = rad * cs; P[row * LP + n1 + 1] = rad * sn;
+        }
+    }
+    ex.sync();
+    double k0 = 0.0;
+    en.for_links([&](int si, int) { k0 += P[si] * P[si]; });
+    k0 = ex.sum(k0);
+    const double s0 = action();
+    const double h0 = s0 + 0.5 * k0;
+    leapfrog_plain_resident(en, io.beta, io.dt, io.nstep);
+    en.for_links([&](int si, int) { X[si] = regularize1_fast(X[si]); });
+    ex.sync();
+    double k1 = 0.0;
+    en.for_links([&](int si, int) { k1 += P[si] * P[si]; });
+    k1 = ex.sum(k1);
+    const double s1 = action();
+    const double h1 = s1 + 0.5 * k1;
+    const double u = io.u_in ? *io.u_in : philox_uniform(io);
+    const double dH = h1 - h0;
+    const double e = exp(-dH);
+    const bool acc = u < e;
+    if (io.p_out) en.for_links([&](int si, int gi) { io.p_out[gi] = P[si]; });
+    if (!acc) {
+        ex.sync();
+        en.for_links([&](int si, int gi) { X[si] = en.wsX0[gi]; });   // newx = x (bit-identical input)
+    }
+    ex.sync();
+    double qs = 0.0;
+    for (int i = ex.tid(); i < V; i += ex.nt()) { int n0, n1; en.site_map(i, n0, n1); qs += regularize1_fast(en.plaq(en.oX, n0, n1, 1)); }
+    const double q = floor(0.1 + ex.sum(qs) / TWO_PI_D);
+    if (io.last) en.store_field(io.field_out, en.oX);
+    if (ex.tid() == 0) {
+        if (io.out_dH) *io.out_dH = dH;
+        if (io.out_expmdH) *io.out_expmdH = e;
+        if (io.out_acc) *io.out_acc = acc ? 1 : 0;
+        if (io.out_plaq) *io.out_plaq = (acc ? s1 : s0) / (-io.beta * V);
         if (io.out_Q) *io.out_Q = q;
         if (io.out_h0) *io.out_h0 = h0;
         if (io.out_h1) *io.out_h1 = h1;

@@ -173,7 +173,7 @@ FT_HD void run_chain_plain(Engine<E>& en, const ChainArgs& a, int b) {
         io.out_Q = a.topo ? a.topo + row : nullptr;
         io.out_h0 = nullptr; io.out_h1 = nullptr;
         io.first = t == 0; io.last = t == nt - 1;
-        hmc_trajectory<E, true>(en, io);
+        if constexpr (E::kCluster) hmc_trajectory<E, true>(en, io); else hmc_trajectory_plain(en, io);
     }
 }
 
