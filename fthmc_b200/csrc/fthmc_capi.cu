@@ -625,11 +625,14 @@ __global__ void __launch_bounds__(256, FT_TMA_MINB) k_action_topo_tma(const T* _
                 t0[N] = f[o0n[it]];
                 *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + o1[it]);
                 *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + o1p[it]);
+                T grp = (T)0;                                // (fp32: the four sites of a vector are summed in fp32, ONE conversion and fp64 add per vector)
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
-                    acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
+                    const T v = what == 0 ? M<T>::cosv(p) : (what == 1 ? regularize_t(p) : wrap_t(p));
+                    if constexpr (sizeof(T) == 4) grp += v; else acc += (double)v;
                 }
+                if constexpr (sizeof(T) == 4) acc += (double)grp;
             }
         }
 #pragma unroll
