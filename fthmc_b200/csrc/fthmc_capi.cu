@@ -335,6 +335,7 @@ template <> struct M<double> {
     static __device__ double cosv(double x) { return FT_FAST_TRIG ? fthmc::cos_fast(x) : cos(x); }
     static __device__ double sinv(double x) { return fthmc::sin_force(x); }
     static __device__ double floorv(double x) { return floor(x); }
+    static __device__ double fmav(double a, double b, double c) { return fma(a, b, c); }
     static __device__ double modv(double x, double y) { return fmod(x, y); }
 };
 // cosf for the fp32 action scan: x = n pi + r by a two-term reduction (fmaf), cos x = (-1)^n cos r, one even polynomial
@@ -368,6 +369,7 @@ template <> struct M<float> {
     static __device__ float cosv(float x) { return FT_FAST_TRIG ? cosf_pi(x) : cosf(x); }
     static __device__ float sinv(float x) { return FT_FAST_TRIG ? sinf_pi(x) : sinf(x); }
     static __device__ float floorv(float x) { return floorf(x); }
+    static __device__ float fmav(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ float modv(float x, float y) { return fmodf(x, y); }
 };
 
@@ -378,10 +380,14 @@ __device__ __forceinline__ T plaq_g(const T* __restrict__ f, int L0, int L1, int
     return order == 0 ? ((a + b) - c) - d : ((a - d) - c) + b;
 }
 
+// (f - pi) / 2pi without the division routine, bit for bit: with C = RN(1 / 2pi), q0 = RN(a C) is a faithful quotient, the
+// remainder a - q0 * 2pi is exact in one fma, and RN(q0 + r C) is the correctly rounded quotient (Markstein).  Checked
+// against the division exhaustively in fp32 (every finite float) and on 4e8 random arguments in fp64; a non-finite
+// argument gives NaN either way.  The charge scan and the elementwise wrap spend ~15 instructions less per value.
 template <typename T>
 __device__ __forceinline__ T regularize_t(T f) {
-    const T PI = (T)3.141592653589793, TP = (T)6.283185307179586;
-    T g = (f - PI) / TP;
+    const T PI = (T)3.141592653589793, TP = (T)6.283185307179586, C = (T)1 / TP;
+    const T a = f - PI, q0 = a * C, r = M<T>::fmav(-q0, TP, a), g = M<T>::fmav(r, C, q0);
     return TP * (g - M<T>::floorv(g) - (T)0.5);
 }
 
