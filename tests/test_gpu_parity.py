@@ -127,6 +127,21 @@ def test_action_on_unwrapped_links(scale, dtype):
     assert bool(torch.isnan(a[1])) and float(a[0]) == -2.5 * 1024 and float(a[2]) == -2.5 * 1024
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_regularize_is_bit_identical_without_the_division(dtype):
+    """hmc_2dU1.regularize (hmc_2dU1.py:127-129) divides by 2 pi; the kernels form that quotient by a multiply and two fused
+    multiply-adds (Markstein's correction), which must give the correctly rounded quotient, i.e. the SAME bits as torch's
+    division, on every argument: 2^24 random values per magnitude class, in the caller's precision."""
+    gen = torch.Generator().manual_seed(77)
+    for scale in (3.2, 40.0, 1.0e4, 1.0e-3):
+        f = ((torch.rand(4096, 2, 32, 64, generator=gen, dtype=torch.float64) * 2 - 1) * scale).to(dtype)
+        pi, tp = torch.tensor(np.pi, dtype=dtype), torch.tensor(2 * np.pi, dtype=dtype)
+        g = (f - pi) / tp
+        ref = tp * (g - torch.floor(g) - 0.5)
+        got = ft.regularize(f.cuda()).cpu()
+        assert torch.equal(got, ref), (dtype, scale, float((got - ref).abs().max()))
+
+
 # ---------------------------------------------------------------- plain HMC
 def test_plain_hmc_teacher_forced_golden(golden):
     g = golden("plain_L8")
