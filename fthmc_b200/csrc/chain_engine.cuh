@@ -226,8 +226,10 @@ __constant__ double c_trig[11] = FT_TRIG_CONSTS;
 __constant__ double c_cospi[15] = FT_COSPI_CONSTS;
 __constant__ double c_sinpi[10] = FT_SINPI_CONSTS;
 #endif
-FT_HD double cos_fast(double x) {
-    if (!(fabs(x) < 524288.0)) return cos(x);
+FT_HD double cos_core(double x);
+FT_HD double cos_fast(double x) { return fabs(x) < 524288.0 ? cos_core(x) : cos(x); }
+// the polynomial path alone, |x| < 2^19 (the scans test the sites of a vector together: one branch per vector)
+FT_HD double cos_core(double x) {
 #ifdef __CUDA_ARCH__
     const double* K = c_cospi;
 #else

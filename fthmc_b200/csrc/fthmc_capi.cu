@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_chain(const ChainArgs a) {
 template <typename T> struct M;
 template <> struct M<double> {
     static __device__ double cosv(double x) { return FT_FAST_TRIG ? fthmc::cos_fast(x) : cos(x); }
+    static __device__ double cos_core(double x) { return fthmc::cos_core(x); }
+    static __device__ bool cos_in_range(double x) { return fabs(x) < 524288.0; }
     static __device__ double sinv(double x) { return fthmc::sin_force(x); }
     static __device__ double floorv(double x) { return floor(x); }
     static __device__ double fmav(double a, double b, double c) { return fma(a, b, c); }
@@ -341,8 +343,7 @@ template <> struct M<double> {
 };
 // cosf for the fp32 action scan: x = n pi + r by a two-term reduction (fmaf), cos x = (-1)^n cos r, one even polynomial
 // (Taylor to r^12: truncation 6e-9 on |r| <= pi/2) -- 11 fp32 operations; |x| < 2^15, beyond that the library.
-static __device__ __forceinline__ float cosf_pi(float x) {
-    if (!(fabsf(x) < 32768.0f)) return cosf(x);
+static __device__ __forceinline__ float cosf_pi_core(float x) {
     const float t = fmaf(x, 0.318309886f, 12582912.0f);                        // n = rint(x / pi) in the low mantissa bits
     const float n = t - 12582912.0f;
     float r = fmaf(n, -3.14159274101257324f, x);
@@ -353,6 +354,7 @@ static __device__ __forceinline__ float cosf_pi(float x) {
     p = fmaf(p, s, 1.0f / 24.0f); p = fmaf(p, s, -0.5f); p = fmaf(p, s, 1.0f);
     return __int_as_float(__float_as_int(p) ^ (__float_as_int(t) << 31));
 }
+static __device__ __forceinline__ float cosf_pi(float x) { return fabsf(x) < 32768.0f ? cosf_pi_core(x) : cosf(x); }
 // sinf for the fp32 force: the same reduction, sin x = (-1)^n sin r, odd Taylor polynomial to r^11 (truncation 6e-8 at pi/2)
 static __device__ __forceinline__ float sinf_pi(float x) {
     if (!(fabsf(x) < 32768.0f)) return sinf(x);
@@ -368,6 +370,8 @@ static __device__ __forceinline__ float sinf_pi(float x) {
 }
 template <> struct M<float> {
     static __device__ float cosv(float x) { return FT_FAST_TRIG ? cosf_pi(x) : cosf(x); }
+    static __device__ float cos_core(float x) { return cosf_pi_core(x); }
+    static __device__ bool cos_in_range(float x) { return fabsf(x) < 32768.0f; }
     static __device__ float sinv(float x) { return FT_FAST_TRIG ? sinf_pi(x) : sinf(x); }
     static __device__ float floorv(float x) { return floorf(x); }
     static __device__ float fmav(float a, float b, float c) { return fmaf(a, b, c); }
@@ -419,6 +423,24 @@ template <typename T> struct Vec;
 template <> struct Vec<double> { static constexpr int N = 2; using type = double2; };
 template <> struct Vec<float> { static constexpr int N = 4; using type = float4; };
 
+// cos of the N plaquettes of a vector with ONE range test for all of them (the dedicated cosine's polynomial path, or -- any
+// |P| beyond its reduction range -- the per-value form with the library): a branch per value put four divergence regions
+// into the issue-bound fp32 scan
+template <typename T, int N>
+__device__ __forceinline__ void cos_vec(const T (&p)[N], T (&v)[N]) {
+    bool ok = FT_FAST_TRIG;
+#pragma unroll
+    for (int j = 0; j < N; ++j) ok = ok && M<T>::cos_in_range(p[j]);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = M<T>::cos_core(p[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = M<T>::cosv(p[j]);
+    }
+}
+
+
 // plaquettes of the N sites (n0, n1 .. n1+N-1): three 16-byte loads and one scalar instead of 4N scalar loads
 template <typename T>
 __device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1, int n0, int n1, int order, T (&p)[Vec<T>::N]) {
@@ -432,6 +454,26 @@ __device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1
     *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0p) * L1 + n1);
 #pragma unroll
     for (int j = 0; j < N; ++j) p[j] = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+}
+
+// acc += f(P_j) over the N plaquettes of a vector (f = cos / regularize / wrap by WHAT); fp32 sums the vector in fp32 first
+template <typename T, int WHAT, int N>
+__device__ __forceinline__ void accumulate_vec(const T (&p)[N], double& acc) {
+    T v[N];
+    if constexpr (WHAT == 0) cos_vec<T, N>(p, v);
+    else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = WHAT == 1 ? regularize_t(p[j]) : wrap_t(p[j]);
+    }
+    if constexpr (sizeof(T) == 4) {
+        T grp = (T)0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) grp += v[j];
+        acc += (double)grp;
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc += (double)v[j];
+    }
 }
 
 // what: 0 = sum cos P (action), 1 = sum regularize(P) (floored charge), 2 = sum wrap(P) (batched charge)
@@ -484,20 +526,17 @@ __global__ void __launch_bounds__(256) k_action_topo(const T* __restrict__ links
                 __align__(16) T t0[N + 1], t1[N], t1p[N];
                 *reinterpret_cast<VT*>(t0) = qa.t0; t0[N] = qa.t0n;
                 *reinterpret_cast<VT*>(t1) = qa.t1; *reinterpret_cast<VT*>(t1p) = qa.t1p;
+                T p[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
-                    acc += what == 0 ? (double)M<T>::cosv(p) : (what == 1 ? (double)regularize_t(p) : (double)wrap_t(p));
-                }
+                for (int j = 0; j < N; ++j) p[j] = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+                accumulate_vec<T, WHAT, N>(p, acc);
                 qa = qb; qb = qc; va = vb; vb = vc;
             }
         } else {
             while (row < nr) {
                 T p[N];
                 plaq_vec<T>(f, L0, L1, r0 + row, col * N, order, p);
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
+                accumulate_vec<T, WHAT, N>(p, acc);
                 col += dc; row += dr;
                 if (col >= W) { col -= W; ++row; }
             }
@@ -550,9 +589,7 @@ __global__ void __launch_bounds__(256) k_action_topo_warp(const T* __restrict__ 
     for (int i = lane; i < nvec; i += 32) {
         T p[N];
         plaq_vec<T>(f, L0, L1, row, col * N, order, p);
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-            acc += what == 0 ? (double)M<T>::cosv(p[j]) : (what == 1 ? (double)regularize_t(p[j]) : (double)wrap_t(p[j]));
+        accumulate_vec<T, WHAT, N>(p, acc);
         col += dc; row += dr;
         if (col >= W) { col -= W; ++row; }
     }
@@ -645,14 +682,10 @@ __global__ void __launch_bounds__(256, FT_TMA_MINB) k_action_topo_tma(const T* _
                 t0[N] = f[o0n[it]];
                 *reinterpret_cast<VT*>(t1) = *reinterpret_cast<const VT*>(f + o1[it]);
                 *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + o1p[it]);
-                T grp = (T)0;                                // (fp32: the four sites of a vector are summed in fp32, ONE conversion and fp64 add per vector)
+                T pp[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const T p = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
-                    const T v = what == 0 ? M<T>::cosv(p) : (what == 1 ? regularize_t(p) : wrap_t(p));
-                    if constexpr (sizeof(T) == 4) grp += v; else acc += (double)v;
-                }
-                if constexpr (sizeof(T) == 4) acc += (double)grp;
+                for (int j = 0; j < N; ++j) pp[j] = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+                accumulate_vec<T, WHAT, N>(pp, acc);
             }
         }
 #pragma unroll
