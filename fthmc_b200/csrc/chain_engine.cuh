@@ -256,8 +256,9 @@ FT_HD double cos_core(double x) {
 #endif
 // sin for the Wilson force (k_force, the plain-HMC leapfrog): 18 fp64 operations; absolute error ~2e-16, relative accuracy
 // next to the zeros at multiples of pi as well (the result is r (1 + ...) there).
-FT_HD double sin_fast(double x) {
-    if (!(fabs(x) < 524288.0)) return sin(x);
+FT_HD double sin_core(double x);
+FT_HD double sin_fast(double x) { return fabs(x) < 524288.0 ? sin_core(x) : sin(x); }
+FT_HD double sin_core(double x) {                                              // the polynomial path alone, |x| < 2^19
 #ifdef __CUDA_ARCH__
     const double* K = c_cospi; const double* S = c_sinpi;
 #else

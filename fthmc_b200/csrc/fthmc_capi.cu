@@ -334,6 +334,7 @@ template <typename T> struct M;
 template <> struct M<double> {
     static __device__ double cosv(double x) { return FT_FAST_TRIG ? fthmc::cos_fast(x) : cos(x); }
     static __device__ double cos_core(double x) { return fthmc::cos_core(x); }
+    static __device__ double sin_core(double x) { return FT_FAST_SIN ? fthmc::sin_core(x) : sin(x); }
     static __device__ bool cos_in_range(double x) { return fabs(x) < 524288.0; }
     static __device__ double sinv(double x) { return fthmc::sin_force(x); }
     static __device__ double floorv(double x) { return floor(x); }
@@ -356,8 +357,7 @@ static __device__ __forceinline__ float cosf_pi_core(float x) {
 }
 static __device__ __forceinline__ float cosf_pi(float x) { return fabsf(x) < 32768.0f ? cosf_pi_core(x) : cosf(x); }
 // sinf for the fp32 force: the same reduction, sin x = (-1)^n sin r, odd Taylor polynomial to r^11 (truncation 6e-8 at pi/2)
-static __device__ __forceinline__ float sinf_pi(float x) {
-    if (!(fabsf(x) < 32768.0f)) return sinf(x);
+static __device__ __forceinline__ float sinf_pi_core(float x) {
     const float t = fmaf(x, 0.318309886f, 12582912.0f);
     const float n = t - 12582912.0f;
     float r = fmaf(n, -3.14159274101257324f, x);
@@ -368,9 +368,11 @@ static __device__ __forceinline__ float sinf_pi(float x) {
     p = fmaf(r * s, p, r);
     return __int_as_float(__float_as_int(p) ^ (__float_as_int(t) << 31));
 }
+static __device__ __forceinline__ float sinf_pi(float x) { return fabsf(x) < 32768.0f ? sinf_pi_core(x) : sinf(x); }
 template <> struct M<float> {
     static __device__ float cosv(float x) { return FT_FAST_TRIG ? cosf_pi(x) : cosf(x); }
     static __device__ float cos_core(float x) { return cosf_pi_core(x); }
+    static __device__ float sin_core(float x) { return sinf_pi_core(x); }
     static __device__ bool cos_in_range(float x) { return fabsf(x) < 32768.0f; }
     static __device__ float sinv(float x) { return FT_FAST_TRIG ? sinf_pi(x) : sinf(x); }
     static __device__ float floorv(float x) { return floorf(x); }
@@ -454,6 +456,20 @@ __device__ __forceinline__ void plaq_vec(const T* __restrict__ f, int L0, int L1
     *reinterpret_cast<VT*>(t1p) = *reinterpret_cast<const VT*>(f + (size_t)(L0 + n0p) * L1 + n1);
 #pragma unroll
     for (int j = 0; j < N; ++j) p[j] = order == 0 ? ((t0[j] + t1p[j]) - t0[j + 1]) - t1[j] : ((t0[j] - t1[j]) - t0[j + 1]) + t1p[j];
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void sin_vec(T (&p)[N]) {                      // in place, one range test per vector (as cos_vec)
+    bool ok = FT_FAST_TRIG;
+#pragma unroll
+    for (int j = 0; j < N; ++j) ok = ok && M<T>::cos_in_range(p[j]);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = M<T>::sin_core(p[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p[j] = M<T>::sinv(p[j]);
+    }
 }
 
 // acc += f(P_j) over the N plaquettes of a vector (f = cos / regularize / wrap by WHAT); fp32 sums the vector in fp32 first
@@ -725,8 +741,7 @@ __global__ void __launch_bounds__(256) k_force(const T* __restrict__ links, int 
             int n0 = r0 - 1 + row; if (n0 < 0) n0 += L0;
             __align__(16) T p[N];
             plaq_vec<T>(f, L0, L1, n0, col * N, order, p);
-#pragma unroll
-            for (int j = 0; j < N; ++j) p[j] = M<T>::sinv(p[j]);
+            sin_vec<T, N>(p);
             *reinterpret_cast<VT*>(S + row * L1 + col * N) = *reinterpret_cast<const VT*>(p);
             col += dc; row += dr;
             if (col >= W) { col -= W; ++row; }
@@ -783,8 +798,7 @@ __global__ void __launch_bounds__(256) k_force_tiled(const T* __restrict__ links
             int n0 = r0 - 1 + row; if (n0 < 0) n0 += L0;
             __align__(16) T p[N];
             plaq_vec<T>(f, L0, L1, n0, c0 + col * N, order, p);
-#pragma unroll
-            for (int j = 0; j < N; ++j) p[j] = M<T>::sinv(p[j]);
+            sin_vec<T, N>(p);
             *reinterpret_cast<VT*>(S + row * SP + N + col * N) = *reinterpret_cast<const VT*>(p);
             col += dc; row += dr;
             if (col >= W) { col -= W; ++row; }
