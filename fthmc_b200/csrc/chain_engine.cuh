@@ -2483,12 +2483,29 @@ FT_HD void plain_md_steps(Engine<E>& en, double beta, double dt, int nstep) {
     }
     for (int st = 0; st < nstep; ++st) {
         const double step = st == nstep - 1 ? hdt : dt;
+        // the plaquettes of the thread's sites, ONE range test for all of them, then NS independent sine chains (a branch per
+        // site put NS convergence regions in the step and serialised the chains)
+        double pl[NS];
+        bool inr = FT_FAST_SIN != 0;
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
+        for (int k = 0; k < NS; ++k) {
+            pl[k] = 0.0;
             if (ok[k]) {
                 const double a = X[xb[k]], b = X[X1 + xb[k] + dr[k]], c = X[xb[k] + dc[k]], d = X[X1 + xb[k]];
-                S[sb[k]] = sin_force(((a - d) - c) + b);
+                pl[k] = ((a - d) - c) + b;
             }
+            inr = inr && fabs(pl[k]) < 524288.0;
+        }
+        if (inr) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) pl[k] = sin_core(pl[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) pl[k] = sin_force(pl[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (ok[k]) S[sb[k]] = pl[k];
         ex.sync();
 #pragma unroll
         for (int k = 0; k < NS; ++k)
