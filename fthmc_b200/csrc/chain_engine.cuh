@@ -121,8 +121,8 @@ FT_HD double rem_2pi(double x) {
 }
 // torch_mod: convention 0 -> [0,2pi) (ipynb/field_transformation.py:17-18); 1 -> remainder(x+pi,2pi)-pi
 FT_HD double mod_2pi(double x, int conv) {
-    if (conv == 0) return rem_2pi(x);
-    return rem_2pi(x + PI_D) - PI_D;
+    const double sh = conv == 0 ? 0.0 : PI_D;            // (a select, not a branch; x + 0.0 and r - 0.0 are exact)
+    return rem_2pi(x + sh) - sh;
 }
 
 // hmc_2dU1.py:127-129
@@ -294,8 +294,14 @@ FT_HD double sin_force(double x) { return FT_FAST_SIN ? sin_fast(x) : sin(x); }
 #ifdef __CUDACC__
 __constant__ double c_cosk[6] = FT_COS_CONSTS;
 #endif
+// RANGE_OK: the caller has tested |x| < 2^19 itself.  The per-site phases of the engine test ONCE per site and run the whole
+// site's arithmetic in one branch-free block (site_fast / site_slow below): a range test inside this function splits the
+// block, and the scheduler does not interleave the sine / cosine chain with the exponential chains around it across the split.
+struct TrigFast { static constexpr bool value = true; };
+struct TrigChecked { static constexpr bool value = false; };
+template <bool RANGE_OK = false>
 FT_HD void sincos_fast(double x, double& sn, double& cs) {
-    if (!(fabs(x) < 524288.0)) { sn = sin(x); cs = cos(x); return; }
+    if (!RANGE_OK) { if (!(fabs(x) < 524288.0)) { sn = sin(x); cs = cos(x); return; } }
 #ifdef __CUDA_ARCH__
     const double* K = c_trig; const double* C = c_cosk;
 #else
@@ -387,12 +393,10 @@ FT_HD double atan2x2_fast(double y, double x) {
 }
 // torch_mod of a value already within [-2pi, 2pi]
 FT_HD double mod_2pi_near(double g, int conv) {
-    if (conv == 0) {
-        double r = g < 0.0 ? g + TWO_PI_D : g;
-        return r >= TWO_PI_D ? r - TWO_PI_D : r;
-    }
-    double r = g < -PI_D ? g + TWO_PI_D : g;
-    return r >= PI_D ? r - TWO_PI_D : r;
+    // (selects, no branch on the convention: a branch splits the branch-free site blocks of the phases that call this)
+    const double lo = conv == 0 ? 0.0 : -PI_D, hi = conv == 0 ? TWO_PI_D : PI_D;
+    const double r = g < lo ? g + TWO_PI_D : g;
+    return r >= hi ? r - TWO_PI_D : r;
 }
 
 // 1/d for d >= 1 (one cubic Newton step on the hardware seed: three DFMA); host: plain division
@@ -895,15 +899,14 @@ struct Engine {
         for (int t = ex.tid(); t < T; t += ex.nt()) {
             int gi = t / g.R, r = t - gi * g.R;
             UA[t] = plaq_canon(g, r, 4 * gi, order);
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-                double p = plaq_canon(g, r, 4 * gi + 1 + k, order);
-                double sp, cp;
-                sincos_fast(p, sp, cp);
-                const int i = (2 * gi + k) * g.R + r;
-                CS[i] = cp; CS[V / 2 + i] = sp;
-                if (cs_save) { cs_save[i] = cp; cs_save[V / 2 + i] = sp; }
-            }
+            // the two frozen plaquettes of the row: one range test, then both sine / cosine chains in one branch-free block
+            const double p0 = plaq_canon(g, r, 4 * gi + 1, order), p1 = plaq_canon(g, r, 4 * gi + 2, order);
+            double sp0, cp0, sp1, cp1;
+            if (fabs(p0) < 524288.0 && fabs(p1) < 524288.0) { sincos_fast<true>(p0, sp0, cp0); sincos_fast<true>(p1, sp1, cp1); }
+            else { sincos_fast(p0, sp0, cp0); sincos_fast(p1, sp1, cp1); }
+            const int i = 2 * gi * g.R + r, j = i + g.R;
+            CS[i] = cp0; CS[V / 2 + i] = sp0; CS[j] = cp1; CS[V / 2 + j] = sp1;
+            if (cs_save) { cs_save[i] = cp0; cs_save[V / 2 + i] = sp0; cs_save[j] = cp1; cs_save[V / 2 + j] = sp1; }
         }
     }
 
@@ -1372,15 +1375,16 @@ struct Engine {
         // one site per thread: everything below is branch-free (exp_fast, sincos_fast, atan2x2_fast), so the independent
         // chains of a site -- two exponentials and the half-angle sine/cosine, then the two arctangents -- interleave
         for (int t = ex.tid(); t < T; t += ex.nt()) {
+          const double u = UA[t];
+          auto site_body = [&](auto trig) {
             int gi = t / R, r = t - gi * R;
             const double out[NOUT] = { OUT[t], OUT[T + t], OUT[2 * T + t] };
-            const double u = UA[t];
             int n0, n1; site(g, r, 4 * gi, n0, n1);
             double* xl = xat(oX, g.mu, n0, n1);
             const double xo = *xl;                            // (cluster mode: possibly a remote load -- in flight under the arithmetic)
             const double es0 = exp_fast(out[0]), es1 = exp_fast(out[1]);
             double sh, ch;
-            sincos_fast(0.5 * u, sh, ch);
+            sincos_fast<decltype(trig)::value>(0.5 * u, sh, ch);
             const double fx1 = mixture_fwd_sc(sh, ch, es0, es1, conv);
             const double newp = mod_2pi(fx1 + out[2], conv);
             const double delta = newp - u;
@@ -1396,6 +1400,8 @@ struct Engine {
                 double m = l0 > l1 ? l0 : l1;
                 lj += (m + log(exp(l0 - m) + exp(l1 - m))) - 0.6931471805599453;
             }
+          };
+          if (fabs(u) < 1048576.0) site_body(TrigFast{}); else site_body(TrigChecked{});   // (|u / 2| < 2^19: one test per site)
         }
         return lj;
     }
@@ -1599,13 +1605,14 @@ struct Engine {
             int gi = t / R, r = t - gi * R, n0, n1;
             site(g, r, 4 * gi, n0, n1);
             *xat(oX, g.mu, n0, n1) = OUT[2 * T + t];
-            double gl = *xat(oGR, g.mu, n0, n1);
-            double db = g.mu == 0 ? gl : -gl;                 // delta-bar
             double u;
             if constexpr (SAVED) u = ua[t]; else u = plaq(oX, n0, n1, order);
+          auto site_body = [&](auto trig) {                   // (one branch-free block per site, see sincos_fast)
+            double gl = *xat(oGR, g.mu, n0, n1);
+            double db = g.mu == 0 ? gl : -gl;                 // delta-bar
             double s0 = OUT[t], s1 = OUT[T + t];
             double c, s;
-            sincos_fast(0.5 * u, s, c);
+            sincos_fast<decltype(trig)::value>(0.5 * u, s, c);
             const double su = 2.0 * s * c;                                                  // sin u
             double c2 = c * c, s2 = s * s;
             double ep0 = exp_fast(s0), em0 = exp_fast(-s0), ep1 = exp_fast(s1), em1 = exp_fast(-s1);
@@ -1619,6 +1626,8 @@ struct Engine {
             double sb1 = db * su * e1 * 0.5 - mwl * (sg1 * (em1 * c2 - ep1 * s2) * e1);
             OUT[t] = sb0; OUT[T + t] = sb1; OUT[2 * T + t] = db;
             UA[t] = ub;
+          };
+          if (fabs(u) < 1048576.0) site_body(TrigFast{}); else site_body(TrigChecked{});
         }
     }
 
