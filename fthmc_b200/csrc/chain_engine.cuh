@@ -420,6 +420,9 @@ FT_HD double rcp_ge1(double d) {
 #ifndef FT_CL_PLANES
 #define FT_CL_PLANES 1
 #endif
+#ifndef FT_C3_UNROLL
+#define FT_C3_UNROLL 8
+#endif
 #ifndef FT_CL_SAVED_U
 #define FT_CL_SAVED_U 1
 #endif
@@ -1327,7 +1330,8 @@ struct Engine {
         double o0[3][3], o1[3][3];                           // [kernel row a][output]: site r, site r+1
 #pragma unroll
         for (int a = 0; a < 3; ++a) { o0[a][0] = o0[a][1] = o0[a][2] = 0.0; o1[a][0] = o1[a][1] = o1[a][2] = 0.0; }
-#pragma unroll 2
+        constexpr int C3U = FT_C3_UNROLL;
+#pragma unroll C3U
         for (int ci = 0; ci < NH; ++ci) {
             const double* Bp = B + ci * sB + 3 * gi * R;
 #pragma unroll
@@ -1466,7 +1470,7 @@ struct Engine {
             for (int k = 0; k < 12; ++k) {
                 // f through the half-angle sine / cosine (mixture_fwd_sc), f' = mean_k e^s_k / (cos^2 + e^2s_k sin^2) from the same pair
                 double sh, ch;
-                sincos_fast(0.5 * x, sh, ch);
+                sincos_fast<true>(0.5 * x, sh, ch);                   // (x lies inside the bisection interval: always in range)
                 const double fx = mixture_fwd_sc(sh, ch, es0, es1, conv), r = fx - y;
                 const double c2 = ch * ch, s2 = sh * sh;
                 const double n0 = fma(es0 * es0, s2, c2), n1 = fma(es1 * es1, s2, c2);
